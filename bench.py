@@ -1,0 +1,244 @@
+#!/usr/bin/env python
+"""bench.py -- poses/s of the SAM-6D pose-estimation matching path on B200 (BASELINE.json config #2).
+
+A step = one pass of the hot path (Net.forward after the RGB backbone: FPS, geometric embedding, coarse and fine
+sparse-to-dense point matching, pose solvers) over one batch of 32 synthetic proposals x 2048 scene points x 2048 template
+points, 256-d features, 1024 CAD samples.  Under torchrun every rank runs the same per-GPU batch (weak scaling, proposals
+sharded, no data-path collective) and the step ends with the one all-gather of final poses.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm
+  python bench.py --impl reference ...                          the reference algorithm on the host cores (oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "pem_matching_32x2048x2048"
+B_PER_GPU, N_PTS, N_MODEL, C_FEAT = 32, 2048, 1024, 256
+METRIC, UNIT = "poses/sec", "poses/s"
+CPU_SAMPLE_B = 4
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unsampled"])
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                    reasons=reasons, samples=len(self.samples))
+
+
+def cpu_oracle_throughput(reps: int, threads: int):
+    """the reference algorithm (oracle port, torch fp32 on the host) on a bounded sample of the workload"""
+    from oracle import pem_oracle as po
+    torch.set_num_threads(threads)
+    sd = po.make_state_dict(seed=1)
+    inp = po.make_inputs(B=CPU_SAMPLE_B, n=N_PTS, n_model=N_MODEL, seed=1)
+    torch.manual_seed(1)
+    rand = torch.rand(CPU_SAMPLE_B, po.N_PROPOSAL1 * 3)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        po.pem_forward(sd, inp["pts"], inp["dense_fm"], inp["dense_po"], inp["dense_fo"], inp["model"], rand=rand)
+        times.append(time.perf_counter() - t0)
+    return CPU_SAMPLE_B / (sum(times) / len(times)), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_oracle_throughput(1, threads)
+    t0 = time.perf_counter()
+    val, times = cpu_oracle_throughput(max(1, args.steps), threads)
+    ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
+    sample = f"{CPU_SAMPLE_B} proposals x {N_PTS} pts per step (of the {B_PER_GPU}-proposal batch), fp32, torch CPU"
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, proposals_per_step=CPU_SAMPLE_B, scene_points=N_PTS, template_points=N_PTS,
+                            note="reference algorithm restated on the host (oracle port; the Python reference cannot travel)"),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    from oracle import pem_oracle as po           # synthetic inputs + seeded weights only (generator, not a compute path)
+    from sam6d_b200 import _lib, dist as sdist
+    from sam6d_b200.pem import Net
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU: sam6d_b200 has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+
+    net = Net().to(dev).eval()
+    net.load_state_dict(po.make_state_dict(seed=1), strict=True)
+    keys = ("pts", "dense_fm", "dense_po", "dense_fo", "model")
+    host = [{k: v.pin_memory() for k, v in po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=100 + rank * 7 + s).items()
+             if k in keys} for s in range(2)]
+    resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+
+    def step_resident(i):
+        ep = dict(resident[i % 2])
+        rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev, generator=gen)
+        out = net(ep, rand=rand)
+        poses = sdist.pack_poses(out)
+        return sdist.all_gather_poses(poses)
+
+    host_out = torch.empty(world * B, sdist.POSE_FLOATS).pin_memory()
+
+    def step_e2e(i):
+        ep = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev, generator=gen)
+        out = net(ep, rand=rand)
+        poses = sdist.all_gather_poses(sdist.pack_poses(out))
+        host_out.copy_(poses, non_blocking=True)
+        return poses
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile_kernel=None):
+        barrier()
+        if profile_kernel:
+            _lib.time_kernel(profile_kernel, True)
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        kernel_ms = None
+        if profile_kernel:
+            ev = _lib.timed_events(profile_kernel)
+            kernel_ms = [a.elapsed_time(b) for a, b in ev]
+            _lib.time_kernel(profile_kernel, False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, kernel_ms
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, launches, _ = timed(step_resident, args.steps)
+    # dominant-kernel roofline: same steps again with CUDA events around every rpe_scores launch
+    _, _, kms = timed(step_resident, args.steps, profile_kernel="sam6d_rpe_scores")
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    if rank == 0:
+        pk = peaks()
+        S = net.coarse_npoint + 1
+        e_bytes = B * S * S * 256 * 4                  # fp32 geometric embedding streamed once per launch
+        alg_bytes = e_bytes + B * S * 1024 * 4 + B * 4 * S * S * 4
+        k_avg_ms = sum(kms) / len(kms)
+        achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+        value = world * B * args.steps / (ms * 1e-3)
+        e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "rpe_scores_traffic.json")
+        if os.path.exists(prof):
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload=WORKLOAD, proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
+                        feat_dim=C_FEAT, model_points=N_MODEL, parallelism=f"proposal-sharded x{world}, 1 all-gather of poses",
+                        cache="inputs+intermediates per step (>1 GB) exceed the 126 MB L2; two input sets alternate"),
+            e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=world * B * sdist.POSE_FLOATS * 4,
+                     ms_per_step=ms_e2e / args.steps),
+            gpu_launches=launches,
+            roofline=dict(kernel="rpe_scores_kernel<float> (PEM RPE attention, streams the geometric embedding)", bound="hbm",
+                          achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
+                          peak_source=pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if pk["source"] == "measured" else "fallback 6650 GB/s",
+                          algorithmic_bytes_per_launch=alg_bytes, launches_timed=len(kms), avg_launch_ms=k_avg_ms,
+                          share_of_step=sum(kms) / ms),
+            clocks=sampler.summary() if sampler else None,
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cpu_oracle_throughput(1, threads)
+            val, times = cpu_oracle_throughput(2, threads)
+            line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=threads, kind="port",
+                                        sample=f"{CPU_SAMPLE_B} of the {B} proposals, 2 timed passes after 1 warm-up, "
+                                               f"{sum(times):.1f} s of CPU work, torch fp32 on {threads} threads")
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

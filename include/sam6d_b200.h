@@ -1,0 +1,133 @@
+/*
+ * sam6d_b200.h -- C ABI of libsam6d_b200.so: the B200 (sm_100a) kernels behind SAM-6D's data-parallel hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (the Python host passes torch storage);
+ *     nothing is allocated, freed or synchronised inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous;
+ *   - return value: 0 on success, a positive cudaError_t if a launch / runtime call failed, -22 (EINVAL) if an
+ *     argument violates the documented contract.  The library never calls exit() (the reference's native layer
+ *     does: PEM/model/pointnet2/_ext_src/include/cuda_utils.h:35-44);
+ *   - tensors are dense row-major fp32 unless stated; index tensors are int32 (as in the reference's _ext).
+ *
+ * Reference paths: PEM = SAM-6D/Pose_Estimation_Model, ISM = SAM-6D/Instance_Segmentation_Model,
+ *                  PN2 = PEM/model/pointnet2.
+ */
+#ifndef SAM6D_B200_H
+#define SAM6D_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- point-cloud ops: replace the pybind module pointnet2._ext (PN2/_ext_src/src/bindings.cpp:11-24) ---------- */
+
+/* _ext.furthest_point_sampling (PN2/_ext_src/src/sampling.cpp:67-91, sampling_gpu.cu:75-178).
+ * xyz (b,n,3) -> idx (b,m); idx[:,0] = 0; ties resolved exactly like the reference kernel.
+ * temp: scratch (b,n) f32, required only when n > 4096. */
+int sam6d_fps(const float* xyz, int b, int n, int m, float* temp, int* idx, void* stream);
+
+/* _ext.gather_points (PN2/_ext_src/src/sampling.cpp:18-41, sampling_gpu.cu:13-25): points (b,c,n), idx (b,m) -> (b,c,m) */
+int sam6d_gather_points(const float* points, const int* idx, int b, int c, int n, int m, float* out, void* stream);
+
+/* channel-last form used inside the model: out[b,j,:] = src[b, idx[b,j], :], src batch stride in elements
+ * (sample_pts_feats PEM/utils/model_utils.py:53-66; SparseToDenseTransformer._sample_feats PEM/model/transformer.py:651-658) */
+int sam6d_gather_rows(const float* src, const int* idx, int b, int n, int m, int c, long long src_bstride, float* out,
+                      void* stream);
+
+/* _ext.ball_query (PN2/_ext_src/src/ball_query.cpp:11-35, ball_query_gpu.cu:14-49): new_xyz (b,m,3), xyz (b,n,3)
+ * -> idx (b,m,nsample): first nsample hits with d2 < r*r in ascending index order, padded with the first hit,
+ * all zero when empty.  cnt (b,m), optional: number of distinct hits kept. */
+int sam6d_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius, int nsample, int* idx,
+                     int* cnt, void* stream);
+
+/* _ext.group_points (PN2/_ext_src/src/group_points.cpp:13-38, group_points_gpu.cu:13-33): points (b,c,n), idx (b,np,ns) -> (b,c,np,ns) */
+int sam6d_group_points(const float* points, const int* idx, int b, int c, int n, int np, int ns, float* out, void* stream);
+
+/* ---- dense linear algebra ------------------------------------------------------------------------------------ */
+
+/* C[z] = alpha * A[z] W[z]^T (+ bias) (ReLU) (+ R[z]) for z < batch.  A (M,K) lda; W (N,K) ldw (nn.Linear layout);
+ * C (M,N) ldc; R (M,N) ldr or NULL; sA..sR batch strides in elements (0 = shared).  fp32 CUDA-core path
+ * (every nn.Linear / 1x1 conv of PEM/model/transformer.py, coarse/fine_point_matching.py; the score matrix
+ * compute_feature_similarity PEM/utils/model_utils.py:114-136 as a batched call with alpha = 1/temp). */
+int sam6d_gemm_f32(const float* A, const float* W, const float* bias, const float* R, float* C, int M, int N, int K,
+                   long long lda, long long ldw, long long ldc, long long ldr, int batch, long long sA, long long sW,
+                   long long sC, long long sR, float alpha, int relu, void* stream);
+
+/* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
+
+/* nn.LayerNorm(C) (PEM/model/transformer.py:156,188,423,572) */
+int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                    long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                    float eps, void* stream);
+/* F.normalize(x, p=2, dim=-1) (PEM/utils/model_utils.py:124-126; ISM/model/loss.py:32-33) */
+int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                      long long y_bstride, long long y_ld, long long rows, int C, void* stream);
+/* focused-linear-attention feature map (PEM/model/transformer.py:541-550); softplus_scale (C) = softplus(scale) */
+int sam6d_focus_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                     long long y_bstride, long long y_ld, const float* softplus_scale, long long rows, int C, void* stream);
+/* out = (p - t) @ R per proposal (PEM/model/fine_point_matching.py:44) */
+int sam6d_rigid_warp(const float* p, const float* R, const float* t, int b, int n, float* out, void* stream);
+/* radius[b] = max_i ||po[b,i]|| and x / (radius + 1e-6) (PEM/model/feature_extraction.py:139-142) */
+int sam6d_cloud_radius(const float* po, int b, int n, float* radius, void* stream);
+int sam6d_scale_by_radius(const float* src, const float* radius, int b, long long per_batch, float* dst, void* stream);
+
+/* ---- geometric structure embedding (PEM/model/transformer.py:286-349) -------------------------------------------- */
+
+/* pts (b,S,3) -> T (b,S,S,4) = {angle index k=0..2, distance index} (get_embedding_indices, :302-332) */
+int sam6d_geo_indices(const float* pts, int b, int S, float sigma_d, float factor_a, float* T, void* stream);
+/* T (npairs,4) -> E (npairs,256) = proj_d(sin_emb(d)) + max_k proj_a(sin_emb(a_k)) (forward, :334-349); WaT/WdT are
+ * (in,out) transposes of the nn.Linear weights, bias = proj_a.bias + proj_d.bias, div_term the module buffer. */
+int sam6d_geo_embed_f32(const float* T, long long npairs, const float* div_term, const float* WaT, const float* WdT,
+                        const float* bias, float* E, void* stream);
+
+/* ---- attention ---------------------------------------------------------------------------------------------------- */
+
+/* relative-position score term of RPEMultiHeadAttention (PEM/model/transformer.py:389-394) with proj_p folded into
+ * the query: E (B,S,S,256) f32 or bf16, U (B*S rows of 4x256, row stride u_ld) = W_p,h^T q_h  ->  SP (B,4,S,S) */
+int sam6d_rpe_scores(const void* E, int e_is_bf16, const float* U, long long u_ld, int B, int S, float* SP, void* stream);
+/* softmax((Q K^T + bias) * scale) V, head dim 64, Sk <= 256 (MultiHeadAttention :109-148, RPEMultiHeadAttention :369-406) */
+int sam6d_mha(const float* Q, long long q_ld, long long q_bs, const float* K, long long k_ld, long long k_bs, const float* V,
+              long long v_ld, long long v_bs, const float* bias, int B, int H, int Sq, int Sk, float scale, float* O,
+              long long o_ld, long long o_bs, void* stream);
+/* LinearAttention kv-first branch (PEM/model/transformer.py:552-559) */
+int sam6d_linattn_kv(const float* Kf, long long k_ld, long long k_bs, const float* V, long long v_ld, long long v_bs, int B,
+                     int H, int J, float* KV, float* KS, void* stream);
+int sam6d_linattn_apply(const float* Qf, long long q_rpb, long long q_bs, long long q_ld, const float* KV, const float* KS,
+                        int B, int H, float* X, long long x_bs, long long x_ld, void* stream);
+
+/* ---- coarse pose (compute_coarse_Rt, PEM/utils/model_utils.py:187-246) -------------------------------------------- */
+int sam6d_coarse_assign(const float* A, int B, int S, float* W, float* w1, void* stream);
+int sam6d_coarse_sample(const float* W, int B, int L, const float* rand, int nr, int* idx, void* stream);
+int sam6d_coarse_hypotheses(const int* idx, const float* pts1, const float* pts2, int B, int n, int n1, float* Rt,
+                            float* resid, void* stream);
+int sam6d_topk_smallest(const float* v, int B, int n, int k, int* out, void* stream);
+int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, int n2, const float* pts1, const float* w1, int n,
+                        const float* model, int nm, float* scores, float* R, float* t, void* stream);
+
+/* ---- fine stage ---------------------------------------------------------------------------------------------------- */
+
+/* fused QueryAndGroup + SharedMLP[6,32,64,128] (BN folded) + max-pool (PEM/model/fine_point_matching.py:101-121) */
+int sam6d_pe_mlp_max(const float* pts, const int* idx, const int* cnt, int B, int N, int ns, const float* W1,
+                     const float* B1, const float* W2, const float* B2, const float* W3, const float* B3, float* out,
+                     int out_ld, int out_off, void* stream);
+/* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls */
+int sam6d_fine_assign(const float* A, int B, int S, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
+                      int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream);
+int sam6d_weighted_procrustes(const float* src, const float* ref, const float* wts, int B, int N, float weight_thresh,
+                              float eps, float* R, float* t, void* stream);
+int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const float* R, const float* t, const float* model,
+                     int nm, float dis_thres, const float* radius, float* score, float* t_scaled, void* stream);
+
+/* ---- ISM template scoring (ISM/model/loss.py:21-44, ISM/model/detector.py:198-207,260-296) ------------------------ */
+int sam6d_template_score(const float* Qn, const float* Rn, int P, int O, int T, int C, float* sim_out, float* obj_score,
+                         int* best_obj, float* best_score, int* best_tmpl, void* stream);
+
+/* ---- library info ------------------------------------------------------------------------------------------------- */
+/* "sam6d_b200 <version> sm_100a" */
+const char* sam6d_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAM6D_B200_H */

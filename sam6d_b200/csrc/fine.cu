@@ -1,0 +1,284 @@
+// fine.cu -- soft assignment on the dense (N+1)x(M+1) score matrix and the final weighted-SVD pose
+// (compute_fine_Rt, PEM/utils/model_utils.py:250-283).
+//
+// A = F1 F2^T / temp with L2-normalised features, so |A| <= 1/temp and softmax can use the fixed shift
+// `shift` = 1/temp instead of a per-row/column maximum: e_ij = exp(A_ij - shift),
+//   P_ij = (e_ij / sum_j e_ij) * (e_ij / sum_i e_ij).
+// Three streaming passes over A (row/col sums; row/col argmax of P; masked weighted sums), then a per-proposal
+// weighted Procrustes and the inlier score against the CAD samples.
+#include "common.cuh"
+#include "svd3.cuh"
+
+namespace {
+
+constexpr int RT = 32;  // rows per tile in the column-reducing passes
+
+// pass 1: rsum (B,S); column partial sums cpart (B,tiles,S)
+__global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict__ A, int S, float shift, float* __restrict__ rsum,
+                                                        float* __restrict__ cpart) {
+  __shared__ float racc[RT];
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int i0 = tile * RT;
+  if (tid < RT) racc[tid] = 0.f;
+  __syncthreads();
+  const float* Ab = A + (size_t)b * S * S;
+  for (int j0 = 0; j0 < S; j0 += 256) {
+    const int j = j0 + tid;
+    float cacc = 0.f;
+    for (int r = 0; r < RT; ++r) {
+      const int i = i0 + r;
+      if (i >= S) break;
+      float e = (j < S) ? __expf(Ab[(size_t)i * S + j] - shift) : 0.f;
+      cacc += e;
+      float rs = warp_sum(e);
+      if (lane == 0) atomicAdd(&racc[r], rs);
+    }
+    if (j < S) cpart[((size_t)b * gridDim.x + tile) * S + j] = cacc;
+  }
+  __syncthreads();
+  if (tid < RT && i0 + tid < S) rsum[(size_t)b * S + i0 + tid] = racc[tid];
+}
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ cpart, int tiles, int S, float* __restrict__ csum) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= S) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += cpart[((size_t)b * tiles + t) * S + j];
+  csum[(size_t)b * S + j] = s;
+}
+
+// pass 2: lab1[b,i] = argmax_j P_ij (first max); per-tile column argmax partials
+__global__ void __launch_bounds__(256) fine_labels_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
+                                                          const float* __restrict__ csum, int* __restrict__ lab1,
+                                                          float* __restrict__ cpv, int* __restrict__ cpi) {
+  __shared__ float rv[RT][8];
+  __shared__ int ri[RT][8];
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = tile * RT;
+  const float* Ab = A + (size_t)b * S * S;
+  float rbv[RT];
+  int rbi[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) { rbv[r] = -INFINITY; rbi[r] = 0x7fffffff; }
+  for (int j0 = 0; j0 < S; j0 += 256) {
+    const int j = j0 + tid;
+    const float cs = (j < S) ? csum[(size_t)b * S + j] : 1.f;
+    float cbv = -INFINITY;
+    int cbi = 0;
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      const int i = i0 + r;
+      if (i < S && j < S) {
+        float e = __expf(Ab[(size_t)i * S + j] - shift);
+        float p = (e / rsum[(size_t)b * S + i]) * (e / cs);
+        if (p > cbv) { cbv = p; cbi = i; }                     // ascending i: first max wins
+        if (p > rbv[r]) { rbv[r] = p; rbi[r] = j; }            // ascending j within this thread
+      }
+    }
+    if (j < S) { cpv[((size_t)b * gridDim.x + tile) * S + j] = cbv; cpi[((size_t)b * gridDim.x + tile) * S + j] = cbi; }
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    float v = rbv[r]; int ix = rbi[r];
+    warp_argmax_first(v, ix);
+    if (lane == 0) { rv[r][warp] = v; ri[r][warp] = ix; }
+  }
+  __syncthreads();
+  if (tid < RT && i0 + tid < S) {
+    float v = rv[tid][0]; int ix = ri[tid][0];
+    for (int w = 1; w < 8; ++w) argmax_first(v, ix, rv[tid][w], ri[tid][w]);
+    lab1[(size_t)b * S + i0 + tid] = ix;
+  }
+}
+
+__global__ void collab_reduce_kernel(const float* __restrict__ cpv, const int* __restrict__ cpi, int tiles, int S,
+                                     int* __restrict__ lab2) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= S) return;
+  float bv = -INFINITY; int bi = 0;
+  for (int t = 0; t < tiles; ++t) {
+    float v = cpv[((size_t)b * tiles + t) * S + j];
+    if (v > bv) { bv = v; bi = cpi[((size_t)b * tiles + t) * S + j]; }
+  }
+  lab2[(size_t)b * S + j] = bi;
+}
+
+// pass 3: for dense point i (row i+1): w_i = sum_j P'_ij, pred_i = sum_j P'_ij pts2_j / (w_i + 1e-6)
+__global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
+                                                            const float* __restrict__ csum, const int* __restrict__ lab1,
+                                                            const int* __restrict__ lab2, const float* __restrict__ pts2,
+                                                            float* __restrict__ wts, float* __restrict__ pred) {
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);   // dense index 0..N-1
+  const int N = S - 1;
+  if (i >= N) return;
+  float w = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+  if (lab1[(size_t)b * S + i + 1] > 0) {
+    const float* row = A + ((size_t)b * S + i + 1) * S;
+    const float rs = rsum[(size_t)b * S + i + 1];
+    for (int j = 1 + lane; j < S; j += 32) {
+      if (lab2[(size_t)b * S + j] > 0) {
+        float e = __expf(row[j] - shift);
+        float p = (e / rs) * (e / csum[(size_t)b * S + j]);
+        const float* q = pts2 + ((size_t)b * N + (j - 1)) * 3;
+        w += p; px = fmaf(p, q[0], px); py = fmaf(p, q[1], py); pz = fmaf(p, q[2], pz);
+      }
+    }
+    w = warp_sum(w); px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
+  }
+  if (lane == 0) {
+    wts[(size_t)b * N + i] = w;
+    float d = w + 1e-6f;
+    float* o = pred + ((size_t)b * N + i) * 3;
+    o[0] = px / d; o[1] = py / d; o[2] = pz / d;
+  }
+}
+
+// weighted Procrustes (model_utils.py:287-363, weight_thresh 0, eps 1e-5): ref ~= R src + t
+__device__ __forceinline__ double block_sum_d(double v, double* sh) {
+  v = warp_sum_d(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) weighted_procrustes_kernel(const float* __restrict__ src, const float* __restrict__ ref,
+                                                                  const float* __restrict__ wts, int N, float thresh, float eps,
+                                                                  float* __restrict__ R, float* __restrict__ t) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* s = src + (size_t)b * N * 3;
+  const float* r = ref + (size_t)b * N * 3;
+  const float* w = wts + (size_t)b * N;
+  double ws = 0.0;
+  for (int i = tid; i < N; i += 256) { float wi = w[i]; ws += (wi < thresh) ? 0.0 : (double)wi; }
+  const float wsum = (float)block_sum_d(ws, sh) + eps;
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < N; i += 256) {
+    float wi = w[i];
+    wi = (wi < thresh) ? 0.f : wi;
+    float wn = wi / wsum;
+    for (int d = 0; d < 3; ++d) { c[d] += (double)(s[i * 3 + d] * wn); c[3 + d] += (double)(r[i * 3 + d] * wn); }
+  }
+  float cen[6];
+  for (int d = 0; d < 6; ++d) cen[d] = (float)block_sum_d(c[d], sh);
+  double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = tid; i < N; i += 256) {
+    float wi = w[i];
+    wi = (wi < thresh) ? 0.f : wi;
+    float wn = wi / wsum;
+    float sc[3] = {s[i * 3] - cen[0], s[i * 3 + 1] - cen[1], s[i * 3 + 2] - cen[2]};
+    float rc[3] = {wn * (r[i * 3] - cen[3]), wn * (r[i * 3 + 1] - cen[4]), wn * (r[i * 3 + 2] - cen[5])};
+    for (int a = 0; a < 3; ++a)
+      for (int d = 0; d < 3; ++d) h[a * 3 + d] += (double)sc[a] * (double)rc[d];
+  }
+  double H[3][3];
+  for (int a = 0; a < 9; ++a) H[a / 3][a % 3] = block_sum_d(h[a], sh);
+  if (tid == 0) {
+    double Rd[3][3];
+    procrustes_rotation(H, Rd);
+    for (int a = 0; a < 3; ++a) {
+      float Ra[3] = {(float)Rd[a][0], (float)Rd[a][1], (float)Rd[a][2]};
+      for (int d = 0; d < 3; ++d) R[(size_t)b * 9 + a * 3 + d] = Ra[d];
+      t[(size_t)b * 3 + a] = cen[3 + a] - (Ra[0] * cen[0] + Ra[1] * cen[1] + Ra[2] * cen[2]);
+    }
+  }
+}
+
+// pose score (model_utils.py:275-281) and rescaled translation (fine_point_matching.py:80)
+__global__ void __launch_bounds__(1024) pose_score_kernel(const float* __restrict__ pts1, const int* __restrict__ lab1, int S,
+                                                          const float* __restrict__ R, const float* __restrict__ t,
+                                                          const float* __restrict__ model, int nm, float dis_thres,
+                                                          const float* __restrict__ radius, float* __restrict__ score,
+                                                          float* __restrict__ t_scaled) {
+  extern __shared__ float sm[];
+  float* mx = sm; float* my = mx + nm; float* mz = my + nm; float* m2 = mz + nm;
+  __shared__ double sh[32];
+  const int b = blockIdx.x, tid = threadIdx.x, N = S - 1;
+  for (int i = tid; i < nm; i += 1024) {
+    const float* q = model + ((size_t)b * nm + i) * 3;
+    float x = q[0], y = q[1], z = q[2];
+    mx[i] = x; my[i] = y; mz[i] = z; m2[i] = x * x + y * y + z * z;
+  }
+  float Rb[9], tb[3];
+  for (int a = 0; a < 9; ++a) Rb[a] = R[(size_t)b * 9 + a];
+  for (int a = 0; a < 3; ++a) tb[a] = t[(size_t)b * 3 + a];
+  __syncthreads();
+  double hits = 0.0, msum = 0.0;
+  for (int i = tid; i < N; i += 1024) {
+    const float* p = pts1 + ((size_t)b * N + i) * 3;
+    float x = p[0] - tb[0], y = p[1] - tb[1], z = p[2] - tb[2];
+    float tx = x * Rb[0] + y * Rb[3] + z * Rb[6];
+    float ty = x * Rb[1] + y * Rb[4] + z * Rb[7];
+    float tz = x * Rb[2] + y * Rb[5] + z * Rb[8];
+    float x2 = tx * tx + ty * ty + tz * tz;
+    float best = INFINITY;
+    for (int m = 0; m < nm; ++m) {
+      float xy = tx * mx[m] + ty * my[m] + tz * mz[m];
+      best = fminf(best, fmaxf(x2 - 2.f * xy + m2[m], 0.f));
+    }
+    float mk = lab1[(size_t)b * S + i + 1] > 0 ? 1.f : 0.f;
+    if (sqrtf(best) < dis_thres) hits += mk;
+    msum += mk;
+  }
+  hits = block_sum_d(hits, sh);
+  msum = block_sum_d(msum, sh);
+  if (tid == 0) {
+    float h = (float)hits, ms = (float)msum;
+    score[b] = (h / (ms + 1e-8f)) * (ms / (float)N);
+    float rad = radius[b] + 1e-6f;
+    for (int a = 0; a < 3; ++a) t_scaled[(size_t)b * 3 + a] = tb[a] * rad;
+  }
+}
+
+}  // namespace
+
+// A (B,S,S) f32 score matrix (row/col 0 = background), pts2 (B,S-1,3).
+// Outputs: lab1 (B,S) i32 (row argmax of P; entry 0 unused), lab2 (B,S) i32, wts (B,S-1), pred (B,S-1,3).
+// Scratch: rsum (B,S), csum (B,S), cpart (B,tiles,S) f32, cpi (B,tiles,S) i32, tiles = ceil(S/32).
+S6_API int sam6d_fine_assign(const float* A, int B, int S, float shift, const float* pts2, float* rsum, float* csum,
+                             float* cpart, int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream) {
+  S6_REQUIRE(A && pts2 && rsum && csum && cpart && cpi && lab1 && lab2 && wts && pred && B >= 0 && S >= 2);
+  if (B == 0) return 0;
+  cudaStream_t st = s6_stream(stream);
+  const int tiles = s6_cdiv(S, RT);
+  dim3 gt(tiles, B), gc(s6_cdiv(S, 256), B);
+  fine_sums_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, cpart);
+  S6_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<gc, 256, 0, st>>>(cpart, tiles, S, csum);
+  S6_LAUNCH_CHECK();
+  fine_labels_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, csum, lab1, cpart, cpi);
+  S6_LAUNCH_CHECK();
+  collab_reduce_kernel<<<gc, 256, 0, st>>>(cpart, cpi, tiles, S, lab2);
+  S6_LAUNCH_CHECK();
+  dim3 gw(s6_cdiv(S - 1, 8), B);
+  fine_weighted_kernel<<<gw, 256, 0, st>>>(A, S, shift, rsum, csum, lab1, lab2, pts2, wts, pred);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// src, ref (B,N,3), wts (B,N) -> R (B,3,3), t (B,3) with ref ~= R src + t
+S6_API int sam6d_weighted_procrustes(const float* src, const float* ref, const float* wts, int B, int N, float weight_thresh,
+                                     float eps, float* R, float* t, void* stream) {
+  S6_REQUIRE(src && ref && wts && R && t && B >= 0 && N > 0);
+  if (B == 0) return 0;
+  weighted_procrustes_kernel<<<B, 256, 0, s6_stream(stream)>>>(src, ref, wts, N, weight_thresh, eps, R, t);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// pts1 (B,N,3), lab1 (B,N+1) from sam6d_fine_assign, R,t, model (B,nm,3), radius (B) -> score (B), t_scaled (B,3)
+S6_API int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const float* R, const float* t, const float* model,
+                            int nm, float dis_thres, const float* radius, float* score, float* t_scaled, void* stream) {
+  S6_REQUIRE(pts1 && lab1 && R && t && model && radius && score && t_scaled && B >= 0 && N > 0 && nm > 0);
+  if (B == 0) return 0;
+  size_t smem = (size_t)nm * 4 * sizeof(float);
+  S6_REQUIRE(smem <= 200 * 1024);
+  S6_CHECK(cudaFuncSetAttribute(pose_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pose_score_kernel<<<B, 1024, smem, s6_stream(stream)>>>(pts1, lab1, N + 1, R, t, model, nm, dis_thres, radius, score, t_scaled);
+  S6_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,323 @@
+// pn2.cu -- point-cloud sampling / grouping kernels (replaces the reference's pointnet2._ext for
+// the four ops PEM inference calls; PEM/model/pointnet2/_ext_src/src/{sampling,ball_query,group_points}_gpu.cu).
+//
+// Index outputs are bit-exact with the reference kernels: the squared-distance expression is
+// evaluated with the same contraction nvcc applies there (FMUL, FFMA, FFMA) and argmax ties
+// follow the reference's reduction order (smallest k mod block_size, then smallest k).
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// furthest point sampling
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sqdist_ref(float x1, float y1, float z1, float x2, float y2, float z2) {
+  float dx = x2 - x1, dy = y2 - y1, dz = z2 - z1;
+  float d = __fmul_rn(dx, dx);
+  d = __fmaf_rn(dy, dy, d);
+  d = __fmaf_rn(dz, dz, d);
+  return d;
+}
+
+struct FpsCand {
+  float d;
+  int k;
+};
+
+// total order equivalent to the reference's per-thread scan + shared-memory tree
+__device__ __forceinline__ bool fps_better(float d2, int k2, float d1, int k1, int bs_mask) {
+  if (d2 != d1) return d2 > d1;
+  int t2 = k2 & bs_mask, t1 = k1 & bs_mask;
+  if (t2 != t1) return t2 < t1;
+  return k2 < k1;
+}
+
+// One CTA per cloud, all points and running min-distances in registers (n <= THREADS*PPT).
+template <int THREADS, int PPT>
+__global__ void __launch_bounds__(THREADS) fps_reg_kernel(const float* __restrict__ xyz, int n, int m,
+                                                           int bs_ref, int* __restrict__ idx) {
+  extern __shared__ float sm[];
+  float* sx = sm;
+  float* sy = sm + n;
+  float* sz = sm + 2 * n;
+  __shared__ float red_d[2][THREADS / 32];
+  __shared__ int red_k[2][THREADS / 32];
+
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * n * 3;
+  int* out = idx + (size_t)b * m;
+  for (int i = tid; i < n * 3; i += THREADS) {
+    float v = p[i];
+    int k = i / 3, c = i - k * 3;
+    (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
+  }
+  __syncthreads();
+  float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    int k = tid + i * THREADS;
+    bool ok = k < n;
+    px[i] = ok ? sx[k] : 0.f;
+    py[i] = ok ? sy[k] : 0.f;
+    pz[i] = ok ? sz[k] : 0.f;
+    tmp[i] = 1e10f;
+  }
+  const int bs_mask = bs_ref - 1;
+  int old = 0;
+  if (tid == 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    float x1 = sx[old], y1 = sy[old], z1 = sz[old];
+    float best = -1.f;
+    int besti = 0;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      int k = tid + i * THREADS;
+      if (k < n) {
+        float d = sqdist_ref(x1, y1, z1, px[i], py[i], pz[i]);
+        float d2 = fminf(d, tmp[i]);
+        tmp[i] = d2;
+        if (fps_better(d2, k, best, besti, bs_mask) || best < 0.f) { best = d2; besti = k; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, besti, o);
+      // a lane without points carries best = -1 and loses to any real candidate
+      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
+    }
+    const int buf = j & 1;
+    if (lane == 0) { red_d[buf][warp] = best; red_k[buf][warp] = besti; }
+    __syncthreads();
+    best = red_d[buf][0];
+    besti = red_k[buf][0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) {
+      float d2 = red_d[buf][w];
+      int k2 = red_k[buf][w];
+      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
+    }
+    old = besti;
+    if (tid == 0) out[j] = old;
+  }
+}
+
+// General n: running min-distances in a caller-provided scratch (b,n) f32, points from global/L2.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) fps_big_kernel(const float* __restrict__ xyz, int n, int m, int bs_ref,
+                                                           float* __restrict__ temp, int* __restrict__ idx) {
+  __shared__ float red_d[2][THREADS / 32];
+  __shared__ int red_k[2][THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* p = xyz + (size_t)b * n * 3;
+  float* tmp = temp + (size_t)b * n;
+  int* out = idx + (size_t)b * m;
+  for (int k = tid; k < n; k += THREADS) tmp[k] = 1e10f;
+  const int bs_mask = bs_ref - 1;
+  int old = 0;
+  if (tid == 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    float x1 = p[old * 3 + 0], y1 = p[old * 3 + 1], z1 = p[old * 3 + 2];
+    float best = -1.f;
+    int besti = 0;
+    for (int k = tid; k < n; k += THREADS) {
+      float d = sqdist_ref(x1, y1, z1, p[k * 3 + 0], p[k * 3 + 1], p[k * 3 + 2]);
+      float d2 = fminf(d, tmp[k]);
+      tmp[k] = d2;
+      if (best < 0.f || fps_better(d2, k, best, besti, bs_mask)) { best = d2; besti = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float d2 = __shfl_xor_sync(0xffffffffu, best, o);
+      int k2 = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
+    }
+    const int buf = j & 1;
+    if (lane == 0) { red_d[buf][warp] = best; red_k[buf][warp] = besti; }
+    __syncthreads();
+    best = red_d[buf][0];
+    besti = red_k[buf][0];
+#pragma unroll
+    for (int w = 1; w < THREADS / 32; ++w) {
+      float d2 = red_d[buf][w];
+      int k2 = red_k[buf][w];
+      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
+    }
+    old = besti;
+    if (tid == 0) out[j] = old;
+  }
+}
+
+static int ref_block_size(int n) {  // cuda_utils.h:20-24
+  int p = 1;
+  while (p * 2 <= n && p * 2 <= 512) p *= 2;
+  return p;
+}
+
+// Replaces _ext.furthest_point_sampling (bindings.cpp:14, sampling.cpp:67-91).
+// xyz (b,n,3) f32, idx (b,m) i32; temp: scratch (b,n) f32, only needed when n > 4096 (may be null otherwise).
+S6_API int sam6d_fps(const float* xyz, int b, int n, int m, float* temp, int* idx, void* stream) {
+  S6_REQUIRE(xyz && idx && b >= 0 && n > 0 && m >= 0);
+  if (b == 0 || m == 0) return 0;
+  const int bs_ref = ref_block_size(n);
+  cudaStream_t st = s6_stream(stream);
+  if (n <= 4096) {
+    size_t smem = (size_t)n * 3 * sizeof(float);
+    if (n <= 1024) {
+      fps_reg_kernel<256, 4><<<b, 256, smem, st>>>(xyz, n, m, bs_ref, idx);
+    } else if (n <= 2048) {
+      fps_reg_kernel<512, 4><<<b, 512, smem, st>>>(xyz, n, m, bs_ref, idx);
+    } else {
+      S6_CHECK(cudaFuncSetAttribute(fps_reg_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fps_reg_kernel<512, 8><<<b, 512, smem, st>>>(xyz, n, m, bs_ref, idx);
+    }
+  } else {
+    S6_REQUIRE(temp != nullptr);
+    fps_big_kernel<1024><<<b, 1024, 0, st>>>(xyz, n, m, bs_ref, temp, idx);
+  }
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// gathers
+// ------------------------------------------------------------------------------------------
+// channel-last row gather: out[b,j,:] = src[b, idx[b,j], :]; rows are C floats (C % 4 == 0 -> float4 path)
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, int m, int c,
+                                   long long src_bstride, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c4 = c >> 2;
+  const long long total = (long long)m * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i / c4), q = (int)(i - (long long)j * c4);
+    int a = idx[(size_t)b * m + j];
+    const float4* s = reinterpret_cast<const float4*>(src + (size_t)b * src_bstride + (size_t)a * c);
+    reinterpret_cast<float4*>(out + ((size_t)b * m + j) * c)[q] = s[q];
+  }
+}
+__global__ void gather_rows_scalar_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, int m, int c,
+                                          long long src_bstride, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const long long total = (long long)m * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i / c), q = (int)(i - (long long)j * c);
+    int a = idx[(size_t)b * m + j];
+    out[((size_t)b * m + j) * c + q] = src[(size_t)b * src_bstride + (size_t)a * c + q];
+  }
+}
+
+// src (b,n,c) f32 with batch stride src_bstride (elements), idx (b,m) i32 -> out (b,m,c)
+S6_API int sam6d_gather_rows(const float* src, const int* idx, int b, int n, int m, int c, long long src_bstride,
+                             float* out, void* stream) {
+  S6_REQUIRE(src && idx && out && b >= 0 && n > 0 && m >= 0 && c > 0);
+  if (b == 0 || m == 0) return 0;
+  cudaStream_t st = s6_stream(stream);
+  bool vec = (c % 4 == 0) && (src_bstride % 4 == 0) && (((uintptr_t)src | (uintptr_t)out) % 16 == 0);
+  long long total = (long long)m * (vec ? c / 4 : c);
+  dim3 grid((unsigned)min((long long)1024, (total + 255) / 256), b);
+  if (vec) gather_rows_kernel<<<grid, 256, 0, st>>>(src, idx, n, m, c, src_bstride, out);
+  else gather_rows_scalar_kernel<<<grid, 256, 0, st>>>(src, idx, n, m, c, src_bstride, out);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// channel-first gather, the reference ABI: points (b,c,n), idx (b,m) -> out (b,c,m)   (sampling_gpu.cu:13-25)
+__global__ void gather_points_cf_kernel(const float* __restrict__ points, const int* __restrict__ idx, int c, int n, int m,
+                                        float* __restrict__ out) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x)
+    out[((size_t)b * c + l) * m + j] = points[((size_t)b * c + l) * n + idx[(size_t)b * m + j]];
+}
+S6_API int sam6d_gather_points(const float* points, const int* idx, int b, int c, int n, int m, float* out, void* stream) {
+  S6_REQUIRE(points && idx && out && b >= 0 && c > 0 && n > 0 && m >= 0);
+  if (b == 0 || m == 0) return 0;
+  S6_REQUIRE(c <= 65535 && b <= 65535);
+  dim3 grid(s6_cdiv(m, 256), c, b);
+  gather_points_cf_kernel<<<grid, 256, 0, s6_stream(stream)>>>(points, idx, c, n, m, out);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// ball query: one warp per query, ballot + prefix popcount keeps the reference's ascending-k order
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ball_query_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz,
+                                                         int n, int m, float radius2, int nsample, int* __restrict__ idx,
+                                                         int* __restrict__ cnt_out) {
+  extern __shared__ float sp[];  // tile of xyz, 3 * TILE floats
+  const int TILE = 1024;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  const float* p = xyz + (size_t)b * n * 3;
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (j < m) {
+    const float* q = new_xyz + ((size_t)b * m + j) * 3;
+    nx = q[0]; ny = q[1]; nz = q[2];
+  }
+  int* o = (j < m) ? idx + ((size_t)b * m + j) * nsample : nullptr;
+  int cnt = 0, first = 0;
+  for (int base = 0; base < n; base += TILE) {
+    int tn = min(TILE, n - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) sp[i] = p[(size_t)base * 3 + i];
+    __syncthreads();
+    if (j < m && cnt < nsample) {
+      for (int k0 = 0; k0 < tn && cnt < nsample; k0 += 32) {
+        int k = k0 + lane;
+        bool hit = false;
+        if (k < tn) {
+          float dx = nx - sp[k * 3 + 0], dy = ny - sp[k * 3 + 1], dz = nz - sp[k * 3 + 2];
+          float d2 = __fmul_rn(dx, dx);
+          d2 = __fmaf_rn(dy, dy, d2);
+          d2 = __fmaf_rn(dz, dz, d2);
+          hit = d2 < radius2;
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+          if (cnt == 0) first = base + k0 + __ffs(mask) - 1;
+          int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+          if (hit && pos < nsample) o[pos] = base + k;
+          cnt += __popc(mask);
+        }
+      }
+    }
+  }
+  if (j < m) {
+    int c = min(cnt, nsample);
+    // pad with the first hit; all zeros when the ball is empty (the output is defined as pre-zeroed)
+    for (int l = c + lane; l < nsample; l += 32) o[l] = (cnt > 0) ? first : 0;
+    if (cnt_out && lane == 0) cnt_out[(size_t)b * m + j] = c;
+  }
+}
+
+// Replaces _ext.ball_query (bindings.cpp:18, ball_query.cpp:11-35).  cnt (b,m) i32 is optional:
+// the number of distinct hits kept (<= nsample), which lets the fused PE kernel skip padding.
+S6_API int sam6d_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius, int nsample,
+                            int* idx, int* cnt, void* stream) {
+  S6_REQUIRE(new_xyz && xyz && idx && b >= 0 && n > 0 && m >= 0 && nsample > 0);
+  if (b == 0 || m == 0) return 0;
+  dim3 grid(s6_cdiv(m, 8), b);
+  ball_query_kernel<<<grid, 256, 1024 * 3 * sizeof(float), s6_stream(stream)>>>(new_xyz, xyz, n, m, radius * radius,
+                                                                               nsample, idx, cnt);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// group points, the reference ABI: points (b,c,n), idx (b,np,ns) -> out (b,c,np,ns)  (group_points_gpu.cu:13-33)
+// ------------------------------------------------------------------------------------------
+__global__ void group_points_kernel(const float* __restrict__ points, const int* __restrict__ idx, int c, int n, int np,
+                                    int ns, float* __restrict__ out) {
+  const int b = blockIdx.z, l = blockIdx.y;
+  const long long total = (long long)np * ns;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[((size_t)b * c + l) * total + i] = points[((size_t)b * c + l) * n + idx[(size_t)b * total + i]];
+}
+S6_API int sam6d_group_points(const float* points, const int* idx, int b, int c, int n, int np, int ns, float* out,
+                              void* stream) {
+  S6_REQUIRE(points && idx && out && b >= 0 && c > 0 && n > 0 && np >= 0 && ns > 0);
+  if (b == 0 || np == 0) return 0;
+  S6_REQUIRE(c <= 65535 && b <= 65535);
+  dim3 grid(min(4096, s6_cdiv((long long)np * ns, 256)), c, b);
+  group_points_kernel<<<grid, 256, 0, s6_stream(stream)>>>(points, idx, c, n, np, ns, out);
+  S6_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,193 @@
+// rowops.cu -- one-warp-per-token kernels over C-channel rows (C = 256 in the model, any multiple of 32 up to 1024):
+// LayerNorm, L2 normalisation, the focused-linear-attention feature map, and the rigid warp of a point cloud.
+//
+// Rows are addressed as  base + (r / rows_per_batch) * batch_stride + (r % rows_per_batch) * ld  so that the
+// dense-token view "rows 1..N of a (B, N+1, C) sequence" needs no copy.
+#include "common.cuh"
+
+namespace {
+
+struct RowView {
+  long long rpb, bstride, ld;
+  __device__ __forceinline__ size_t off(long long r) const {
+    long long b = r / rpb, i = r - b * rpb;
+    return (size_t)(b * bstride + i * ld);
+  }
+};
+
+constexpr int MAXV = 32;  // per-lane values: C / 32 <= 32
+
+// LayerNorm(x) * gamma + beta, eps as nn.LayerNorm (PEM/model/transformer.py:156,188: nn.LayerNorm(d_model)).
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xp = x + xv.off(r);
+  float* yp = y + yv.off(r);
+  const int nv = C >> 5;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) { v[i] = xp[lane + 32 * i]; s += v[i]; }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) { float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) { int c = lane + 32 * i; yp[c] = (v[i] - mean) * rstd * gamma[c] + beta[c]; }
+}
+
+// F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
+                                                     long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xp = x + xv.off(r);
+  float* yp = y + yv.off(r);
+  const int nv = C >> 5;
+  float v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) { v[i] = xp[lane + 32 * i]; s += v[i] * v[i]; }
+  const float n = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) yp[lane + 32 * i] = v[i] / n;
+}
+
+// Focused linear attention feature map (PEM/model/transformer.py:541-550):
+//   q = relu(x) + 1e-6;  q = q / softplus(scale);  n = ||q||;  q = q^3;  q = q / ||q|| * n
+__global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
+                                                    const float* __restrict__ sp_scale, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* xp = x + xv.off(r);
+  float* yp = y + yv.off(r);
+  const int nv = C >> 5;
+  float v[MAXV];
+  float s1 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) {
+      int c = lane + 32 * i;
+      float q = (fmaxf(xp[c], 0.f) + 1e-6f) / sp_scale[c];
+      s1 += q * q;
+      q = q * q * q;
+      s3 += q * q;
+      v[i] = q;
+    }
+  const float n1 = sqrtf(warp_sum(s1)), n3 = sqrtf(warp_sum(s3));
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+    if (i < nv) yp[lane + 32 * i] = (v[i] / n3) * n1;
+}
+
+// out[b,i,:] = (p[b,i,:] - t[b]) @ R[b]        (PEM/model/fine_point_matching.py:44)
+__global__ void rigid_warp_kernel(const float* __restrict__ p, const float* __restrict__ R, const float* __restrict__ t, int n,
+                                  long long total, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int b = (int)(i / n);
+  const float* Rb = R + (size_t)b * 9;
+  const float* tb = t + (size_t)b * 3;
+  float x = p[i * 3 + 0] - tb[0], y = p[i * 3 + 1] - tb[1], z = p[i * 3 + 2] - tb[2];
+  out[i * 3 + 0] = x * Rb[0] + y * Rb[3] + z * Rb[6];
+  out[i * 3 + 1] = x * Rb[1] + y * Rb[4] + z * Rb[7];
+  out[i * 3 + 2] = x * Rb[2] + y * Rb[5] + z * Rb[8];
+}
+
+// per-cloud radius normalisation (PEM/model/feature_extraction.py:139-142):
+//   radius[b] = max_i ||po[b,i]||;  pm /= radius + 1e-6;  po /= radius + 1e-6;  model /= radius + 1e-6
+__global__ void __launch_bounds__(256) radius_kernel(const float* __restrict__ po, int n, float* __restrict__ radius) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float* q = po + ((size_t)b * n + i) * 3;
+    m = fmaxf(m, sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    radius[b] = m;
+  }
+}
+__global__ void scale_by_radius_kernel(const float* __restrict__ src, const float* __restrict__ radius, long long per_batch,
+                                       long long total, float* __restrict__ dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  dst[i] = src[i] / (radius[i / per_batch] + 1e-6f);
+}
+
+}  // namespace
+
+#define ROW_ARGS_OK(C) ((C) % 32 == 0 && (C) <= 32 * MAXV && (C) > 0)
+
+S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                           long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                           float eps, void* stream) {
+  S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  layernorm_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+                                                                    RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+S6_API int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                             long long y_bstride, long long y_ld, long long rows, int C, void* stream) {
+  S6_REQUIRE(x && y && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  l2norm_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+                                                                 RowView{y_rpb, y_bstride, y_ld}, rows, C);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+S6_API int sam6d_focus_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
+                            long long y_bstride, long long y_ld, const float* softplus_scale, long long rows, int C,
+                            void* stream) {
+  S6_REQUIRE(x && y && softplus_scale && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  focus_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+                                                                RowView{y_rpb, y_bstride, y_ld}, softplus_scale, rows, C);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+S6_API int sam6d_rigid_warp(const float* p, const float* R, const float* t, int b, int n, float* out, void* stream) {
+  S6_REQUIRE(p && R && t && out && b >= 0 && n >= 0);
+  long long total = (long long)b * n;
+  if (total == 0) return 0;
+  rigid_warp_kernel<<<s6_cdiv(total, 256), 256, 0, s6_stream(stream)>>>(p, R, t, n, total, out);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+S6_API int sam6d_cloud_radius(const float* po, int b, int n, float* radius, void* stream) {
+  S6_REQUIRE(po && radius && b >= 0 && n > 0);
+  if (b == 0) return 0;
+  radius_kernel<<<b, 256, 0, s6_stream(stream)>>>(po, n, radius);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+S6_API int sam6d_scale_by_radius(const float* src, const float* radius, int b, long long per_batch, float* dst, void* stream) {
+  S6_REQUIRE(src && radius && dst && b >= 0 && per_batch >= 0);
+  long long total = (long long)b * per_batch;
+  if (total == 0) return 0;
+  scale_by_radius_kernel<<<s6_cdiv(total, 256), 256, 0, s6_stream(stream)>>>(src, radius, per_batch, total, dst);
+  S6_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,356 @@
+"""Tensor-level wrappers over the C ABI (include/sam6d_b200.h).
+
+PyTorch is used here only as the owner of device memory and of the current CUDA stream; every function validates its
+arguments the way the reference's native layer does (CUDA, contiguous, dtype -- PEM/model/pointnet2/_ext_src/include/utils.h:10-30
+raise through TORCH_CHECK -> RuntimeError) and then hands raw pointers to libsam6d_b200.so.
+"""
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _check(t: Tensor, dtype, name: str, ndim: Optional[int] = None):
+    if not isinstance(t, torch.Tensor):
+        raise RuntimeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (CPU not supported)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f"{name} must have {ndim} dims, got {t.dim()}")
+
+
+def _p(t: Optional[Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ll(v):
+    return ctypes.c_longlong(int(v))
+
+
+def _f(v):
+    return ctypes.c_float(float(v))
+
+
+# ---------------------------------------------------------------------------------------------- point-cloud ops
+def furthest_point_sampling(xyz: Tensor, m: int) -> Tensor:
+    """_ext.furthest_point_sampling: (B,N,3) f32 -> (B,m) i32."""
+    _check(xyz, torch.float32, "points", 3)
+    b, n, c = xyz.shape
+    if c != 3:
+        raise RuntimeError("points must be (B,N,3)")
+    idx = torch.zeros(b, m, dtype=torch.int32, device=xyz.device)
+    temp = torch.empty(b, n, dtype=torch.float32, device=xyz.device) if n > 4096 else None
+    _lib.call("sam6d_fps", _p(xyz), b, n, int(m), _p(temp), _p(idx), _s())
+    return idx
+
+
+def gather_points(points: Tensor, idx: Tensor) -> Tensor:
+    """_ext.gather_points: (B,C,N) f32, (B,M) i32 -> (B,C,M)."""
+    _check(points, torch.float32, "points", 3)
+    _check(idx, torch.int32, "idx", 2)
+    b, c, n = points.shape
+    m = idx.shape[1]
+    out = torch.zeros(b, c, m, dtype=torch.float32, device=points.device)
+    _lib.call("sam6d_gather_points", _p(points), _p(idx), b, c, n, m, _p(out), _s())
+    return out
+
+
+def gather_rows(src: Tensor, idx: Tensor, n_rows: Optional[int] = None) -> Tensor:
+    """channel-last gather: src (B,N,C) f32, idx (B,M) i32 -> (B,M,C)."""
+    _check(src, torch.float32, "src", 3)
+    _check(idx, torch.int32, "idx", 2)
+    b, n, c = src.shape
+    m = idx.shape[1]
+    out = torch.empty(b, m, c, dtype=torch.float32, device=src.device)
+    _lib.call("sam6d_gather_rows", _p(src), _p(idx), b, n, m, c, _ll(n * c), _p(out), _s())
+    return out
+
+
+def ball_query(new_xyz: Tensor, xyz: Tensor, radius: float, nsample: int, return_count: bool = False):
+    """_ext.ball_query: new_xyz (B,M,3), xyz (B,N,3) -> (B,M,nsample) i32 [, count (B,M) i32]."""
+    _check(new_xyz, torch.float32, "new_xyz", 3)
+    _check(xyz, torch.float32, "xyz", 3)
+    b, m, _ = new_xyz.shape
+    n = xyz.shape[1]
+    idx = torch.zeros(b, m, nsample, dtype=torch.int32, device=xyz.device)
+    cnt = torch.zeros(b, m, dtype=torch.int32, device=xyz.device) if return_count else None
+    _lib.call("sam6d_ball_query", _p(new_xyz), _p(xyz), b, n, m, _f(radius), int(nsample), _p(idx), _p(cnt), _s())
+    return (idx, cnt) if return_count else idx
+
+
+def group_points(points: Tensor, idx: Tensor) -> Tensor:
+    """_ext.group_points: (B,C,N) f32, (B,np,ns) i32 -> (B,C,np,ns)."""
+    _check(points, torch.float32, "points", 3)
+    _check(idx, torch.int32, "idx", 3)
+    b, c, n = points.shape
+    _, npnt, ns = idx.shape
+    out = torch.zeros(b, c, npnt, ns, dtype=torch.float32, device=points.device)
+    _lib.call("sam6d_group_points", _p(points), _p(idx), b, c, n, npnt, ns, _p(out), _s())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- dense algebra
+def gemm(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
+         out: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0) -> Tensor:
+    """out = alpha * A @ W^T (+bias) (relu) (+residual); A (M,K), W (N,K) contiguous f32."""
+    _check(A, torch.float32, "A", 2)
+    _check(W, torch.float32, "W", 2)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise RuntimeError("gemm: inner dimensions differ")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    _lib.call("sam6d_gemm_f32", _p(A), _p(W), _p(bias), _p(residual), _p(out), M, N, K, _ll(K), _ll(K), _ll(N), _ll(N),
+              1, _ll(0), _ll(0), _ll(0), _ll(0), _f(alpha), int(relu), _s())
+    return out
+
+
+def gemm_raw(A_ptr, W_ptr, bias, R_ptr, C_ptr, M, N, K, lda, ldw, ldc, ldr, batch=1, sA=0, sW=0, sC=0, sR=0,
+             alpha=1.0, relu=False):
+    """strided / batched form over raw device addresses (ints)."""
+    _lib.call("sam6d_gemm_f32", ctypes.c_void_p(A_ptr), ctypes.c_void_p(W_ptr), _p(bias), ctypes.c_void_p(R_ptr or 0),
+              ctypes.c_void_p(C_ptr), int(M), int(N), int(K), _ll(lda), _ll(ldw), _ll(ldc), _ll(ldr), int(batch), _ll(sA),
+              _ll(sW), _ll(sC), _ll(sR), _f(alpha), int(relu), _s())
+
+
+def layernorm_raw(x_ptr, x_view, y_ptr, y_view, gamma: Tensor, beta: Tensor, rows: int, C: int, eps: float = 1e-5):
+    _lib.call("sam6d_layernorm", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
+              ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(gamma), _p(beta), _ll(rows), int(C),
+              _f(eps), _s())
+
+
+def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Optional[Tensor] = None) -> Tensor:
+    _check(x, torch.float32, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    layernorm_raw(x.data_ptr(), (rows, 0, C), out.data_ptr(), (rows, 0, C), gamma, beta, rows, C, eps)
+    return out
+
+
+def l2norm_rows(x: Tensor) -> Tensor:
+    _check(x, torch.float32, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty_like(x)
+    _lib.call("sam6d_l2norm_rows", _p(x), _ll(rows), _ll(0), _ll(C), _p(out), _ll(rows), _ll(0), _ll(C), _ll(rows), C, _s())
+    return out
+
+
+def focus_rows_raw(x_ptr, x_view, y_ptr, y_view, sp_scale: Tensor, rows: int, C: int):
+    _lib.call("sam6d_focus_rows", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
+              ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(sp_scale), _ll(rows), int(C), _s())
+
+
+def rigid_warp(p: Tensor, R: Tensor, t: Tensor) -> Tensor:
+    _check(p, torch.float32, "p", 3)
+    _check(R, torch.float32, "R", 3)
+    _check(t, torch.float32, "t", 2)
+    out = torch.empty_like(p)
+    _lib.call("sam6d_rigid_warp", _p(p), _p(R), _p(t), p.shape[0], p.shape[1], _p(out), _s())
+    return out
+
+
+def cloud_radius(po: Tensor) -> Tensor:
+    _check(po, torch.float32, "dense_po", 3)
+    r = torch.empty(po.shape[0], dtype=torch.float32, device=po.device)
+    _lib.call("sam6d_cloud_radius", _p(po), po.shape[0], po.shape[1], _p(r), _s())
+    return r
+
+
+def scale_by_radius(x: Tensor, radius: Tensor) -> Tensor:
+    _check(x, torch.float32, "x")
+    _check(radius, torch.float32, "radius", 1)
+    out = torch.empty_like(x)
+    b = x.shape[0]
+    _lib.call("sam6d_scale_by_radius", _p(x), _p(radius), b, _ll(x.numel() // max(b, 1)), _p(out), _s())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- geometric embedding
+def geo_indices(pts: Tensor, sigma_d: float, factor_a: float) -> Tensor:
+    _check(pts, torch.float32, "points", 3)
+    b, s, _ = pts.shape
+    T = torch.empty(b, s, s, 4, dtype=torch.float32, device=pts.device)
+    _lib.call("sam6d_geo_indices", _p(pts), b, s, _f(sigma_d), _f(factor_a), _p(T), _s())
+    return T
+
+
+def geo_embed_f32(T: Tensor, div_term: Tensor, WaT: Tensor, WdT: Tensor, bias: Tensor) -> Tensor:
+    _check(T, torch.float32, "T", 4)
+    b, s, _, _ = T.shape
+    E = torch.empty(b, s, s, 256, dtype=torch.float32, device=T.device)
+    _lib.call("sam6d_geo_embed_f32", _p(T), _ll(b * s * s), _p(div_term), _p(WaT), _p(WdT), _p(bias), _p(E), _s())
+    return E
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def rpe_scores(E: Tensor, U: Tensor, u_ptr: Optional[int] = None, u_ld: int = 1024) -> Tensor:
+    """E (B,S,S,256) f32|bf16, U (B,S,4,256) f32 (or a raw address + row stride) -> (B,4,S,S) f32."""
+    if E.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("E must be float32 or bfloat16")
+    _check(E, E.dtype, "E", 4)
+    if u_ptr is None:
+        _check(U, torch.float32, "U", 4)
+        u_ptr = U.data_ptr()
+    B, S = E.shape[0], E.shape[1]
+    SP = torch.empty(B, 4, S, S, dtype=torch.float32, device=E.device)
+    _lib.call("sam6d_rpe_scores", _p(E), int(E.dtype == torch.bfloat16), ctypes.c_void_p(u_ptr), _ll(u_ld), B, S, _p(SP), _s())
+    return SP
+
+
+def mha_raw(q_ptr, q_ld, q_bs, k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, bias: Optional[Tensor], B, H, Sq, Sk, scale,
+            o_ptr, o_ld, o_bs):
+    _lib.call("sam6d_mha", ctypes.c_void_p(q_ptr), _ll(q_ld), _ll(q_bs), ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs),
+              ctypes.c_void_p(v_ptr), _ll(v_ld), _ll(v_bs), _p(bias), int(B), int(H), int(Sq), int(Sk), _f(scale),
+              ctypes.c_void_p(o_ptr), _ll(o_ld), _ll(o_bs), _s())
+
+
+def linattn_kv_raw(k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, B, H, J, KV: Tensor, KS: Tensor):
+    _lib.call("sam6d_linattn_kv", ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs), ctypes.c_void_p(v_ptr), _ll(v_ld), _ll(v_bs),
+              int(B), int(H), int(J), _p(KV), _p(KS), _s())
+
+
+def linattn_apply_raw(q_ptr, q_rpb, q_bs, q_ld, KV: Tensor, KS: Tensor, B, H, x_ptr, x_bs, x_ld):
+    _lib.call("sam6d_linattn_apply", ctypes.c_void_p(q_ptr), _ll(q_rpb), _ll(q_bs), _ll(q_ld), _p(KV), _p(KS), int(B), int(H),
+              ctypes.c_void_p(x_ptr), _ll(x_bs), _ll(x_ld), _s())
+
+
+# ---------------------------------------------------------------------------------------------- coarse pose
+def coarse_assign(A: Tensor) -> Tuple[Tensor, Tensor]:
+    _check(A, torch.float32, "atten", 3)
+    B, S, _ = A.shape
+    n = S - 1
+    W = torch.empty(B, n * n, dtype=torch.float32, device=A.device)
+    w1 = torch.empty(B, n, dtype=torch.float32, device=A.device)
+    _lib.call("sam6d_coarse_assign", _p(A), B, S, _p(W), _p(w1), _s())
+    return W, w1
+
+
+def coarse_sample(W: Tensor, rand: Tensor) -> Tensor:
+    _check(W, torch.float32, "W", 2)
+    _check(rand, torch.float32, "rand", 2)
+    B, L = W.shape
+    nr = rand.shape[1]
+    idx = torch.empty(B, nr, dtype=torch.int32, device=W.device)
+    _lib.call("sam6d_coarse_sample", _p(W), B, L, _p(rand), nr, _p(idx), _s())
+    return idx
+
+
+def coarse_hypotheses(idx: Tensor, pts1: Tensor, pts2: Tensor) -> Tuple[Tensor, Tensor]:
+    _check(idx, torch.int32, "idx", 2)
+    _check(pts1, torch.float32, "pts1", 3)
+    _check(pts2, torch.float32, "pts2", 3)
+    B, n, _ = pts1.shape
+    n1 = idx.shape[1] // 3
+    Rt = torch.empty(B, n1, 12, dtype=torch.float32, device=idx.device)
+    resid = torch.empty(B, n1, dtype=torch.float32, device=idx.device)
+    _lib.call("sam6d_coarse_hypotheses", _p(idx), _p(pts1), _p(pts2), B, n, n1, _p(Rt), _p(resid), _s())
+    return Rt, resid
+
+
+def topk_smallest(v: Tensor, k: int) -> Tensor:
+    _check(v, torch.float32, "v", 2)
+    B, n = v.shape
+    out = torch.empty(B, k, dtype=torch.int32, device=v.device)
+    _lib.call("sam6d_topk_smallest", _p(v), B, n, int(k), _p(out), _s())
+    return out
+
+
+def coarse_select(Rt: Tensor, top: Tensor, pts1: Tensor, w1: Tensor, model: Tensor):
+    _check(Rt, torch.float32, "Rt", 3)
+    _check(top, torch.int32, "top", 2)
+    _check(model, torch.float32, "model", 3)
+    B, n1, _ = Rt.shape
+    n2 = top.shape[1]
+    n = pts1.shape[1]
+    scores = torch.empty(B, n2, dtype=torch.float32, device=Rt.device)
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=Rt.device)
+    t = torch.empty(B, 3, dtype=torch.float32, device=Rt.device)
+    _lib.call("sam6d_coarse_select", _p(Rt), _p(top), B, n1, n2, _p(pts1), _p(w1), n, _p(model), model.shape[1], _p(scores),
+              _p(R), _p(t), _s())
+    return R, t, scores
+
+
+# ---------------------------------------------------------------------------------------------- fine stage
+def pe_mlp_max(pts: Tensor, idx: Tensor, cnt: Tensor, weights, out: Tensor, out_off: int):
+    _check(pts, torch.float32, "pts", 3)
+    _check(idx, torch.int32, "idx", 3)
+    _check(cnt, torch.int32, "cnt", 2)
+    B, N, _ = pts.shape
+    ns = idx.shape[2]
+    W1, B1, W2, B2, W3, B3 = weights
+    _lib.call("sam6d_pe_mlp_max", _p(pts), _p(idx), _p(cnt), B, N, ns, _p(W1), _p(B1), _p(W2), _p(B2), _p(W3), _p(B3),
+              _p(out), out.shape[-1], int(out_off), _s())
+
+
+def fine_assign(A: Tensor, pts2: Tensor, shift: float):
+    _check(A, torch.float32, "atten", 3)
+    _check(pts2, torch.float32, "pts2", 3)
+    B, S, _ = A.shape
+    dev = A.device
+    tiles = (S + 31) // 32
+    rsum = torch.empty(B, S, dtype=torch.float32, device=dev)
+    csum = torch.empty(B, S, dtype=torch.float32, device=dev)
+    cpart = torch.empty(B, tiles, S, dtype=torch.float32, device=dev)
+    cpi = torch.empty(B, tiles, S, dtype=torch.int32, device=dev)
+    lab1 = torch.zeros(B, S, dtype=torch.int32, device=dev)
+    lab2 = torch.zeros(B, S, dtype=torch.int32, device=dev)
+    wts = torch.empty(B, S - 1, dtype=torch.float32, device=dev)
+    pred = torch.empty(B, S - 1, 3, dtype=torch.float32, device=dev)
+    _lib.call("sam6d_fine_assign", _p(A), B, S, _f(shift), _p(pts2), _p(rsum), _p(csum), _p(cpart), _p(cpi), _p(lab1),
+              _p(lab2), _p(wts), _p(pred), _s())
+    return lab1, lab2, wts, pred
+
+
+def weighted_procrustes(src: Tensor, ref: Tensor, wts: Tensor, weight_thresh: float = 0.0, eps: float = 1e-5):
+    _check(src, torch.float32, "src", 3)
+    _check(ref, torch.float32, "ref", 3)
+    _check(wts, torch.float32, "weights", 2)
+    B, N, _ = src.shape
+    R = torch.empty(B, 3, 3, dtype=torch.float32, device=src.device)
+    t = torch.empty(B, 3, dtype=torch.float32, device=src.device)
+    _lib.call("sam6d_weighted_procrustes", _p(src), _p(ref), _p(wts), B, N, _f(weight_thresh), _f(eps), _p(R), _p(t), _s())
+    return R, t
+
+
+def pose_score(pts1: Tensor, lab1: Tensor, R: Tensor, t: Tensor, model: Tensor, radius: Tensor, dis_thres: float = 0.15):
+    _check(pts1, torch.float32, "pts1", 3)
+    _check(lab1, torch.int32, "lab1", 2)
+    B, N, _ = pts1.shape
+    score = torch.empty(B, dtype=torch.float32, device=pts1.device)
+    ts = torch.empty(B, 3, dtype=torch.float32, device=pts1.device)
+    _lib.call("sam6d_pose_score", _p(pts1), _p(lab1), B, N, _p(R), _p(t), _p(model), model.shape[1], _f(dis_thres),
+              _p(radius), _p(score), _p(ts), _s())
+    return score, ts
+
+
+# ---------------------------------------------------------------------------------------------- ISM scoring
+def template_score(Qn: Tensor, Rn: Tensor, want_sim: bool = True):
+    """Qn (P,C), Rn (O,T,C): F.normalize'd descriptors -> sim (P,O,T), obj_score (P,O), best_obj, best_score, best_tmpl."""
+    _check(Qn, torch.float32, "query", 2)
+    _check(Rn, torch.float32, "reference", 3)
+    P, C = Qn.shape
+    O, T, _ = Rn.shape
+    dev = Qn.device
+    sim = torch.empty(P, O, T, dtype=torch.float32, device=dev) if want_sim else None
+    obj = torch.empty(P, O, dtype=torch.float32, device=dev)
+    bo = torch.zeros(P, dtype=torch.int32, device=dev)
+    bs = torch.zeros(P, dtype=torch.float32, device=dev)
+    bt = torch.zeros(P, dtype=torch.int32, device=dev)
+    _lib.call("sam6d_template_score", _p(Qn), _p(Rn), P, O, T, C, _p(sim), _p(obj), _p(bo), _p(bs), _p(bt), _s())
+    return sim, obj, bo, bs, bt

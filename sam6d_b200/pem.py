@@ -1,0 +1,632 @@
+"""Pose Estimation Model matching path on B200 kernels -- drop-in for the reference's model classes.
+
+Class names, constructor arguments, sub-module / parameter names (hence `state_dict` keys) and the `forward` contracts
+mirror the reference:
+    Net                         PEM/model/pose_estimation_model.py:11-53
+    GeometricStructureEmbedding PEM/model/transformer.py:286-349
+    GeometricTransformer        PEM/model/transformer.py:469-513
+    SparseToDenseTransformer    PEM/model/transformer.py:613-673
+    CoarsePointMatching         PEM/model/coarse_point_matching.py:14-81
+    FinePointMatching           PEM/model/fine_point_matching.py:12-126
+so `sam-6d-pem-base.pth` loads unchanged.  The torch modules here are parameter containers only: every forward runs
+hand-written sm_100a kernels through the C ABI (sam6d_b200/ops.py); inference only (the reference's training branches --
+losses, pose-noise augmentation -- are out of scope), and there is no CPU path.
+"""
+import math
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+NUM_HEADS = 4  # hard-coded in the reference (coarse_point_matching.py:31, fine_point_matching.py:29)
+
+
+def _cfg(cfg, **defaults):
+    """accept gorilla Config / dict / namespace like the reference's cfg objects"""
+    if isinstance(cfg, dict):
+        cfg = SimpleNamespace(**cfg)
+    for k, v in defaults.items():
+        if not hasattr(cfg, k):
+            setattr(cfg, k, v)
+    return cfg
+
+
+# =====================================================================================================================
+# parameter containers with the reference's names
+# =====================================================================================================================
+class _MHAParams(nn.Module):
+    def __init__(self, d_model, rpe: bool):
+        super().__init__()
+        self.proj_q = nn.Linear(d_model, d_model)
+        self.proj_k = nn.Linear(d_model, d_model)
+        self.proj_v = nn.Linear(d_model, d_model)
+        if rpe:
+            self.proj_p = nn.Linear(d_model, d_model)
+
+
+class _AttentionLayerParams(nn.Module):
+    def __init__(self, d_model, rpe: bool):
+        super().__init__()
+        self.attention = _MHAParams(d_model, rpe)
+        self.linear = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+
+
+class _AttentionOutputParams(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        self.expand = nn.Linear(d_model, d_model * 2)
+        self.squeeze = nn.Linear(d_model * 2, d_model)
+        self.norm = nn.LayerNorm(d_model)
+
+
+class _TransformerLayerParams(nn.Module):
+    def __init__(self, d_model, rpe: bool):
+        super().__init__()
+        self.attention = _AttentionLayerParams(d_model, rpe)
+        self.output = _AttentionOutputParams(d_model)
+
+
+class _Packed:
+    """device-resident, kernel-ready weights derived from a module's parameters (rebuilt when they change)"""
+
+    def __init__(self):
+        self.key = None
+        self.w = {}
+
+
+def _param_key(module: nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters()) + tuple(
+        (b.data_ptr(), b._version) for b in module.buffers())
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# shared token-layer math
+# ---------------------------------------------------------------------------------------------------------------------
+def _attn_tail(x2d: torch.Tensor, hid: torch.Tensor, lw: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """AttentionLayer / RPEAttentionLayer tail + AttentionOutput (transformer.py:176-197, 435-438):
+       y = LN(linear(hid) + x);  out = LN(y + squeeze(relu(expand(y))))"""
+    y = ops.gemm(hid, lw["wo"], lw["bo"], residual=x2d)
+    y = ops.layernorm(y, lw["g1"], lw["b1"])
+    h = ops.gemm(y, lw["we"], lw["be"], relu=True)
+    z = ops.gemm(h, lw["ws"], lw["bs"], residual=y)
+    return ops.layernorm(z, lw["g2"], lw["b2"])
+
+
+def _pack_tail(layer: _TransformerLayerParams) -> Dict[str, torch.Tensor]:
+    a, o = layer.attention, layer.output
+    return dict(wo=_f32(a.linear.weight), bo=_f32(a.linear.bias), g1=_f32(a.norm.weight), b1=_f32(a.norm.bias),
+                we=_f32(o.expand.weight), be=_f32(o.expand.bias), ws=_f32(o.squeeze.weight), bs=_f32(o.squeeze.bias),
+                g2=_f32(o.norm.weight), b2=_f32(o.norm.bias))
+
+
+class GeometricTransformer(nn.Module):
+    """blocks = ['self', 'cross'] with parallel=False, as instantiated by the reference (coarse_point_matching.py:28-35,
+    transformer.py:633-641).  forward(feats0, embeddings0, feats1, embeddings1) -> (feats0, feats1)."""
+
+    def __init__(self, blocks, d_model, num_heads, dropout=None, activation_fn='ReLU', return_attention_scores=False,
+                 parallel=False):
+        super().__init__()
+        if list(blocks) != ['self', 'cross'] or parallel or return_attention_scores or dropout:
+            raise ValueError("sam6d_b200.GeometricTransformer supports the configuration SAM-6D uses: "
+                             "blocks=['self','cross'], parallel=False, dropout=None, no attention-score output")
+        if activation_fn != 'ReLU' or num_heads != NUM_HEADS or d_model != 256:
+            raise ValueError("sam6d_b200 kernels are built for d_model=256, num_heads=4, ReLU")
+        self.blocks = list(blocks)
+        self.d_model, self.num_heads = d_model, num_heads
+        self.layers = nn.ModuleList([_TransformerLayerParams(d_model, rpe=True), _TransformerLayerParams(d_model, rpe=False)])
+        self._packed = _Packed()
+
+    def _weights(self):
+        key = _param_key(self)
+        if self._packed.key != key:
+            C, H = self.d_model, self.num_heads
+            d = C // H
+            sa = self.layers[0].attention.attention
+            wq, bq = _f32(sa.proj_q.weight), _f32(sa.proj_q.bias)
+            wp = _f32(sa.proj_p.weight)
+            # u_h = W_p,h^T (W_q,h x + b_q,h): fold proj_p into the query side (one (C x C) matrix per head)
+            mu = [wp[h * d:(h + 1) * d, :].t().double() @ wq[h * d:(h + 1) * d, :].double() for h in range(H)]
+            cu = [wp[h * d:(h + 1) * d, :].t().double() @ bq[h * d:(h + 1) * d].double() for h in range(H)]
+            w_self = torch.cat([wq, _f32(sa.proj_k.weight), _f32(sa.proj_v.weight)] + [m.float() for m in mu], dim=0)
+            b_self = torch.cat([bq, _f32(sa.proj_k.bias), _f32(sa.proj_v.bias)] + [c.float() for c in cu], dim=0)
+            ca = self.layers[1].attention.attention
+            self._packed.w = dict(
+                w_self=w_self.contiguous(), b_self=b_self.contiguous(), tail_self=_pack_tail(self.layers[0]),
+                wq_c=_f32(ca.proj_q.weight), bq_c=_f32(ca.proj_q.bias),
+                wkv_c=torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_v.weight)], dim=0).contiguous(),
+                bkv_c=torch.cat([_f32(ca.proj_k.bias), _f32(ca.proj_v.bias)], dim=0).contiguous(),
+                tail_cross=_pack_tail(self.layers[1]))
+            self._packed.key = key
+        return self._packed.w
+
+    def _self_layer(self, x: torch.Tensor, emb: torch.Tensor, w) -> torch.Tensor:
+        B, S, C = x.shape
+        x2d = x.reshape(B * S, C)
+        ld = 3 * C + NUM_HEADS * C
+        qkvu = ops.gemm(x2d, w["w_self"], w["b_self"])                           # (B*S, q|k|v|u0..u3)
+        base, f = qkvu.data_ptr(), 4
+        sp = ops.rpe_scores(emb, None, u_ptr=base + 3 * C * f, u_ld=ld)          # (B,H,S,S)
+        hid = torch.empty(B * S, C, dtype=torch.float32, device=x.device)
+        ops.mha_raw(base, ld, S * ld, base + C * f, ld, S * ld, base + 2 * C * f, ld, S * ld, sp, B, NUM_HEADS, S, S,
+                    1.0 / math.sqrt(C // NUM_HEADS), hid.data_ptr(), C, S * C)
+        return _attn_tail(x2d, hid, w["tail_self"]).view(B, S, C)
+
+    def _cross_layer(self, x: torch.Tensor, mem: torch.Tensor, w) -> torch.Tensor:
+        B, S, C = x.shape
+        Sm = mem.shape[1]
+        x2d = x.reshape(B * S, C)
+        q = ops.gemm(x2d, w["wq_c"], w["bq_c"])
+        kv = ops.gemm(mem.reshape(B * Sm, C), w["wkv_c"], w["bkv_c"])
+        hid = torch.empty(B * S, C, dtype=torch.float32, device=x.device)
+        ops.mha_raw(q.data_ptr(), C, S * C, kv.data_ptr(), 2 * C, Sm * 2 * C, kv.data_ptr() + C * 4, 2 * C, Sm * 2 * C, None,
+                    B, NUM_HEADS, S, Sm, 1.0 / math.sqrt(C // NUM_HEADS), hid.data_ptr(), C, S * C)
+        return _attn_tail(x2d, hid, w["tail_cross"]).view(B, S, C)
+
+    @torch.no_grad()
+    def forward(self, feats0, embeddings0, feats1, embeddings1, masks0=None, masks1=None):
+        if masks0 is not None or masks1 is not None:
+            raise NotImplementedError("key masks are never used on the SAM-6D inference path")
+        w = self._weights()
+        feats0 = self._self_layer(feats0.contiguous(), embeddings0, w)
+        feats1 = self._self_layer(feats1.contiguous(), embeddings1, w)
+        feats0 = self._cross_layer(feats0, feats1, w)
+        feats1 = self._cross_layer(feats1, feats0, w)      # sequential: sees the updated feats0 (transformer.py:505-507)
+        return feats0, feats1
+
+
+# =====================================================================================================================
+class _SinusoidalBuffer(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        div_indices = torch.arange(0, d_model, 2).float()
+        self.register_buffer('div_term', torch.exp(div_indices * (-math.log(10000.0) / d_model)))
+
+
+class GeometricStructureEmbedding(nn.Module):
+    """forward(points (B,S,3)) -> (B,S,S,hidden_dim) pair embedding; cfg: sigma_d, sigma_a, angle_k, reduction_a, hidden_dim."""
+
+    def __init__(self, cfg):
+        super().__init__()
+        cfg = _cfg(cfg)
+        self.sigma_d, self.sigma_a, self.angle_k = cfg.sigma_d, cfg.sigma_a, cfg.angle_k
+        self.factor_a = 180.0 / (self.sigma_a * math.pi)
+        if cfg.reduction_a != 'max' or cfg.angle_k != 3 or cfg.hidden_dim != 256:
+            raise ValueError("sam6d_b200 kernels are built for reduction_a='max', angle_k=3, hidden_dim=256")
+        self.embedding = _SinusoidalBuffer(cfg.hidden_dim)
+        self.proj_d = nn.Linear(cfg.hidden_dim, cfg.hidden_dim)
+        self.proj_a = nn.Linear(cfg.hidden_dim, cfg.hidden_dim)
+        self._packed = _Packed()
+
+    def _weights(self):
+        key = _param_key(self)
+        if self._packed.key != key:
+            self._packed.w = dict(div=_f32(self.embedding.div_term), waT=_f32(self.proj_a.weight).t().contiguous(),
+                                  wdT=_f32(self.proj_d.weight).t().contiguous(),
+                                  bias=(_f32(self.proj_a.bias) + _f32(self.proj_d.bias)).contiguous())
+            self._packed.key = key
+        return self._packed.w
+
+    @torch.no_grad()
+    def get_embedding_indices(self, points):
+        T = ops.geo_indices(points.contiguous(), self.sigma_d, self.factor_a)
+        return T[..., 3], T[..., :3]
+
+    @torch.no_grad()
+    def forward(self, points):
+        w = self._weights()
+        T = ops.geo_indices(points.contiguous(), self.sigma_d, self.factor_a)
+        return ops.geo_embed_f32(T, w["div"], w["waT"], w["wdT"], w["bias"])
+
+
+# =====================================================================================================================
+# pose solvers (PEM/utils/model_utils.py)
+# =====================================================================================================================
+def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
+    """model_utils.py:53-66 (FPS + two gathers, channel-last)."""
+    idx = ops.furthest_point_sampling(pts.contiguous(), npoint)
+    p = ops.gather_rows(pts.contiguous(), idx)
+    f = ops.gather_rows(feats.contiguous(), idx)
+    return (p, f, idx) if return_index else (p, f)
+
+
+def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_feat=True):
+    """model_utils.py:114-136 -> (B,N,M) = normalize(f1) normalize(f2)^T / temp."""
+    if type != 'cosine':
+        raise NotImplementedError("SAM-6D uses sim_type='cosine'")
+    B, N, C = feat1.shape
+    M = feat2.shape[1]
+    f1 = ops.l2norm_rows(feat1.contiguous()) if normalize_feat else feat1.contiguous()
+    f2 = ops.l2norm_rows(feat2.contiguous()) if normalize_feat else feat2.contiguous()
+    A = torch.empty(B, N, M, dtype=torch.float32, device=feat1.device)
+    ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, A.data_ptr(), N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
+                 sC=N * M, alpha=1.0 / temp)
+    return A
+
+
+def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300, rand=None):
+    """model_utils.py:187-246.  `rand` (B, 3*n_proposal1) overrides the torch.rand draw (used by the parity tests to feed the
+    reference and this implementation the same uniforms); by default the call is the reference's own
+    torch.rand(B, n_proposal1*3, device=device), so the Philox stream position matches."""
+    B = pts1.shape[0]
+    if model_pts is None:
+        model_pts = pts2
+    W, w1 = ops.coarse_assign(atten.contiguous())
+    if rand is None:
+        rand = torch.rand(B, n_proposal1 * 3, device=pts1.device)
+    idx = ops.coarse_sample(W, rand.contiguous())
+    Rt, resid = ops.coarse_hypotheses(idx, pts1.contiguous(), pts2.contiguous())
+    top = ops.topk_smallest(resid, n_proposal2)
+    R, t, _ = ops.coarse_select(Rt, top, pts1.contiguous(), w1, model_pts.contiguous())
+    return R, t
+
+
+def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, temp=0.1, radius=None):
+    """model_utils.py:250-283.  Returns (R, t, pose_score); with `radius` also t * (radius + 1e-6)."""
+    if model_pts is None:
+        model_pts = pts2
+    pts1, pts2 = pts1.contiguous(), pts2.contiguous()
+    lab1, _, wts, pred = ops.fine_assign(atten.contiguous(), pts2, shift=1.0 / temp)
+    R, t = ops.weighted_procrustes(pred, pts1, wts, 0.0, 1e-5)
+    rad = radius if radius is not None else torch.ones(pts1.shape[0], device=pts1.device) - 1e-6
+    score, t_scaled = ops.pose_score(pts1, lab1, R, t, model_pts.contiguous(), rad.contiguous(), dis_thres)
+    return (R, t, score) if radius is None else (R, t, score, t_scaled)
+
+
+# =====================================================================================================================
+class CoarsePointMatching(nn.Module):
+    """forward(p1, f1, geo1, p2, f2, geo2, radius, end_points) -> end_points with init_R, init_t."""
+
+    def __init__(self, cfg, return_feat=False):
+        super().__init__()
+        self.cfg = _cfg(cfg)
+        self.return_feat = return_feat
+        self.nblock = self.cfg.nblock
+        self.in_proj = nn.Linear(self.cfg.input_dim, self.cfg.hidden_dim)
+        self.out_proj = nn.Linear(self.cfg.hidden_dim, self.cfg.out_dim)
+        self.bg_token = nn.Parameter(torch.randn(1, 1, self.cfg.hidden_dim) * .02)
+        self.transformers = nn.ModuleList([
+            GeometricTransformer(blocks=['self', 'cross'], d_model=self.cfg.hidden_dim, num_heads=4, dropout=None,
+                                 activation_fn='ReLU', return_attention_scores=False) for _ in range(self.nblock)])
+
+    def _embed(self, f):
+        B, n, C = f.shape
+        out = torch.empty(B, n + 1, self.cfg.hidden_dim, dtype=torch.float32, device=f.device)
+        out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
+        H = self.cfg.hidden_dim
+        ops.gemm_raw(f.data_ptr(), _f32(self.in_proj.weight).data_ptr(), _f32(self.in_proj.bias), 0, out.data_ptr() + H * 4,
+                     n, H, C, C, C, H, 0, batch=B, sA=n * C, sW=0, sC=(n + 1) * H)
+        return out
+
+    @torch.no_grad()
+    def forward(self, p1, f1, geo1, p2, f2, geo2, radius, end_points, rand=None):
+        if self.training:
+            raise NotImplementedError("sam6d_b200 implements the inference path (model.eval())")
+        f1 = self._embed(f1.contiguous())
+        f2 = self._embed(f2.contiguous())
+        for blk in self.transformers:
+            f1, f2 = blk(f1, geo1, f2, geo2)
+        B, S, H = f1.shape
+        wo, bo = _f32(self.out_proj.weight), _f32(self.out_proj.bias)
+        o1 = ops.gemm(f1.reshape(B * S, H), wo, bo).view(B, S, -1)
+        o2 = ops.gemm(f2.reshape(B * S, H), wo, bo).view(B, S, -1)
+        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat)
+        model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
+        init_R, init_t = compute_coarse_Rt(atten, p1, p2, model, self.cfg.nproposal1, self.cfg.nproposal2, rand=rand)
+        end_points['init_R'] = init_R
+        end_points['init_t'] = init_t
+        if self.return_feat:
+            return end_points, o1, o2
+        return end_points
+
+
+# =====================================================================================================================
+class _ConvBN(nn.Module):
+    """pytorch_utils.Conv2d(bn=True): `.conv` (1x1, no bias) + `.normlayer.bn` (PN2/pytorch_utils.py:87-137)"""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size=(1, 1), bias=False)
+        self.normlayer = nn.Module()
+        self.normlayer.bn = nn.BatchNorm2d(cout)
+
+    def folded(self):
+        bn = self.normlayer.bn
+        w = self.conv.weight.detach().double().reshape(self.conv.out_channels, -1)
+        s = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        return (w * s[:, None]).float().contiguous(), (bn.bias.detach().double() - bn.running_mean.detach().double() * s).float().contiguous()
+
+
+class _SharedMLP(nn.Module):
+    def __init__(self, dims):
+        super().__init__()
+        for i in range(len(dims) - 1):
+            self.add_module(f"layer{i}", _ConvBN(dims[i], dims[i + 1]))
+
+
+class _Conv1dParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, kernel_size=1, bias=True)
+
+
+class PositionalEncoding(nn.Module):
+    """fine_point_matching.py:90-125.  forward(pts (B,N,3)) -> (B,N,out_dim)."""
+
+    def __init__(self, out_dim, r1=0.1, r2=0.2, nsample1=32, nsample2=64, use_xyz=True, bn=True):
+        super().__init__()
+        if not (use_xyz and bn) or (nsample1, nsample2) != (32, 64):
+            raise ValueError("sam6d_b200 PositionalEncoding is built for the SAM-6D configuration")
+        self.r1, self.r2, self.ns1, self.ns2 = r1, r2, nsample1, nsample2
+        self.mlp1 = _SharedMLP([6, 32, 64, 128])
+        self.mlp2 = _SharedMLP([6, 32, 64, 128])
+        self.mlp3 = _Conv1dParams(256, out_dim)
+        self._packed = _Packed()
+
+    def _weights(self):
+        key = _param_key(self)
+        if self._packed.key != key:
+            w = {}
+            for name, mlp in (("m1", self.mlp1), ("m2", self.mlp2)):
+                packed = []
+                for j in range(3):
+                    wj, bj = getattr(mlp, f"layer{j}").folded()
+                    packed += [wj, bj]
+                w[name] = tuple(packed)
+            w["w3"] = _f32(self.mlp3.conv.weight).reshape(self.mlp3.conv.out_channels, -1).contiguous()
+            w["b3"] = _f32(self.mlp3.conv.bias)
+            self._packed.w, self._packed.key = w, key
+        return self._packed.w
+
+    @torch.no_grad()
+    def local_features(self, pts):
+        """the (B,N,256) two-scale max-pooled features before mlp3"""
+        w = self._weights()
+        pts = pts.contiguous()
+        B, N, _ = pts.shape
+        feat = torch.empty(B, N, 256, dtype=torch.float32, device=pts.device)
+        for r, ns, name, off in ((self.r1, self.ns1, "m1", 0), (self.r2, self.ns2, "m2", 128)):
+            idx, cnt = ops.ball_query(pts, pts, r, ns, return_count=True)
+            ops.pe_mlp_max(pts, idx, cnt, w[name], feat, off)
+        return feat
+
+    @torch.no_grad()
+    def forward(self, pts1, pts2=None):
+        if pts2 is not None and pts2 is not pts1:
+            raise NotImplementedError("SAM-6D always calls PE(pts) with a single cloud")
+        w = self._weights()
+        feat = self.local_features(pts1)
+        B, N, _ = feat.shape
+        return ops.gemm(feat.view(B * N, 256), w["w3"], w["b3"]).view(B, N, -1)
+
+
+class _LinearAttentionParams(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        self.proj_q = nn.Linear(d_model, d_model)
+        self.proj_k = nn.Linear(d_model, d_model)
+        self.proj_v = nn.Linear(d_model, d_model)
+        self.scale = nn.Parameter(torch.zeros(size=(1, 1, d_model)))
+
+
+class _LinearAttentionLayerParams(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        self.attention = _LinearAttentionParams(d_model)
+        self.linear = nn.Linear(d_model, d_model)
+        self.norm = nn.LayerNorm(d_model)
+
+
+class _LinearTransformerLayerParams(nn.Module):
+    def __init__(self, d_model):
+        super().__init__()
+        self.attention = _LinearAttentionLayerParams(d_model)
+        self.output = _AttentionOutputParams(d_model)
+
+
+class SparseToDenseTransformer(nn.Module):
+    """transformer.py:613-673 with with_bg_token=True, replace_bg_token=True (the SAM-6D configuration).
+    forward(dense_feats0 (B,N+1,C), embeddings0, fps_idx0, dense_feats1, embeddings1, fps_idx1) -> (dense0, dense1)."""
+
+    def __init__(self, d_model, sparse_blocks, num_heads=4, dropout=None, activation_fn='ReLU', parallel=False,
+                 focusing_factor=3, with_bg_token=True, replace_bg_token=True):
+        super().__init__()
+        if not (with_bg_token and replace_bg_token) or focusing_factor != 3:
+            raise ValueError("sam6d_b200 SparseToDenseTransformer is built for the SAM-6D configuration")
+        self.d_model = d_model
+        self.sparse_layer = GeometricTransformer(blocks=sparse_blocks, d_model=d_model, num_heads=num_heads, dropout=dropout,
+                                                 activation_fn=activation_fn, parallel=parallel, return_attention_scores=False)
+        self.dense_layer = _LinearTransformerLayerParams(d_model)
+        self._packed = _Packed()
+
+    def _weights(self):
+        key = _param_key(self.dense_layer)
+        if self._packed.key != key:
+            la = self.dense_layer.attention.attention
+            tail = dict(wo=_f32(self.dense_layer.attention.linear.weight), bo=_f32(self.dense_layer.attention.linear.bias),
+                        g1=_f32(self.dense_layer.attention.norm.weight), b1=_f32(self.dense_layer.attention.norm.bias),
+                        we=_f32(self.dense_layer.output.expand.weight), be=_f32(self.dense_layer.output.expand.bias),
+                        ws=_f32(self.dense_layer.output.squeeze.weight), bs=_f32(self.dense_layer.output.squeeze.bias),
+                        g2=_f32(self.dense_layer.output.norm.weight), b2=_f32(self.dense_layer.output.norm.bias))
+            self._packed.w = dict(
+                wq=_f32(la.proj_q.weight), bq=_f32(la.proj_q.bias),
+                wkv=torch.cat([_f32(la.proj_k.weight), _f32(la.proj_v.weight)], dim=0).contiguous(),
+                bkv=torch.cat([_f32(la.proj_k.bias), _f32(la.proj_v.bias)], dim=0).contiguous(),
+                sp_scale=torch.nn.functional.softplus(_f32(la.scale)).reshape(-1).contiguous(), tail=tail)
+            self._packed.key = key
+        return self._packed.w
+
+    def _sample_feats(self, dense_feats, idx_ext):
+        # quirk Q1 (transformer.py:651-658): the gather runs on the bg-prefixed sequence with the raw FPS index
+        return ops.gather_rows(dense_feats, idx_ext)
+
+    def _dense_layer(self, dense, sparse, w):
+        """LinearTransformerLayer on dense[:,1:,:] with memory sparse[:,1:,:]; returns the new (B,N+1,C) sequence."""
+        B, N1, C = dense.shape
+        N, J = N1 - 1, sparse.shape[1] - 1
+        f = 4
+        dev = dense.device
+        x_ptr, x_view = dense.data_ptr() + C * f, (N, N1 * C, C)          # rows 1..N of every proposal
+        q = torch.empty(B * N, C, dtype=torch.float32, device=dev)
+        ops.gemm_raw(x_ptr, w["wq"].data_ptr(), w["bq"], 0, q.data_ptr(), N, C, C, C, C, C, 0, batch=B, sA=N1 * C, sC=N * C)
+        kv = torch.empty(B * J, 2 * C, dtype=torch.float32, device=dev)
+        ops.gemm_raw(sparse.data_ptr() + C * f, w["wkv"].data_ptr(), w["bkv"], 0, kv.data_ptr(), J, 2 * C, C, C, C, 2 * C, 0,
+                     batch=B, sA=(J + 1) * C, sC=J * 2 * C)
+        ops.focus_rows_raw(q.data_ptr(), (B * N, 0, C), q.data_ptr(), (B * N, 0, C), w["sp_scale"], B * N, C)
+        ops.focus_rows_raw(kv.data_ptr(), (B * J, 0, 2 * C), kv.data_ptr(), (B * J, 0, 2 * C), w["sp_scale"], B * J, C)
+        KV = torch.empty(B, NUM_HEADS, 64, 64, dtype=torch.float32, device=dev)
+        KS = torch.empty(B, NUM_HEADS, 64, dtype=torch.float32, device=dev)
+        ops.linattn_kv_raw(kv.data_ptr(), 2 * C, J * 2 * C, kv.data_ptr() + C * f, 2 * C, J * 2 * C, B, NUM_HEADS, J, KV, KS)
+        x_att = torch.empty(B * N, C, dtype=torch.float32, device=dev)
+        ops.linattn_apply_raw(q.data_ptr(), N, N * C, C, KV, KS, B, NUM_HEADS, x_att.data_ptr(), N * C, C)
+        t = w["tail"]
+        y = torch.empty(B * N, C, dtype=torch.float32, device=dev)
+        ops.gemm_raw(x_att.data_ptr(), t["wo"].data_ptr(), t["bo"], x_ptr, y.data_ptr(), N, C, C, C, C, C, C, batch=B,
+                     sA=N * C, sC=N * C, sR=N1 * C)
+        y = ops.layernorm(y, t["g1"], t["b1"])
+        h = ops.gemm(y, t["we"], t["be"], relu=True)
+        z = ops.gemm(h, t["ws"], t["bs"], residual=y)
+        out = torch.empty(B, N1, C, dtype=torch.float32, device=dev)
+        ops.layernorm_raw(z.data_ptr(), (B * N, 0, C), out.data_ptr() + C * f, (N, N1 * C, C), t["g2"], t["b2"], B * N, C)
+        out[:, 0, :] = sparse[:, 0, :]                                      # replaced bg token (transformer.py:660-668)
+        return out
+
+    @torch.no_grad()
+    def forward(self, dense_feats0, embeddings0, fps_idx0, dense_feats1, embeddings1, fps_idx1, masks0=None, masks1=None):
+        w = self._weights()
+        ext0 = torch.cat([torch.zeros_like(fps_idx0[:, :1]), fps_idx0], dim=1).contiguous()
+        ext1 = torch.cat([torch.zeros_like(fps_idx1[:, :1]), fps_idx1], dim=1).contiguous()
+        feats0 = self._sample_feats(dense_feats0.contiguous(), ext0)
+        feats1 = self._sample_feats(dense_feats1.contiguous(), ext1)
+        feats0, feats1 = self.sparse_layer(feats0, embeddings0, feats1, embeddings1, masks0, masks1)
+        dense_feats0 = self._dense_layer(dense_feats0.contiguous(), feats0, w)
+        dense_feats1 = self._dense_layer(dense_feats1.contiguous(), feats1, w)
+        return dense_feats0, dense_feats1
+
+
+class FinePointMatching(nn.Module):
+    """forward(p1, f1, geo1, fps_idx1, p2, f2, geo2, fps_idx2, radius, end_points) -> end_points with pred_R/pred_t/pred_pose_score."""
+
+    def __init__(self, cfg, return_feat=False):
+        super().__init__()
+        self.cfg = _cfg(cfg)
+        self.return_feat = return_feat
+        self.nblock = self.cfg.nblock
+        self.in_proj = nn.Linear(self.cfg.input_dim, self.cfg.hidden_dim)
+        self.out_proj = nn.Linear(self.cfg.hidden_dim, self.cfg.out_dim)
+        self.bg_token = nn.Parameter(torch.randn(1, 1, self.cfg.hidden_dim) * .02)
+        self.PE = PositionalEncoding(self.cfg.hidden_dim, r1=self.cfg.pe_radius1, r2=self.cfg.pe_radius2)
+        self.transformers = nn.ModuleList([
+            SparseToDenseTransformer(self.cfg.hidden_dim, num_heads=4, sparse_blocks=['self', 'cross'], dropout=None,
+                                     activation_fn='ReLU', focusing_factor=self.cfg.focusing_factor, with_bg_token=True,
+                                     replace_bg_token=True) for _ in range(self.nblock)])
+
+    def _embed(self, f, pts):
+        """[bg_token ; in_proj(f) + PE(pts)] as one (B,N+1,H) sequence (fine_point_matching.py:46-50)"""
+        B, N, C = f.shape
+        H = self.cfg.hidden_dim
+        pw = self.PE._weights()
+        local = self.PE.local_features(pts)                                         # (B,N,256)
+        tmp = ops.gemm(f.reshape(B * N, C), _f32(self.in_proj.weight), _f32(self.in_proj.bias))
+        out = torch.empty(B, N + 1, H, dtype=torch.float32, device=f.device)
+        out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
+        ops.gemm_raw(local.data_ptr(), pw["w3"].data_ptr(), pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 4, N, H, 256, 256, 256,
+                     H, H, batch=B, sA=N * 256, sW=0, sC=(N + 1) * H, sR=N * H)
+        return out
+
+    @torch.no_grad()
+    def forward(self, p1, f1, geo1, fps_idx1, p2, f2, geo2, fps_idx2, radius, end_points):
+        if self.training:
+            raise NotImplementedError("sam6d_b200 implements the inference path (model.eval())")
+        p1, p2 = p1.contiguous(), p2.contiguous()
+        p1_ = ops.rigid_warp(p1, end_points['init_R'].contiguous(), end_points['init_t'].contiguous())
+        f1 = self._embed(f1.contiguous(), p1_)
+        f2 = self._embed(f2.contiguous(), p2)
+        for blk in self.transformers:
+            f1, f2 = blk(f1, geo1, fps_idx1, f2, geo2, fps_idx2)
+        B, S, H = f1.shape
+        wo, bo = _f32(self.out_proj.weight), _f32(self.out_proj.bias)
+        o1 = ops.gemm(f1.reshape(B * S, H), wo, bo).view(B, S, -1)
+        o2 = ops.gemm(f2.reshape(B * S, H), wo, bo).view(B, S, -1)
+        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat)
+        model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
+        pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
+        end_points['pred_R'] = pred_R
+        end_points['pred_t'] = t_scaled
+        end_points['pred_pose_score'] = score
+        if self.return_feat:
+            return end_points, o1, o2
+        return end_points
+
+
+# =====================================================================================================================
+DEFAULT_MODEL_CFG = dict(
+    coarse_npoint=196, fine_npoint=2048,
+    geo_embedding=dict(sigma_d=0.2, sigma_a=15, angle_k=3, reduction_a='max', hidden_dim=256),
+    coarse_point_matching=dict(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, temp=0.1, sim_type='cosine',
+                               normalize_feat=True, loss_dis_thres=0.15, nproposal1=6000, nproposal2=300),
+    fine_point_matching=dict(nblock=3, input_dim=256, hidden_dim=256, out_dim=256, pe_radius1=0.1, pe_radius2=0.2,
+                             focusing_factor=3, temp=0.1, sim_type='cosine', normalize_feat=True, loss_dis_thres=0.15),
+)  # PEM/config/base.yaml:17-54
+
+
+class Net(nn.Module):
+    """Pose_Estimation_Model `Net` (pose_estimation_model.py:11-53).
+
+    forward(end_points) consumes the reference's dict -- 'pts' (B,N,3), 'rgb', 'rgb_choose', 'model' (B,Nm,3), 'dense_po',
+    'dense_fo' -- and adds init_R, init_t, pred_R, pred_t, pred_pose_score.  The RGB backbone (`feature_extraction`, a timm
+    ViT-B in the reference) is pluggable: pass any module with the reference's ViTEncoder interface as
+    `feature_extraction`, or put the per-point features into end_points['dense_fm'] (B,N,256) directly.
+    """
+
+    def __init__(self, cfg=None, feature_extraction: Optional[nn.Module] = None):
+        super().__init__()
+        cfg = _cfg(cfg if cfg is not None else DEFAULT_MODEL_CFG)
+        self.cfg = cfg
+        self.coarse_npoint = cfg.coarse_npoint
+        self.fine_npoint = cfg.fine_npoint
+        if feature_extraction is not None:
+            self.feature_extraction = feature_extraction
+        self.geo_embedding = GeometricStructureEmbedding(cfg.geo_embedding)
+        self.coarse_point_matching = CoarsePointMatching(cfg.coarse_point_matching)
+        self.fine_point_matching = FinePointMatching(cfg.fine_point_matching)
+
+    def _features(self, end_points):
+        """ViTEncoder.forward, inference branch (feature_extraction.py:128-142)"""
+        if 'dense_fm' in end_points:
+            dense_fm = end_points['dense_fm']
+        elif hasattr(self, 'feature_extraction'):
+            dense_fm = self.feature_extraction.get_img_feats(end_points['rgb'], end_points['rgb_choose'])
+        else:
+            raise RuntimeError("Net needs end_points['dense_fm'] or a feature_extraction module for the RGB branch")
+        if 'dense_po' not in end_points or 'dense_fo' not in end_points:
+            raise RuntimeError("inference needs the template bank: end_points['dense_po'], end_points['dense_fo']")
+        dense_po = end_points['dense_po'].contiguous()
+        radius = ops.cloud_radius(dense_po)
+        dense_pm = ops.scale_by_radius(end_points['pts'].contiguous(), radius)
+        dense_po = ops.scale_by_radius(dense_po, radius)
+        return dense_pm, dense_fm.contiguous(), dense_po, end_points['dense_fo'].contiguous(), radius
+
+    @torch.no_grad()
+    def forward(self, end_points, rand=None):
+        if self.training:
+            raise NotImplementedError("sam6d_b200 implements the inference path: call model.eval()")
+        dense_pm, dense_fm, dense_po, dense_fo, radius = self._features(end_points)
+        B = dense_pm.size(0)
+        bg_point = torch.ones(B, 1, 3, dtype=torch.float32, device=dense_pm.device) * 100
+        sparse_pm, sparse_fm, fps_idx_m = sample_pts_feats(dense_pm, dense_fm, self.coarse_npoint, return_index=True)
+        geo_embedding_m = self.geo_embedding(torch.cat([bg_point, sparse_pm], dim=1))
+        sparse_po, sparse_fo, fps_idx_o = sample_pts_feats(dense_po, dense_fo, self.coarse_npoint, return_index=True)
+        geo_embedding_o = self.geo_embedding(torch.cat([bg_point, sparse_po], dim=1))
+        end_points = self.coarse_point_matching(sparse_pm, sparse_fm, geo_embedding_m, sparse_po, sparse_fo, geo_embedding_o,
+                                                radius, end_points, rand=rand)
+        end_points = self.fine_point_matching(dense_pm, dense_fm, geo_embedding_m, fps_idx_m, dense_po, dense_fo,
+                                              geo_embedding_o, fps_idx_o, radius, end_points)
+        return end_points

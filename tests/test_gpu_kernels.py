@@ -1,0 +1,365 @@
+"""GPU parity: every C-ABI kernel against the CPU oracle / plain torch fp32 on the same seeded inputs.
+
+Index-valued outputs (FPS, ball query, gathers, top-k, labels, template indices) must be bit-exact; floating-point outputs
+carry the tolerance written next to each check."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pem_oracle as po      # noqa: E402
+from oracle import pn2                   # noqa: E402
+from oracle import ism_oracle as io      # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from sam6d_b200 import ops as _ops
+    return _ops
+
+
+def G(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+# ------------------------------------------------------------------------------------------------- point cloud ops
+@pytest.mark.parametrize("b,n,m", [(3, 2048, 196), (2, 1000, 64), (2, 300, 40), (1, 4096, 128), (1, 5000, 50), (1, 37, 9)])
+def test_fps_exact(ops, b, n, m):
+    x = torch.randn(b, n, 3, generator=G(n))
+    ref = pn2.furthest_point_sampling(x, m)
+    got = ops.furthest_point_sampling(x.cuda(), m).cpu()
+    assert got.dtype == torch.int32
+    assert torch.equal(got, ref)
+
+
+def test_fps_duplicates_and_ties(ops):
+    # masks with < 2048 px are sampled with replacement upstream -> many exact duplicates
+    base = torch.randn(2, 300, 3, generator=G(5))
+    pick = torch.randint(0, 300, (2, 2048), generator=G(6))
+    x = torch.gather(base, 1, pick.unsqueeze(2).expand(2, 2048, 3)).contiguous()
+    assert torch.equal(ops.furthest_point_sampling(x.cuda(), 196).cpu(), pn2.furthest_point_sampling(x, 196))
+    # symmetric lattice: plenty of exact distance ties
+    g = torch.stack(torch.meshgrid(torch.arange(8.), torch.arange(8.), torch.arange(8.), indexing="ij"), -1).reshape(1, 512, 3)
+    assert torch.equal(ops.furthest_point_sampling(g.cuda(), 100).cpu(), pn2.furthest_point_sampling(g, 100))
+    ones = torch.ones(1, 100, 3)
+    assert ops.furthest_point_sampling(ones.cuda(), 5).cpu().tolist() == [[0, 0, 0, 0, 0]]
+
+
+def test_gather_and_group_exact(ops):
+    pts = torch.randn(2, 7, 300, generator=G(1))
+    idx = torch.randint(0, 300, (2, 50), generator=G(2), dtype=torch.int32)
+    assert torch.equal(ops.gather_points(pts.cuda(), idx.cuda()).cpu(), pn2.gather_points(pts, idx))
+    gi = torch.randint(0, 300, (2, 50, 16), generator=G(3), dtype=torch.int32)
+    assert torch.equal(ops.group_points(pts.cuda(), gi.cuda()).cpu(), pn2.group_points(pts, gi))
+    rows = torch.randn(2, 300, 256, generator=G(4))
+    got = ops.gather_rows(rows.cuda(), idx.cuda()).cpu()
+    assert torch.equal(got, torch.gather(rows, 1, idx.long().unsqueeze(2).expand(2, 50, 256)))
+    rows3 = torch.randn(2, 300, 3, generator=G(4))
+    got = ops.gather_rows(rows3.cuda(), idx.cuda()).cpu()
+    assert torch.equal(got, torch.gather(rows3, 1, idx.long().unsqueeze(2).expand(2, 50, 3)))
+
+
+@pytest.mark.parametrize("n,r,ns", [(2048, 0.1, 32), (2048, 0.2, 64), (1500, 0.15, 32), (100, 0.5, 64)])
+def test_ball_query_exact(ops, n, r, ns):
+    d = torch.randn(2, n, 3, generator=G(n + ns))
+    x = (d / d.norm(dim=2, keepdim=True) * (0.6 + 0.4 * torch.rand(2, n, 1, generator=G(1)))).contiguous()
+    ref = pn2.ball_query(x, x, r, ns)
+    got, cnt = ops.ball_query(x.cuda(), x.cuda(), r, ns, return_count=True)
+    assert torch.equal(got.cpu(), ref)
+    # cnt = number of distinct leading hits
+    d2 = ((x.unsqueeze(2) - x.unsqueeze(1)) ** 2).sum(-1)
+    approx = (d2 < r * r).sum(-1).clamp(max=ns)
+    assert (cnt.cpu() - approx).abs().max() <= 1
+    # empty balls -> zeros
+    far = torch.full((2, 5, 3), 50.0)
+    assert ops.ball_query(far.cuda(), x.cuda(), r, ns).abs().sum().item() == 0
+
+
+def test_native_layer_argument_errors(ops):
+    x = torch.randn(1, 64, 3)
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sampling(x, 8)                         # CPU tensor: "CPU not supported" in the reference
+    with pytest.raises(RuntimeError):
+        ops.furthest_point_sampling(x.cuda().double(), 8)         # dtype
+    with pytest.raises(RuntimeError):
+        ops.gather_points(torch.randn(1, 3, 64).cuda().transpose(1, 2), torch.zeros(1, 4, dtype=torch.int32).cuda())
+
+
+# ------------------------------------------------------------------------------------------------- dense algebra / rows
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 1792, 256), (1000, 512, 256), (77, 33, 19), (4096, 256, 512), (130, 64, 6)])
+def test_gemm(ops, M, N, K):
+    A = torch.randn(M, K, generator=G(1))
+    W = torch.randn(N, K, generator=G(2)) / math.sqrt(K)
+    bias = torch.randn(N, generator=G(3))
+    R = torch.randn(M, N, generator=G(4))
+    ref = torch.relu(A.double() @ W.double().t() * 0.5 + bias.double()) + R.double()
+    got = ops.gemm(A.cuda(), W.cuda(), bias.cuda(), residual=R.cuda(), relu=True, alpha=0.5).cpu()
+    torch.testing.assert_close(got.double(), ref, atol=2e-5, rtol=1e-5)     # fp32 accumulate over K <= 512
+
+
+def test_gemm_batched_strided(ops):
+    B, N, M, C = 3, 65, 70, 256
+    f1 = torch.randn(B, N, C, generator=G(1))
+    f2 = torch.randn(B, M, C, generator=G(2))
+    out = torch.empty(B, N, M).cuda()
+    a, w = f1.cuda(), f2.cuda()
+    ops.gemm_raw(a.data_ptr(), w.data_ptr(), None, 0, out.data_ptr(), N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
+                 sC=N * M, alpha=10.0)
+    torch.testing.assert_close(out.cpu(), 10.0 * f1 @ f2.transpose(1, 2), atol=2e-4, rtol=1e-5)
+
+
+def test_row_ops(ops):
+    x = torch.randn(500, 256, generator=G(1)) * 3 + 0.5
+    g, b = torch.randn(256, generator=G(2)), torch.randn(256, generator=G(3))
+    torch.testing.assert_close(ops.layernorm(x.cuda(), g.cuda(), b.cuda()).cpu(),
+                               torch.nn.functional.layer_norm(x, (256,), g, b, 1e-5), atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(ops.l2norm_rows(x.cuda()).cpu(), torch.nn.functional.normalize(x, dim=-1), atol=1e-6, rtol=1e-5)
+    x1024 = torch.randn(9, 1024, generator=G(4))
+    torch.testing.assert_close(ops.l2norm_rows(x1024.cuda()).cpu(), torch.nn.functional.normalize(x1024, dim=-1), atol=1e-6, rtol=1e-5)
+    # focus map (transformer.py:541-550)
+    scale = torch.nn.functional.softplus(0.2 * torch.randn(256, generator=G(5)))
+    q = torch.relu(x) + 1e-6
+    q = q / scale
+    qn = q.norm(dim=-1, keepdim=True)
+    q = q ** 3
+    ref = q / q.norm(dim=-1, keepdim=True) * qn
+    xc = x.cuda()
+    out = torch.empty_like(xc)
+    ops.focus_rows_raw(xc.data_ptr(), (500, 0, 256), out.data_ptr(), (500, 0, 256), scale.cuda(), 500, 256)
+    torch.testing.assert_close(out.cpu(), ref, atol=1e-5, rtol=2e-5)
+    # rigid warp, radius
+    p = torch.randn(2, 100, 3, generator=G(6))
+    R = po.random_rotation(2, G(7))
+    t = torch.randn(2, 3, generator=G(8))
+    torch.testing.assert_close(ops.rigid_warp(p.cuda(), R.cuda(), t.cuda()).cpu(), (p - t.unsqueeze(1)) @ R, atol=1e-5, rtol=1e-5)
+    rad = torch.norm(p, dim=2).max(1)[0]
+    torch.testing.assert_close(ops.cloud_radius(p.cuda()).cpu(), rad, atol=0, rtol=1e-6)
+    torch.testing.assert_close(ops.scale_by_radius(p.cuda(), rad.cuda()).cpu(), p / (rad.reshape(-1, 1, 1) + 1e-6), atol=0, rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- geometric embedding
+def _sparse_cloud(B, S, seed, scale=1.0, offset=0.0):
+    d = torch.randn(B, S - 1, 3, generator=G(seed))
+    pts = d / d.norm(dim=2, keepdim=True) * (0.5 + 0.5 * torch.rand(B, S - 1, 1, generator=G(seed + 1))) * scale + offset
+    return torch.cat([torch.ones(B, 1, 3) * 100, pts], dim=1).contiguous()
+
+
+def test_geo_indices(ops):
+    pts = _sparse_cloud(2, 197, 3)
+    d_ref, a_ref = po.geo_embedding_indices(pts)
+    T = ops.geo_indices(pts.cuda(), po.SIGMA_D, 180.0 / (po.SIGMA_A * math.pi)).cpu()
+    torch.testing.assert_close(T[..., 3], d_ref, atol=2e-4, rtol=1e-5)         # fp32 cancellation in x2 - 2xy + y2
+    # the neighbour *set* matters (max over k): compare sorted angle triplets, allow a vanishing fraction of knn ties
+    got, ref = T[..., :3].sort(dim=-1)[0], a_ref.sort(dim=-1)[0]
+    bad = ((got - ref).abs() > 2e-3).any(dim=-1).float().mean().item()
+    assert bad < 2e-3, f"{bad:.2e} of pairs differ in their angle triplet"
+
+
+def test_geo_embed(ops):
+    sd = po.make_state_dict(seed=2)
+    pts = _sparse_cloud(2, 64, 9)
+    ref = po.geo_embedding(sd, pts)
+    T = ops.geo_indices(pts.cuda(), po.SIGMA_D, 180.0 / (po.SIGMA_A * math.pi))
+    E = ops.geo_embed_f32(T, sd["geo_embedding.embedding.div_term"].cuda(), sd["geo_embedding.proj_a.weight"].t().contiguous().cuda(),
+                          sd["geo_embedding.proj_d.weight"].t().contiguous().cuda(),
+                          (sd["geo_embedding.proj_a.bias"] + sd["geo_embedding.proj_d.bias"]).cuda()).cpu()
+    err = (E - ref).abs()
+    assert (err > 5e-3).float().mean().item() < 2e-3
+    assert err.median().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------- attention
+def test_rpe_scores_and_mha(ops):
+    B, S, C, H = 2, 197, 256, 4
+    E = torch.randn(B, S, S, C, generator=G(1))
+    U = torch.randn(B, S, H, C, generator=G(2))
+    ref = torch.einsum("bnhc,bnmc->bhnm", U, E)
+    got = ops.rpe_scores(E.cuda(), U.cuda()).cpu()
+    torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-5)
+    got16 = ops.rpe_scores(E.cuda().bfloat16(), U.cuda()).cpu()
+    ref16 = torch.einsum("bnhc,bnmc->bhnm", U, E.bfloat16().float())
+    torch.testing.assert_close(got16, ref16, atol=2e-4, rtol=1e-5)
+    q = torch.randn(B, S, C, generator=G(3))
+    k = torch.randn(B, 150, C, generator=G(4))
+    v = torch.randn(B, 150, C, generator=G(5))
+    bias = torch.randn(B, H, S, 150, generator=G(6))
+    qh, kh, vh = (t.view(B, -1, H, 64).permute(0, 2, 1, 3) for t in (q, k, v))
+    att = torch.softmax((qh @ kh.transpose(-1, -2) + bias) / 8.0, dim=-1)
+    ref = (att @ vh).permute(0, 2, 1, 3).reshape(B, S, C)
+    qc, kc, vc = q.cuda(), k.cuda(), v.cuda()
+    out = torch.empty(B, S, C).cuda()
+    ops.mha_raw(qc.data_ptr(), C, S * C, kc.data_ptr(), C, 150 * C, vc.data_ptr(), C, 150 * C, bias.cuda(), B, H, S, 150, 0.125,
+                out.data_ptr(), C, S * C)
+    torch.testing.assert_close(out.cpu(), ref, atol=2e-5, rtol=1e-4)
+
+
+def test_linear_attention(ops):
+    sd = po.make_state_dict(seed=4)
+    p = "fine_point_matching.transformers.0.dense_layer.attention.attention"
+    B, N, J, C = 2, 300, 50, 256
+    xq = torch.randn(B, N, C, generator=G(1))
+    xkv = torch.randn(B, J, C, generator=G(2))
+    ref = po.linear_attention(sd, p, xq, xkv)
+    q = torch.nn.functional.linear(xq, sd[p + ".proj_q.weight"], sd[p + ".proj_q.bias"]).cuda().contiguous()
+    k = torch.nn.functional.linear(xkv, sd[p + ".proj_k.weight"], sd[p + ".proj_k.bias"]).cuda().contiguous()
+    v = torch.nn.functional.linear(xkv, sd[p + ".proj_v.weight"], sd[p + ".proj_v.bias"]).cuda().contiguous()
+    sp = torch.nn.functional.softplus(sd[p + ".scale"]).reshape(-1).cuda()
+    ops.focus_rows_raw(q.data_ptr(), (B * N, 0, C), q.data_ptr(), (B * N, 0, C), sp, B * N, C)
+    ops.focus_rows_raw(k.data_ptr(), (B * J, 0, C), k.data_ptr(), (B * J, 0, C), sp, B * J, C)
+    KV = torch.empty(B, 4, 64, 64).cuda()
+    KS = torch.empty(B, 4, 64).cuda()
+    ops.linattn_kv_raw(k.data_ptr(), C, J * C, v.data_ptr(), C, J * C, B, 4, J, KV, KS)
+    x = torch.empty(B, N, C).cuda()
+    ops.linattn_apply_raw(q.data_ptr(), N, N * C, C, KV, KS, B, 4, x.data_ptr(), N * C, C)
+    torch.testing.assert_close(x.cpu(), ref, atol=1e-4, rtol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------- coarse pose pieces
+def _score_matrix(B, S, seed, peak=6.0):
+    """cosine/temp-like matrix in [-10,10] with a planted permutation so that labels are decisive"""
+    g = G(seed)
+    A = torch.rand(B, S, S, generator=g) * 4 - 2
+    for b in range(B):
+        perm = torch.randperm(S - 1, generator=g) + 1
+        keep = torch.rand(S - 1, generator=g) < 0.8
+        rows = torch.arange(1, S)[keep]
+        A[b, rows, perm[keep]] += peak
+        A[b, torch.arange(1, S)[~keep], 0] += peak
+    return A.clamp(-10, 10).contiguous()
+
+
+def test_coarse_assign_sample(ops):
+    A = _score_matrix(3, 197, 1)
+    inner, w1, _, _, _ = po.soft_assignment(A)
+    ref = inner.reshape(3, -1) ** 1.5
+    W, w1g = ops.coarse_assign(A.cuda())
+    assert torch.equal(w1g.cpu(), w1)
+    torch.testing.assert_close(W.cpu(), ref, atol=1e-7, rtol=2e-5)
+    # cdf + searchsorted on identical weights must give identical indices (double accumulation like the CPU cumsum)
+    rand = torch.rand(3, 18000, generator=G(2))
+    cdf = torch.cumsum(ref, dim=1)
+    cdf = cdf / (cdf[:, -1].unsqueeze(1) + 1e-8)
+    idx_ref = torch.searchsorted(cdf, rand)
+    idx = ops.coarse_sample(ref.cuda().contiguous(), rand.cuda()).cpu()
+    mism = (idx.long() != idx_ref).float().mean().item()
+    assert mism < 1e-3, f"searchsorted mismatch fraction {mism}"
+
+
+def test_hypotheses_topk_select(ops):
+    B, n, n1, n2, nm = 2, 196, 6000, 300, 1024
+    g = G(3)
+    pts2 = torch.randn(B, n, 3, generator=g) * 0.4
+    R = po.random_rotation(B, g)
+    t = torch.randn(B, 3, generator=g) * 0.2
+    pts1 = pts2 @ R.transpose(1, 2) + t.unsqueeze(1) + 0.002 * torch.randn(B, n, 3, generator=g)
+    model = torch.cat([pts2, torch.randn(B, nm - n, 3, generator=g) * 0.4], dim=1).contiguous()
+    i1 = torch.randint(0, n, (B, n1 * 3), generator=g)
+    # 70% correct correspondences, 30% random
+    i2 = torch.where(torch.rand(B, n1 * 3, generator=g) < 0.7, i1, torch.randint(0, n, (B, n1 * 3), generator=g))
+    idx = (i1 * n + i2).int()
+    p1 = torch.gather(pts1, 1, i1.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
+    p2 = torch.gather(pts2, 1, i2.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
+    Rs, ts = po.weighted_procrustes(p2, p1, None, weight_thresh=0.5)
+    resid_ref = torch.norm((p1 - ts.unsqueeze(1)) @ Rs - p2, dim=2).mean(1).reshape(B, n1)
+    Rt, resid = ops.coarse_hypotheses(idx.cuda(), pts1.cuda(), pts2.cuda())
+    Rt, resid = Rt.cpu(), resid.cpu()
+    # degenerate triplets (repeated correspondences -> rank-deficient H) have no unique rotation in any SVD: exclude them
+    tri1 = i1.reshape(B, n1, 3)
+    tri2 = i2.reshape(B, n1, 3)
+    distinct = ((tri1[..., 0] != tri1[..., 1]) & (tri1[..., 0] != tri1[..., 2]) & (tri1[..., 1] != tri1[..., 2]) &
+                (tri2[..., 0] != tri2[..., 1]) & (tri2[..., 0] != tri2[..., 2]) & (tri2[..., 1] != tri2[..., 2]))
+    assert distinct.float().mean() > 0.9
+    dR = (Rt[..., :9].reshape(B, n1, 3, 3) - Rs.reshape(B, n1, 3, 3)).abs().amax(dim=(2, 3))
+    dt = (Rt[..., 9:] - ts.reshape(B, n1, 3)).abs().amax(dim=2)
+    assert dR[distinct].quantile(0.999).item() < 2e-3 and dR[distinct].median().item() < 1e-5
+    assert dt[distinct].quantile(0.999).item() < 2e-3
+    torch.testing.assert_close(resid[distinct], resid_ref[distinct], atol=2e-5, rtol=1e-3)
+    # top-k: same set as torch.topk on the same values, ascending (value, index) order
+    top = ops.topk_smallest(resid.cuda(), n2).cpu().long()
+    vals = torch.gather(resid, 1, top)
+    assert (vals[:, 1:] >= vals[:, :-1]).all()
+    ref_vals = torch.topk(resid, n2, dim=1, largest=False)[0]
+    assert torch.equal(vals, ref_vals)
+    # selection: score every retained hypothesis like the reference and take the first maximum
+    w1 = (torch.rand(B, n, generator=g) < 0.8).float()
+    Rsel = torch.gather(Rt[..., :9], 1, top.unsqueeze(2).expand(B, n2, 9)).reshape(B, n2, 3, 3)
+    tsel = torch.gather(Rt[..., 9:], 1, top.unsqueeze(2).expand(B, n2, 3)).reshape(B, n2, 1, 3)
+    tp = ((pts1.unsqueeze(1) - tsel) @ Rsel).reshape(B * n2, -1, 3)
+    mp = model.unsqueeze(1).repeat(1, n2, 1, 1).reshape(B * n2, -1, 3)
+    dis = torch.sqrt(po.pairwise_sqdist(tp, mp)).min(2)[0].reshape(B, n2, -1)
+    sc_ref = w1.unsqueeze(1).sum(2) / ((dis * w1.unsqueeze(1)).sum(2) + 1e-8)
+    Rb, tb, sc = ops.coarse_select(Rt.cuda(), top.int().cuda(), pts1.cuda(), w1.cuda(), model.cuda())
+    torch.testing.assert_close(sc.cpu(), sc_ref, atol=0, rtol=2e-4)
+    best = sc.cpu().max(1)[1]
+    torch.testing.assert_close(Rb.cpu(), Rsel[torch.arange(B), best], atol=0, rtol=0)
+    torch.testing.assert_close(tb.cpu(), tsel[torch.arange(B), best, 0], atol=0, rtol=0)
+    # and the chosen pose is the planted one
+    torch.testing.assert_close(Rb.cpu(), R, atol=2e-2, rtol=0)
+
+
+def test_procrustes_degenerate_is_finite(ops):
+    # all three correspondences identical / two identical: R must still be a proper rotation
+    pts1 = torch.randn(1, 10, 3, generator=G(1))
+    pts2 = torch.randn(1, 10, 3, generator=G(2))
+    idx = torch.tensor([[3 * 10 + 4] * 3 + [3 * 10 + 4, 3 * 10 + 4, 5 * 10 + 6] + [11, 23, 35]], dtype=torch.int32)
+    Rt, resid = ops.coarse_hypotheses(idx.cuda(), pts1.cuda(), pts2.cuda())
+    R = Rt.cpu()[0, :, :9].reshape(3, 3, 3)
+    assert torch.isfinite(R).all() and torch.isfinite(resid).all()
+    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand(3, 3, 3), atol=1e-5, rtol=0)
+    torch.testing.assert_close(torch.det(R), torch.ones(3), atol=1e-5, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------- fine stage pieces
+def test_positional_encoding_kernel(ops):
+    from sam6d_b200.pem import PositionalEncoding
+    sd = po.make_state_dict(seed=5)
+    pe = PositionalEncoding(256).cuda().eval()
+    pe.load_state_dict({k[len("fine_point_matching.PE."):]: v for k, v in sd.items() if k.startswith("fine_point_matching.PE.")})
+    inp = po.make_inputs(B=2, n=2048, seed=5)
+    pts = inp["dense_po"] / (torch.norm(inp["dense_po"], dim=2).max(1)[0].reshape(-1, 1, 1) + 1e-6)
+    ref = po.positional_encoding(sd, pts)
+    got = pe(pts.cuda()).cpu()
+    torch.testing.assert_close(got, ref, atol=5e-4, rtol=1e-4)
+
+
+def test_fine_assign_procrustes_score(ops):
+    B, S, nm = 2, 513, 256
+    A = _score_matrix(B, S, 7, peak=8.0)
+    g = G(8)
+    pts2 = torch.randn(B, S - 1, 3, generator=g) * 0.4
+    R = po.random_rotation(B, g)
+    t = torch.randn(B, 3, generator=g) * 0.1
+    pts1 = pts2 @ R.transpose(1, 2) + t.unsqueeze(1)
+    model = pts2[:, :nm].contiguous()
+    Rr, tr, sr, dbg = po.fine_Rt(A, pts1, pts2, model, return_debug=True)
+    lab1, lab2, wts, pred = ops.fine_assign(A.cuda(), pts2.cuda(), shift=10.0)
+    assert torch.equal(lab1.cpu()[:, 1:].long(), dbg["lab1"])
+    assert torch.equal(lab2.cpu()[:, 1:].long(), dbg["lab2"])
+    torch.testing.assert_close(wts.cpu(), dbg["wts"], atol=1e-6, rtol=2e-4)
+    torch.testing.assert_close(pred.cpu(), dbg["pred"], atol=1e-5, rtol=1e-4)
+    Rg, tg = ops.weighted_procrustes(pred, pts1.cuda(), wts)
+    torch.testing.assert_close(Rg.cpu(), Rr, atol=1e-4, rtol=0)
+    torch.testing.assert_close(tg.cpu(), tr, atol=1e-4, rtol=0)
+    radius = torch.tensor([0.7, 1.3])
+    score, ts = ops.pose_score(pts1.cuda(), lab1, Rg, tg, model.cuda(), radius.cuda(), 0.15)
+    torch.testing.assert_close(score.cpu(), sr, atol=2e-3, rtol=0)
+    torch.testing.assert_close(ts.cpu(), tr * (radius.reshape(-1, 1) + 1e-6), atol=2e-4, rtol=0)
+
+
+# ------------------------------------------------------------------------------------------------- ISM template scoring
+@pytest.mark.parametrize("P,O,T", [(64, 8, 42), (200, 21, 42), (5, 1, 3)])
+def test_template_score(ops, P, O, T):
+    from sam6d_b200 import ism
+    q, r = io.make_descriptors(P=P, O=O, T=T, C=1024, seed=P)
+    idx_sel, pred_obj, sem, best_t, scores, per_obj = io.compute_semantic_score(q, r)
+    sim = ism.PairwiseSimilarity()(q.cuda(), r.cuda()).cpu()
+    torch.testing.assert_close(sim, scores, atol=2e-6, rtol=1e-5)
+    g_sel, g_obj, g_sem, g_t = ism.compute_semantic_score(q.cuda(), r.cuda())
+    assert torch.equal(g_sel.cpu(), idx_sel)
+    assert torch.equal(g_obj.cpu(), pred_obj)                     # bit-exact argmax object
+    assert torch.equal(g_t.cpu(), best_t)                         # bit-exact argmax template indices
+    assert g_t.dtype == torch.int64 and g_obj.dtype == torch.int64
+    torch.testing.assert_close(g_sem.cpu(), sem, atol=2e-6, rtol=1e-5)
