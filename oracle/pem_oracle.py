@@ -232,8 +232,16 @@ def coarse_Rt(atten, pts1, pts2, model_pts, rand: Optional[torch.Tensor] = None,
     R = torch.gather(Rsel, 1, best.reshape(B, 1, 1, 1).repeat(1, 1, 3, 3)).squeeze(1)
     t = torch.gather(tsel, 1, best.reshape(B, 1, 1, 1).repeat(1, 1, 1, 3)).squeeze(2).squeeze(1)
     if return_debug:
-        return R, t, dict(score=score, cdf=cdf, idx=idx, w1=w1, Rs=Rs, ts=ts.squeeze(2), resid=resid,
-                          top=top, sel_scores=scores, best=best)
+        # a hypothesis is rank-deficient when a correspondence repeats inside its triplet: H then has one singular value
+        # above fp32 noise and the reference's rotation is decided by LAPACK on rounding noise ("Parity")
+        tri1, tri2 = i1.reshape(B, n1, 3), i2.reshape(B, n1, 3)
+        rep = lambda a: (a[..., 0] == a[..., 1]) | (a[..., 0] == a[..., 2]) | (a[..., 1] == a[..., 2])  # noqa: E731
+        degenerate = rep(tri1) | rep(tri2)
+        win = torch.gather(top, 1, best.unsqueeze(1)).squeeze(1)
+        return R, t, dict(score=score, cdf=cdf, idx=idx, w1=w1, Rs=Rs, ts=ts.squeeze(2), resid=resid, top=top,
+                          sel_scores=scores, best=best, degenerate=degenerate,
+                          winner_degenerate=torch.gather(degenerate, 1, win.unsqueeze(1)).squeeze(1),
+                          best_score=scores.max(1)[0])
     return R, t
 
 
@@ -269,10 +277,13 @@ def coarse_features(sd: SD, f1, geo1, f2, geo2, prefix: str = "coarse_point_matc
 
 
 def coarse_point_matching(sd: SD, p1, f1, geo1, p2, f2, geo2, radius, model,
-                          rand: Optional[torch.Tensor] = None, prefix: str = "coarse_point_matching"):
+                          rand: Optional[torch.Tensor] = None, prefix: str = "coarse_point_matching",
+                          return_debug: bool = False):
     f1, f2 = coarse_features(sd, f1, geo1, f2, geo2, prefix)
     atten = feature_similarity(_lin(sd, prefix + ".out_proj", f1), _lin(sd, prefix + ".out_proj", f2))
-    init_R, init_t = coarse_Rt(atten, p1, p2, model / (radius.reshape(-1, 1, 1) + 1e-6), rand)
+    init_R, init_t, dbg = coarse_Rt(atten, p1, p2, model / (radius.reshape(-1, 1, 1) + 1e-6), rand, return_debug=True)
+    if return_debug:
+        return init_R, init_t, atten, dbg
     return init_R, init_t, atten
 
 
@@ -413,14 +424,16 @@ def pem_forward(sd: SD, pts, dense_fm, dense_po, dense_fo, model,
     geo_m = geo_embedding(sd, torch.cat([bg_point, sp_m], dim=1))
     sp_o, sf_o, idx_o = sample_pts_feats(dense_po, dense_fo, coarse_npoint)
     geo_o = geo_embedding(sd, torch.cat([bg_point, sp_o], dim=1))
-    init_R, init_t, atten_c = coarse_point_matching(sd, sp_m, sf_m, geo_m, sp_o, sf_o, geo_o, radius, model, rand)
+    init_R, init_t, atten_c, cdbg = coarse_point_matching(sd, sp_m, sf_m, geo_m, sp_o, sf_o, geo_o, radius, model, rand,
+                                                          return_debug=True)
     pred_R, pred_t, score, atten_f = fine_point_matching(
         sd, dense_pm, dense_fm, geo_m, idx_m, dense_po, dense_fo, geo_o, idx_o, radius, model,
         init_R, init_t, return_atten=True)
     out = dict(init_R=init_R, init_t=init_t, pred_R=pred_R, pred_t=pred_t, pred_pose_score=score)
     if return_stages:
         out.update(fps_idx_m=idx_m, fps_idx_o=idx_o, sparse_pm=sp_m, sparse_po=sp_o, geo_m=geo_m, geo_o=geo_o,
-                   atten_coarse=atten_c, atten_fine=atten_f, radius=radius)
+                   atten_coarse=atten_c, atten_fine=atten_f, radius=radius,
+                   init_degenerate=cdbg["winner_degenerate"], init_score=cdbg["best_score"])
     return out
 
 

@@ -52,8 +52,9 @@ static inline float sqdist_ref(float x1, float y1, float z1, float x2, float y2,
  * The reference runs one CTA of `bs` threads per cloud: thread t scans
  * k = t, t+bs, ... keeping (best, besti) under a strict '>' (first k wins a
  * tie inside a thread), then a shared-memory tree reduce where slot t absorbs
- * slot t+s only if strictly greater (lower t wins a tie).  Net effect on exact
- * ties: smallest (k mod bs) wins, then smallest k.  We emulate the threads.
+ * slot t+s only if strictly greater (slot t wins a tie).  Net effect on exact
+ * ties: the smallest BIT-REVERSED (k mod bs) wins, then the smallest k.  We emulate
+ * the threads and the tree literally.
  */
 void pn2_oracle_fps(const float *xyz, int b, int n, int m, int32_t *idx) {
   if (m <= 0) return;

@@ -3,7 +3,7 @@
 //
 // Index outputs are bit-exact with the reference kernels: the squared-distance expression is
 // evaluated with the same contraction nvcc applies there (FMUL, FFMA, FFMA) and argmax ties
-// follow the reference's reduction order (smallest k mod block_size, then smallest k).
+// follow the reference's reduction tree (smallest bit-reversed k mod block_size, then smallest k).
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -22,10 +22,13 @@ struct FpsCand {
   int k;
 };
 
-// total order equivalent to the reference's per-thread scan + shared-memory tree
+// Total order equivalent to the reference's per-thread scan + shared-memory tree (sampling_gpu.cu:64-70,113-170).
+// Thread t = k mod block_size keeps its first maximal k (strict '>').  The tree then folds slot t+s into slot t for
+// s = bs/2 ... 1 and a tie keeps slot t, so between two tied threads the one with a 0 at the LOWEST differing bit of
+// t survives: ties go to the smallest bit-reversed thread id, then to the smallest k.
 __device__ __forceinline__ bool fps_better(float d2, int k2, float d1, int k1, int bs_mask) {
   if (d2 != d1) return d2 > d1;
-  int t2 = k2 & bs_mask, t1 = k1 & bs_mask;
+  unsigned t2 = __brev((unsigned)(k2 & bs_mask)), t1 = __brev((unsigned)(k1 & bs_mask));
   if (t2 != t1) return t2 < t1;
   return k2 < k1;
 }

@@ -251,7 +251,7 @@ def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_
     return A
 
 
-def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300, rand=None):
+def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300, rand=None, return_scores=False):
     """model_utils.py:187-246.  `rand` (B, 3*n_proposal1) overrides the torch.rand draw (used by the parity tests to feed the
     reference and this implementation the same uniforms); by default the call is the reference's own
     torch.rand(B, n_proposal1*3, device=device), so the Philox stream position matches."""
@@ -264,7 +264,9 @@ def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_pro
     idx = ops.coarse_sample(W, rand.contiguous())
     Rt, resid = ops.coarse_hypotheses(idx, pts1.contiguous(), pts2.contiguous())
     top = ops.topk_smallest(resid, n_proposal2)
-    R, t, _ = ops.coarse_select(Rt, top, pts1.contiguous(), w1, model_pts.contiguous())
+    R, t, scores = ops.coarse_select(Rt, top, pts1.contiguous(), w1, model_pts.contiguous())
+    if return_scores:
+        return R, t, scores          # (B, n_proposal2) selection scores of the retained hypotheses
     return R, t
 
 
@@ -319,7 +321,8 @@ class CoarsePointMatching(nn.Module):
         o2 = ops.gemm(f2.reshape(B * S, H), wo, bo).view(B, S, -1)
         atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
-        init_R, init_t = compute_coarse_Rt(atten, p1, p2, model, self.cfg.nproposal1, self.cfg.nproposal2, rand=rand)
+        init_R, init_t, self.last_select_scores = compute_coarse_Rt(atten, p1, p2, model, self.cfg.nproposal1,
+                                                                    self.cfg.nproposal2, rand=rand, return_scores=True)
         end_points['init_R'] = init_R
         end_points['init_t'] = init_t
         if self.return_feat:

@@ -26,16 +26,18 @@ def test_fps_basic_and_ties():
 
 
 def test_fps_duplicates_tie_rule():
-    # all-identical points: every distance ties at 0 -> (k mod bs) smallest, then smallest k -> 0
+    # all-identical points: every distance ties at 0 -> slot 0 survives the tree -> 0
     x = torch.ones(1, 100, 3)
     idx = pn2.furthest_point_sampling(x, 5)
     assert idx.tolist() == [[0, 0, 0, 0, 0]]
-    # two far points tie exactly: 1 and 65 with bs = 64 share thread 1; smallest k wins
+    # exact ties: 1 and 65 share thread 1 (bs = 64) -> smallest k; thread 2 (bit-reversed 16) beats thread 1
+    # (bit-reversed 32) because the tree folds slot t+s into slot t and a tie keeps slot t
     x = torch.zeros(1, 100, 3)
     x[0, 1] = x[0, 65] = torch.tensor([1.0, 0, 0])
-    x[0, 3] = torch.tensor([1.0, 0, 0])               # thread 3 loses to thread 1
     assert pn2.lib().pn2_oracle_block_size(100) == 64
     assert pn2.furthest_point_sampling(x, 2).tolist() == [[0, 1]]
+    x[0, 2] = torch.tensor([1.0, 0, 0])
+    assert pn2.furthest_point_sampling(x, 2).tolist() == [[0, 2]]
 
 
 def test_ball_query_semantics():

@@ -125,6 +125,8 @@ def run_case(mods, tag, B, n, coarse_npoint, seed, out_dir, store_inputs):
         geo_m_sum=r["geo_m"].double().sum(dim=(1, 2)).float(),
         init_R=r["init_R"], init_t=r["init_t"], pred_R=r["pred_R"], pred_t=r["pred_t"],
         pred_pose_score=r["pred_pose_score"],
+        # is the reference's winning pose hypothesis rank-deficient (its rotation decided by SVD rounding noise)?
+        init_degenerate=o["init_degenerate"], init_score=o["init_score"],
         atten_coarse=o["atten_coarse"] if S <= 64 else o["atten_coarse"][:, :8, :].clone(),
     )
     if store_inputs:
@@ -142,7 +144,7 @@ def main():
     # small: inputs stored in the fixture; runs in seconds everywhere
     run_case(mods, "small", B=2, n=256, coarse_npoint=32, seed=3, out_dir=out_dir, store_inputs=True)
     # full BASELINE shapes for one proposal pair: inputs regenerated from the seed
-    run_case(mods, "full", B=2, n=2048, coarse_npoint=196, seed=1, out_dir=out_dir, store_inputs=False)
+    run_case(mods, "full", B=4, n=2048, coarse_npoint=196, seed=1, out_dir=out_dir, store_inputs=False)
 
 
 if __name__ == "__main__":
