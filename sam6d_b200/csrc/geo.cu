@@ -80,7 +80,9 @@ __global__ void __launch_bounds__(256) geo_indices_kernel(const float* __restric
       float cy = rz[k] * ax - rx[k] * az;
       float cz = rx[k] * ay - ry[k] * ax;
       float sinv = sqrtf(cx * cx + cy * cy + cz * cz);
-      float cosv = rx[k] * ax + ry[k] * ay + rz[k] * az;
+      // + 0.0f: torch.sum starts from +0, so an all-(-0) product sum (anchor == query, negative ref vector) is +0 there and
+      // atan2(0, +0) = 0; without it the FMA chain yields -0 and atan2f(0, -0) = pi
+      float cosv = (rx[k] * ax + ry[k] * ay + rz[k] * az) + 0.0f;
       a[k] = atan2f(sinv, cosv) * factor_a;
     }
     o.x = a[0]; o.y = a[1]; o.z = a[2];
