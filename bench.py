@@ -110,6 +110,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core exact path")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -129,7 +131,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     B = args.batch
 
-    net = Net().to(dev).eval()
+    net = Net(precision=args.precision).to(dev).eval()
     net.load_state_dict(po.make_state_dict(seed=1), strict=True)
     keys = ("pts", "dense_fm", "dense_po", "dense_fo", "model")
     host = [{k: v.pin_memory() for k, v in po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=100 + rank * 7 + s).items()
@@ -186,6 +188,14 @@ def main():
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
+    if os.environ.get("SAM6D_PROFILE_ONE_STEP"):
+        # ncu --profile-from-start off: capture exactly one warmed-up step
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step_resident(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -202,7 +212,8 @@ def main():
     if rank == 0:
         pk = peaks()
         S = net.coarse_npoint + 1
-        e_bytes = B * S * S * 256 * 4                  # fp32 geometric embedding streamed once per launch
+        e_size = 2 if args.precision == "bf16" else 4
+        e_bytes = B * S * S * 256 * e_size             # geometric embedding streamed once per launch
         alg_bytes = e_bytes + B * S * 1024 * 4 + B * 4 * S * S * 4
         k_avg_ms = sum(kms) / len(kms)
         achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
@@ -214,14 +225,15 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
-            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
             config=dict(workload=WORKLOAD, proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
                         feat_dim=C_FEAT, model_points=N_MODEL, parallelism=f"proposal-sharded x{world}, 1 all-gather of poses",
                         cache="inputs+intermediates per step (>1 GB) exceed the 126 MB L2; two input sets alternate"),
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=world * B * sdist.POSE_FLOATS * 4,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=launches,
-            roofline=dict(kernel="rpe_scores_kernel<float> (PEM RPE attention, streams the geometric embedding)", bound="hbm",
+            roofline=dict(kernel=f"rpe_scores_kernel<{'bf16' if args.precision == 'bf16' else 'float'}> (PEM RPE attention, streams the geometric embedding)", bound="hbm",
                           achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                           peak_source=pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if pk["source"] == "measured" else "fallback 6650 GB/s",
                           algorithmic_bytes_per_launch=alg_bytes, launches_timed=len(kms), avg_launch_ms=k_avg_ms,

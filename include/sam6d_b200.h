@@ -54,6 +54,12 @@ int sam6d_gemm_f32(const float* A, const float* W, const float* bias, const floa
                    long long lda, long long ldw, long long ldc, long long ldr, int batch, long long sA, long long sW,
                    long long sC, long long sR, float alpha, int relu, void* stream);
 
+/* Same contract on the 5th-gen tensor cores: bf16 operands (dtype code 0 = fp32 converted while staging, 1 = bf16), fp32
+ * accumulation in TMEM (tcgen05.mma M128 N256 K16), C fp32 (0) or bf16 (1).  K % 8 == 0, 16-byte aligned operand rows. */
+int sam6d_gemm_bf16(const void* A, int a_dtype, const void* W, int w_dtype, const float* bias, const float* R, void* C,
+                    int c_dtype, int M, int N, int K, long long lda, long long ldw, long long ldc, long long ldr, int batch,
+                    long long sA, long long sW, long long sC, long long sR, float alpha, int relu, void* stream);
+
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
 
 /* nn.LayerNorm(C) (PEM/model/transformer.py:156,188,423,572) */
@@ -80,6 +86,10 @@ int sam6d_geo_indices(const float* pts, int b, int S, float sigma_d, float facto
  * (in,out) transposes of the nn.Linear weights, bias = proj_a.bias + proj_d.bias, div_term the module buffer. */
 int sam6d_geo_embed_f32(const float* T, long long npairs, const float* div_term, const float* WaT, const float* WdT,
                         const float* bias, float* E, void* stream);
+
+/* tensor-core version (tcgen05, bf16 operands, fp32 accumulate): Wa/Wd are the (out,in) weights in bf16, E fp32 (0) or bf16 (1) */
+int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div_term, const void* Wa_bf16, const void* Wd_bf16,
+                       const float* bias, void* E, int e_is_bf16, void* stream);
 
 /* ---- attention ---------------------------------------------------------------------------------------------------- */
 

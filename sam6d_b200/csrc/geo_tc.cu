@@ -1,0 +1,248 @@
+// geo_tc.cu -- GeometricStructureEmbedding projections on the 5th-gen tensor cores (PEM/model/transformer.py:334-349).
+//
+//   E[p,:] = proj_d(sin_emb(d_p)) + max_{k<3} proj_a(sin_emb(a_{p,k})) + (b_a + b_d)           p = (b,i,j) pair
+//
+// The reference materialises sin_emb for 4 scalars per pair (3.8 GB at B=32) and runs two 256x256 Linears over them
+// (651 GFLOP per cloud).  Here one persistent, warp-specialised kernel per projection keeps the 256x256 bf16 weight
+// resident in shared memory (128 KB, UMMA K-major SWIZZLE_128B slabs) and never materialises the embeddings:
+//   producers (warps 4-7) : one thread per token row: x*omega_f -> __sincosf -> bf16 (sin,cos) pairs written straight into
+//                           the swizzled A slab of a 4-deep k-block ring (16 KB per 128x64 slab)
+//   MMA issuer (warp 8)   : 4 x tcgen05.mma M128 N256 K16 per k-block into one of two 256-column TMEM accumulators
+//   epilogue (warps 0-3)  : tcgen05.ld; pass ANGLE: rows are (pair, k) quadruples (k = 3 unused), max over k by a 24-shuffle
+//                           transpose-reduce, each lane stores its 8-column share -> E ; pass DIST: rows are pairs,
+//                           E += acc + bias (read-modify-write of the ANGLE result).
+// E is fp32 or bf16.  Accuracy: operands rounded to bf16 (sin/cos via MUFU), fp32 accumulation.
+#include "tc.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, KBLOCKS = 4, ASTAGES = 4;
+constexpr int A_SLAB = BM * BK * 2;          // 16 KB
+constexpr int W_SLAB = BN * BK * 2;          // 32 KB
+constexpr int NUM_THREADS = 288;
+constexpr int SMEM_BYTES = KBLOCKS * W_SLAB + ASTAGES * A_SLAB + 1024;
+
+template <typename ET>
+__device__ __forceinline__ void store8(ET* p, const float v[8]);
+template <>
+__device__ __forceinline__ void store8<float>(float* p, const float v[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <>
+__device__ __forceinline__ void store8<__nv_bfloat16>(__nv_bfloat16* p, const float v[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
+                                            tc::pack_bf16(v[6], v[7]));
+}
+template <typename ET>
+__device__ __forceinline__ void load8(const ET* p, float v[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float v[8]) {
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float v[8]) {
+  uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+// MODE 0: angle pass (rows = pair*4 + k), MODE 1: distance pass (rows = pairs)
+template <int MODE, typename ET>
+__global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const float* __restrict__ T, long long npairs,
+                                                                      const float* __restrict__ div_term,
+                                                                      const __nv_bfloat16* __restrict__ Wb,   // (256 out, 256 in) bf16
+                                                                      const float* __restrict__ bias, ET* __restrict__ E) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* w_smem = smem;                              // 4 slabs [256][64] bf16
+  uint8_t* a_smem = smem + KBLOCKS * W_SLAB;           // ring of [128][64] bf16
+  __shared__ __align__(8) uint64_t full_bar[ASTAGES], empty_bar[ASTAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ float omega[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int PAIRS_PER_TILE = (MODE == 0) ? 32 : 128;
+  const long long ntiles = (npairs + PAIRS_PER_TILE - 1) / PAIRS_PER_TILE;
+
+  if (tid == 0) {
+    for (int s = 0; s < ASTAGES; ++s) { tc::mbar_init(&full_bar[s], 128); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 128); }
+    tc::mbar_fence_init();
+  }
+  if (tid < 128) omega[tid] = div_term[tid];
+  // resident weight: W (n, k) row-major bf16 -> slab kb holds columns [64 kb, 64 kb + 64) of every row, swizzled
+  for (int u = tid; u < 256 * 32; u += NUM_THREADS) {      // 16-byte units: 256 rows x 32 units
+    const int n = u >> 5, c = (u & 31) << 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(Wb + (size_t)n * 256 + c);
+    *reinterpret_cast<uint4*>(w_smem + (c >> 6) * W_SLAB + tc::sw128_offset(n, c & 63)) = v;
+  }
+  tc::fence_proxy_async_smem();
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------------ producers: thread <-> token row
+    const int r = tid - 128;
+    long long g = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      float x;
+      if (MODE == 0) {
+        const long long pair = tile * 32 + (r >> 2);
+        x = (pair < npairs && (r & 3) < 3) ? T[pair * 4 + (r & 3)] : 0.f;
+      } else {
+        const long long pair = tile * 128 + r;
+        x = (pair < npairs) ? T[pair * 4 + 3] : 0.f;
+      }
+      for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
+        const int s = (int)(g % ASTAGES);
+        tc::mbar_wait(&empty_bar[s], (uint32_t)(((g / ASTAGES) & 1) ^ 1));
+        uint8_t* row_ptr = a_smem + s * A_SLAB + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {       // 16-byte chunk c = frequencies 32 kb + 4c .. + 3, (sin, cos) interleaved
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float sv, cv;
+            __sincosf(x * omega[kb * 32 + c * 4 + q], &sv, &cv);
+            w[q] = tc::pack_bf16(sv, cv);
+          }
+          *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&full_bar[s]);
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+      const uint32_t w_addr = tc::smem_u32(w_smem), a_addr0 = tc::smem_u32(a_smem);
+      long long g = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        tc::mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc::tc_fence_after_sync();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
+          const int s = (int)(g % ASTAGES);
+          tc::mbar_wait(&full_bar[s], (uint32_t)((g / ASTAGES) & 1));
+          tc::tc_fence_after_sync();
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(d_addr, tc::umma_desc_sw128(a_addr0 + s * A_SLAB + k * 32), tc::umma_desc_sw128(w_addr + kb * W_SLAB + k * 32),
+                          idesc, (kb | k) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);
+        }
+        tc::umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp w <-> TMEM lanes 32w .. 32w+31
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+      tc::tc_fence_after_sync();
+      const int r = warp * 32 + lane;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      if (MODE == 0) {
+        const long long pair = tile * 32 + (r >> 2);
+        const int q = r & 3;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          tc::tmem_ld32(t_addr + c * 32, v);
+          if (q == 3) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+          }
+          // max over the 4 rows of the pair, transposed so that lane q ends with columns [8q, 8q+8) of the chunk
+          float m[16];
+          const bool up2 = (lane & 2) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float keep = up2 ? v[16 + i] : v[i], send = up2 ? v[i] : v[16 + i];
+            m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+          }
+          float o[8];
+          const bool up1 = (lane & 1) != 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float keep = up1 ? m[8 + i] : m[i], send = up1 ? m[i] : m[8 + i];
+            o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+          }
+          if (pair < npairs) store8<ET>(E + pair * 256 + c * 32 + q * 8, o);
+        }
+      } else {
+        const long long pair = tile * 128 + r;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+          float v[32];
+          tc::tmem_ld32(t_addr + c * 32, v);
+          if (pair < npairs) {
+            ET* dst = E + pair * 256 + c * 32;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float e[8];
+              load8<ET>(dst + h * 8, e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] += v[h * 8 + i] + bias[c * 32 + h * 8 + i];
+              store8<ET>(dst + h * 8, e);
+            }
+          }
+        }
+      }
+      tc::tc_fence_before_sync();
+      tc::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
+}
+
+template <int MODE, typename ET>
+int launch_pass(const float* T, long long npairs, const float* div_term, const __nv_bfloat16* W, const float* bias, ET* E, int sms,
+                cudaStream_t st) {
+  auto kern = geo_embed_tc_kernel<MODE, ET>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return (int)e;
+  const long long per = (MODE == 0) ? 32 : 128;
+  const long long ntiles = (npairs + per - 1) / per;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(T, npairs, div_term, W, bias, E);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+// T (npairs,4) fp32 -> E (npairs,256) fp32 (e_is_bf16 = 0) or bf16 (1).  Wa, Wd: proj_a / proj_d weights (out,in) in bf16;
+// bias = proj_a.bias + proj_d.bias (fp32); div_term: the module buffer (128 frequencies).  Two persistent launches.
+S6_API int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div_term, const void* Wa_bf16, const void* Wd_bf16,
+                              const float* bias, void* E, int e_is_bf16, void* stream) {
+  S6_REQUIRE(T && div_term && Wa_bf16 && Wd_bf16 && bias && E && npairs >= 0);
+  if (npairs == 0) return 0;
+  int dev = 0, sms = 0;
+  S6_CHECK(cudaGetDevice(&dev));
+  S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  cudaStream_t st = s6_stream(stream);
+  const __nv_bfloat16* Wa = reinterpret_cast<const __nv_bfloat16*>(Wa_bf16);
+  const __nv_bfloat16* Wd = reinterpret_cast<const __nv_bfloat16*>(Wd_bf16);
+  int rc;
+  if (e_is_bf16) {
+    rc = launch_pass<0, __nv_bfloat16>(T, npairs, div_term, Wa, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
+    if (rc) return rc;
+    rc = launch_pass<1, __nv_bfloat16>(T, npairs, div_term, Wd, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
+  } else {
+    rc = launch_pass<0, float>(T, npairs, div_term, Wa, bias, reinterpret_cast<float*>(E), sms, st);
+    if (rc) return rc;
+    rc = launch_pass<1, float>(T, npairs, div_term, Wd, bias, reinterpret_cast<float*>(E), sms, st);
+  }
+  return rc;
+}

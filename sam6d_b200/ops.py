@@ -126,6 +126,35 @@ def gemm_raw(A_ptr, W_ptr, bias, R_ptr, C_ptr, M, N, K, lda, ldw, ldc, ldr, batc
               _ll(sW), _ll(sC), _ll(sR), _f(alpha), int(relu), _s())
 
 
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def gemm_tc_raw(A_ptr, a_dt, W_ptr, w_dt, bias, R_ptr, C_ptr, c_dt, M, N, K, lda, ldw, ldc, ldr, batch=1, sA=0, sW=0, sC=0, sR=0,
+                alpha=1.0, relu=False):
+    """tcgen05 bf16 GEMM over raw device addresses; *_dt: 0 = fp32, 1 = bf16"""
+    _lib.call("sam6d_gemm_bf16", ctypes.c_void_p(A_ptr), int(a_dt), ctypes.c_void_p(W_ptr), int(w_dt), _p(bias),
+              ctypes.c_void_p(R_ptr or 0), ctypes.c_void_p(C_ptr), int(c_dt), int(M), int(N), int(K), _ll(lda), _ll(ldw), _ll(ldc),
+              _ll(ldr), int(batch), _ll(sA), _ll(sW), _ll(sC), _ll(sR), _f(alpha), int(relu), _s())
+
+
+def gemm_tc(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
+            relu: bool = False, alpha: float = 1.0, out_dtype=torch.float32) -> Tensor:
+    """tensor-core form of gemm(): A (M,K) fp32|bf16, W (N,K) fp32|bf16 -> (M,N) fp32|bf16, fp32 accumulate"""
+    for t, n in ((A, "A"), (W, "W")):
+        if t.dtype not in _DT:
+            raise RuntimeError(f"{n} must be float32 or bfloat16")
+        _check(t, t.dtype, n, 2)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise RuntimeError("gemm: inner dimensions differ")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    gemm_tc_raw(A.data_ptr(), _DT[A.dtype], W.data_ptr(), _DT[W.dtype], bias, residual.data_ptr() if residual is not None else 0,
+                out.data_ptr(), _DT[out.dtype], M, N, K, K, K, N, N, alpha=alpha, relu=relu)
+    return out
+
+
 def layernorm_raw(x_ptr, x_view, y_ptr, y_view, gamma: Tensor, beta: Tensor, rows: int, C: int, eps: float = 1e-5):
     _lib.call("sam6d_layernorm", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
               ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(gamma), _p(beta), _ll(rows), int(C),
@@ -195,6 +224,18 @@ def geo_embed_f32(T: Tensor, div_term: Tensor, WaT: Tensor, WdT: Tensor, bias: T
     b, s, _, _ = T.shape
     E = torch.empty(b, s, s, 256, dtype=torch.float32, device=T.device)
     _lib.call("sam6d_geo_embed_f32", _p(T), _ll(b * s * s), _p(div_term), _p(WaT), _p(WdT), _p(bias), _p(E), _s())
+    return E
+
+
+def geo_embed_tc(T: Tensor, div_term: Tensor, Wa_bf16: Tensor, Wd_bf16: Tensor, bias: Tensor, out_dtype=torch.bfloat16) -> Tensor:
+    """tcgen05 version: weights (out,in) bf16, E (B,S,S,256) fp32 or bf16"""
+    _check(T, torch.float32, "T", 4)
+    _check(Wa_bf16, torch.bfloat16, "Wa", 2)
+    _check(Wd_bf16, torch.bfloat16, "Wd", 2)
+    b, s, _, _ = T.shape
+    E = torch.empty(b, s, s, 256, dtype=out_dtype, device=T.device)
+    _lib.call("sam6d_geo_embed_tc", _p(T), _ll(b * s * s), _p(div_term), _p(Wa_bf16), _p(Wd_bf16), _p(bias), _p(E),
+              int(out_dtype == torch.bfloat16), _s())
     return E
 
 

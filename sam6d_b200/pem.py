@@ -23,6 +23,34 @@ from . import ops
 
 NUM_HEADS = 4  # hard-coded in the reference (coarse_point_matching.py:31, fine_point_matching.py:29)
 
+# Arithmetic of the dense projections.  "fp32": CUDA-core kernels, fp32 storage (exact path, parity reference).
+# "bf16": tcgen05 tensor-core kernels -- operands rounded to bf16, fp32 accumulation in TMEM, geometric embedding stored
+# in bf16.  Index-valued results (FPS, ball query, labels) and the pose solvers are identical in both modes.
+PRECISIONS = ("fp32", "bf16")
+
+
+class _W:
+    """a weight matrix in both operand formats"""
+    __slots__ = ("f32", "bf16")
+
+    def __init__(self, w: torch.Tensor):
+        self.f32 = w.detach().to(torch.float32).contiguous()
+        self.bf16 = self.f32.to(torch.bfloat16).contiguous()
+
+
+def _gemm(prec, A, W: "_W", bias=None, residual=None, relu=False):
+    if prec == "bf16":
+        return ops.gemm_tc(A, W.bf16, bias, residual=residual, relu=relu)
+    return ops.gemm(A, W.f32, bias, residual=residual, relu=relu)
+
+
+def _gemm_raw(prec, A_ptr, W: "_W", bias, R_ptr, C_ptr, M, N, K, lda, ldc, ldr=0, batch=1, sA=0, sC=0, sR=0):
+    if prec == "bf16":
+        ops.gemm_tc_raw(A_ptr, 0, W.bf16.data_ptr(), 1, bias, R_ptr, C_ptr, 0, M, N, K, lda, K, ldc, ldr, batch=batch, sA=sA, sW=0,
+                        sC=sC, sR=sR)
+    else:
+        ops.gemm_raw(A_ptr, W.f32.data_ptr(), bias, R_ptr, C_ptr, M, N, K, lda, K, ldc, ldr, batch=batch, sA=sA, sW=0, sC=sC, sR=sR)
+
 
 def _cfg(cfg, **defaults):
     """accept gorilla Config / dict / namespace like the reference's cfg objects"""
@@ -90,20 +118,20 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 # ---------------------------------------------------------------------------------------------------------------------
 # shared token-layer math
 # ---------------------------------------------------------------------------------------------------------------------
-def _attn_tail(x2d: torch.Tensor, hid: torch.Tensor, lw: Dict[str, torch.Tensor]) -> torch.Tensor:
+def _attn_tail(prec, x2d: torch.Tensor, hid: torch.Tensor, lw) -> torch.Tensor:
     """AttentionLayer / RPEAttentionLayer tail + AttentionOutput (transformer.py:176-197, 435-438):
        y = LN(linear(hid) + x);  out = LN(y + squeeze(relu(expand(y))))"""
-    y = ops.gemm(hid, lw["wo"], lw["bo"], residual=x2d)
+    y = _gemm(prec, hid, lw["wo"], lw["bo"], residual=x2d)
     y = ops.layernorm(y, lw["g1"], lw["b1"])
-    h = ops.gemm(y, lw["we"], lw["be"], relu=True)
-    z = ops.gemm(h, lw["ws"], lw["bs"], residual=y)
+    h = _gemm(prec, y, lw["we"], lw["be"], relu=True)
+    z = _gemm(prec, h, lw["ws"], lw["bs"], residual=y)
     return ops.layernorm(z, lw["g2"], lw["b2"])
 
 
 def _pack_tail(layer: _TransformerLayerParams) -> Dict[str, torch.Tensor]:
     a, o = layer.attention, layer.output
-    return dict(wo=_f32(a.linear.weight), bo=_f32(a.linear.bias), g1=_f32(a.norm.weight), b1=_f32(a.norm.bias),
-                we=_f32(o.expand.weight), be=_f32(o.expand.bias), ws=_f32(o.squeeze.weight), bs=_f32(o.squeeze.bias),
+    return dict(wo=_W(a.linear.weight), bo=_f32(a.linear.bias), g1=_f32(a.norm.weight), b1=_f32(a.norm.bias),
+                we=_W(o.expand.weight), be=_f32(o.expand.bias), ws=_W(o.squeeze.weight), bs=_f32(o.squeeze.bias),
                 g2=_f32(o.norm.weight), b2=_f32(o.norm.bias))
 
 
@@ -123,6 +151,7 @@ class GeometricTransformer(nn.Module):
         self.d_model, self.num_heads = d_model, num_heads
         self.layers = nn.ModuleList([_TransformerLayerParams(d_model, rpe=True), _TransformerLayerParams(d_model, rpe=False)])
         self._packed = _Packed()
+        self.precision = "fp32"
 
     def _weights(self):
         key = _param_key(self)
@@ -139,9 +168,9 @@ class GeometricTransformer(nn.Module):
             b_self = torch.cat([bq, _f32(sa.proj_k.bias), _f32(sa.proj_v.bias)] + [c.float() for c in cu], dim=0)
             ca = self.layers[1].attention.attention
             self._packed.w = dict(
-                w_self=w_self.contiguous(), b_self=b_self.contiguous(), tail_self=_pack_tail(self.layers[0]),
-                wq_c=_f32(ca.proj_q.weight), bq_c=_f32(ca.proj_q.bias),
-                wkv_c=torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_v.weight)], dim=0).contiguous(),
+                w_self=_W(w_self), b_self=b_self.contiguous(), tail_self=_pack_tail(self.layers[0]),
+                wq_c=_W(ca.proj_q.weight), bq_c=_f32(ca.proj_q.bias),
+                wkv_c=_W(torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_v.weight)], dim=0)),
                 bkv_c=torch.cat([_f32(ca.proj_k.bias), _f32(ca.proj_v.bias)], dim=0).contiguous(),
                 tail_cross=_pack_tail(self.layers[1]))
             self._packed.key = key
@@ -151,24 +180,24 @@ class GeometricTransformer(nn.Module):
         B, S, C = x.shape
         x2d = x.reshape(B * S, C)
         ld = 3 * C + NUM_HEADS * C
-        qkvu = ops.gemm(x2d, w["w_self"], w["b_self"])                           # (B*S, q|k|v|u0..u3)
+        qkvu = _gemm(self.precision, x2d, w["w_self"], w["b_self"])              # (B*S, q|k|v|u0..u3)
         base, f = qkvu.data_ptr(), 4
         sp = ops.rpe_scores(emb, None, u_ptr=base + 3 * C * f, u_ld=ld)          # (B,H,S,S)
         hid = torch.empty(B * S, C, dtype=torch.float32, device=x.device)
         ops.mha_raw(base, ld, S * ld, base + C * f, ld, S * ld, base + 2 * C * f, ld, S * ld, sp, B, NUM_HEADS, S, S,
                     1.0 / math.sqrt(C // NUM_HEADS), hid.data_ptr(), C, S * C)
-        return _attn_tail(x2d, hid, w["tail_self"]).view(B, S, C)
+        return _attn_tail(self.precision, x2d, hid, w["tail_self"]).view(B, S, C)
 
     def _cross_layer(self, x: torch.Tensor, mem: torch.Tensor, w) -> torch.Tensor:
         B, S, C = x.shape
         Sm = mem.shape[1]
         x2d = x.reshape(B * S, C)
-        q = ops.gemm(x2d, w["wq_c"], w["bq_c"])
-        kv = ops.gemm(mem.reshape(B * Sm, C), w["wkv_c"], w["bkv_c"])
+        q = _gemm(self.precision, x2d, w["wq_c"], w["bq_c"])
+        kv = _gemm(self.precision, mem.reshape(B * Sm, C), w["wkv_c"], w["bkv_c"])
         hid = torch.empty(B * S, C, dtype=torch.float32, device=x.device)
         ops.mha_raw(q.data_ptr(), C, S * C, kv.data_ptr(), 2 * C, Sm * 2 * C, kv.data_ptr() + C * 4, 2 * C, Sm * 2 * C, None,
                     B, NUM_HEADS, S, Sm, 1.0 / math.sqrt(C // NUM_HEADS), hid.data_ptr(), C, S * C)
-        return _attn_tail(x2d, hid, w["tail_cross"]).view(B, S, C)
+        return _attn_tail(self.precision, x2d, hid, w["tail_cross"]).view(B, S, C)
 
     @torch.no_grad()
     def forward(self, feats0, embeddings0, feats1, embeddings1, masks0=None, masks1=None):
@@ -204,12 +233,15 @@ class GeometricStructureEmbedding(nn.Module):
         self.proj_d = nn.Linear(cfg.hidden_dim, cfg.hidden_dim)
         self.proj_a = nn.Linear(cfg.hidden_dim, cfg.hidden_dim)
         self._packed = _Packed()
+        self.precision = "fp32"
 
     def _weights(self):
         key = _param_key(self)
         if self._packed.key != key:
             self._packed.w = dict(div=_f32(self.embedding.div_term), waT=_f32(self.proj_a.weight).t().contiguous(),
                                   wdT=_f32(self.proj_d.weight).t().contiguous(),
+                                  wa_bf=_f32(self.proj_a.weight).to(torch.bfloat16).contiguous(),
+                                  wd_bf=_f32(self.proj_d.weight).to(torch.bfloat16).contiguous(),
                                   bias=(_f32(self.proj_a.bias) + _f32(self.proj_d.bias)).contiguous())
             self._packed.key = key
         return self._packed.w
@@ -223,6 +255,8 @@ class GeometricStructureEmbedding(nn.Module):
     def forward(self, points):
         w = self._weights()
         T = ops.geo_indices(points.contiguous(), self.sigma_d, self.factor_a)
+        if self.precision == "bf16":
+            return ops.geo_embed_tc(T, w["div"], w["wa_bf"], w["wd_bf"], w["bias"], out_dtype=torch.bfloat16)
         return ops.geo_embed_f32(T, w["div"], w["waT"], w["wdT"], w["bias"])
 
 
@@ -237,7 +271,7 @@ def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
     return (p, f, idx) if return_index else (p, f)
 
 
-def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_feat=True):
+def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_feat=True, precision="fp32"):
     """model_utils.py:114-136 -> (B,N,M) = normalize(f1) normalize(f2)^T / temp."""
     if type != 'cosine':
         raise NotImplementedError("SAM-6D uses sim_type='cosine'")
@@ -246,8 +280,12 @@ def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_
     f1 = ops.l2norm_rows(feat1.contiguous()) if normalize_feat else feat1.contiguous()
     f2 = ops.l2norm_rows(feat2.contiguous()) if normalize_feat else feat2.contiguous()
     A = torch.empty(B, N, M, dtype=torch.float32, device=feat1.device)
-    ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, A.data_ptr(), N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
-                 sC=N * M, alpha=1.0 / temp)
+    if precision == "bf16":
+        ops.gemm_tc_raw(f1.data_ptr(), 0, f2.data_ptr(), 0, None, 0, A.data_ptr(), 0, N, M, C, C, C, M, 0, batch=B, sA=N * C,
+                        sW=M * C, sC=N * M, alpha=1.0 / temp)
+    else:
+        ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, A.data_ptr(), N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
+                     sC=N * M, alpha=1.0 / temp)
     return A
 
 
@@ -297,14 +335,25 @@ class CoarsePointMatching(nn.Module):
         self.transformers = nn.ModuleList([
             GeometricTransformer(blocks=['self', 'cross'], d_model=self.cfg.hidden_dim, num_heads=4, dropout=None,
                                  activation_fn='ReLU', return_attention_scores=False) for _ in range(self.nblock)])
+        self._packed = _Packed()
+        self.precision = "fp32"
+
+    def _weights(self):
+        key = _param_key(self.in_proj) + _param_key(self.out_proj)
+        if self._packed.key != key:
+            self._packed.w = dict(w_in=_W(self.in_proj.weight), b_in=_f32(self.in_proj.bias), w_out=_W(self.out_proj.weight),
+                                  b_out=_f32(self.out_proj.bias))
+            self._packed.key = key
+        return self._packed.w
 
     def _embed(self, f):
         B, n, C = f.shape
+        w = self._weights()
         out = torch.empty(B, n + 1, self.cfg.hidden_dim, dtype=torch.float32, device=f.device)
         out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
         H = self.cfg.hidden_dim
-        ops.gemm_raw(f.data_ptr(), _f32(self.in_proj.weight).data_ptr(), _f32(self.in_proj.bias), 0, out.data_ptr() + H * 4,
-                     n, H, C, C, C, H, 0, batch=B, sA=n * C, sW=0, sC=(n + 1) * H)
+        _gemm_raw(self.precision, f.data_ptr(), w["w_in"], w["b_in"], 0, out.data_ptr() + H * 4, n, H, C, C, H, 0, batch=B,
+                  sA=n * C, sC=(n + 1) * H)
         return out
 
     @torch.no_grad()
@@ -316,10 +365,10 @@ class CoarsePointMatching(nn.Module):
         for blk in self.transformers:
             f1, f2 = blk(f1, geo1, f2, geo2)
         B, S, H = f1.shape
-        wo, bo = _f32(self.out_proj.weight), _f32(self.out_proj.bias)
-        o1 = ops.gemm(f1.reshape(B * S, H), wo, bo).view(B, S, -1)
-        o2 = ops.gemm(f2.reshape(B * S, H), wo, bo).view(B, S, -1)
-        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat)
+        w = self._weights()
+        o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
         init_R, init_t, self.last_select_scores = compute_coarse_Rt(atten, p1, p2, model, self.cfg.nproposal1,
                                                                     self.cfg.nproposal2, rand=rand, return_scores=True)
@@ -372,6 +421,7 @@ class PositionalEncoding(nn.Module):
         self.mlp2 = _SharedMLP([6, 32, 64, 128])
         self.mlp3 = _Conv1dParams(256, out_dim)
         self._packed = _Packed()
+        self.precision = "fp32"
 
     def _weights(self):
         key = _param_key(self)
@@ -383,7 +433,7 @@ class PositionalEncoding(nn.Module):
                     wj, bj = getattr(mlp, f"layer{j}").folded()
                     packed += [wj, bj]
                 w[name] = tuple(packed)
-            w["w3"] = _f32(self.mlp3.conv.weight).reshape(self.mlp3.conv.out_channels, -1).contiguous()
+            w["w3"] = _W(_f32(self.mlp3.conv.weight).reshape(self.mlp3.conv.out_channels, -1))
             w["b3"] = _f32(self.mlp3.conv.bias)
             self._packed.w, self._packed.key = w, key
         return self._packed.w
@@ -407,7 +457,7 @@ class PositionalEncoding(nn.Module):
         w = self._weights()
         feat = self.local_features(pts1)
         B, N, _ = feat.shape
-        return ops.gemm(feat.view(B * N, 256), w["w3"], w["b3"]).view(B, N, -1)
+        return _gemm(self.precision, feat.view(B * N, 256), w["w3"], w["b3"]).view(B, N, -1)
 
 
 class _LinearAttentionParams(nn.Module):
@@ -448,19 +498,20 @@ class SparseToDenseTransformer(nn.Module):
                                                  activation_fn=activation_fn, parallel=parallel, return_attention_scores=False)
         self.dense_layer = _LinearTransformerLayerParams(d_model)
         self._packed = _Packed()
+        self.precision = "fp32"
 
     def _weights(self):
         key = _param_key(self.dense_layer)
         if self._packed.key != key:
             la = self.dense_layer.attention.attention
-            tail = dict(wo=_f32(self.dense_layer.attention.linear.weight), bo=_f32(self.dense_layer.attention.linear.bias),
+            tail = dict(wo=_W(self.dense_layer.attention.linear.weight), bo=_f32(self.dense_layer.attention.linear.bias),
                         g1=_f32(self.dense_layer.attention.norm.weight), b1=_f32(self.dense_layer.attention.norm.bias),
-                        we=_f32(self.dense_layer.output.expand.weight), be=_f32(self.dense_layer.output.expand.bias),
-                        ws=_f32(self.dense_layer.output.squeeze.weight), bs=_f32(self.dense_layer.output.squeeze.bias),
+                        we=_W(self.dense_layer.output.expand.weight), be=_f32(self.dense_layer.output.expand.bias),
+                        ws=_W(self.dense_layer.output.squeeze.weight), bs=_f32(self.dense_layer.output.squeeze.bias),
                         g2=_f32(self.dense_layer.output.norm.weight), b2=_f32(self.dense_layer.output.norm.bias))
             self._packed.w = dict(
-                wq=_f32(la.proj_q.weight), bq=_f32(la.proj_q.bias),
-                wkv=torch.cat([_f32(la.proj_k.weight), _f32(la.proj_v.weight)], dim=0).contiguous(),
+                wq=_W(la.proj_q.weight), bq=_f32(la.proj_q.bias),
+                wkv=_W(torch.cat([_f32(la.proj_k.weight), _f32(la.proj_v.weight)], dim=0)),
                 bkv=torch.cat([_f32(la.proj_k.bias), _f32(la.proj_v.bias)], dim=0).contiguous(),
                 sp_scale=torch.nn.functional.softplus(_f32(la.scale)).reshape(-1).contiguous(), tail=tail)
             self._packed.key = key
@@ -478,10 +529,11 @@ class SparseToDenseTransformer(nn.Module):
         dev = dense.device
         x_ptr, x_view = dense.data_ptr() + C * f, (N, N1 * C, C)          # rows 1..N of every proposal
         q = torch.empty(B * N, C, dtype=torch.float32, device=dev)
-        ops.gemm_raw(x_ptr, w["wq"].data_ptr(), w["bq"], 0, q.data_ptr(), N, C, C, C, C, C, 0, batch=B, sA=N1 * C, sC=N * C)
+        prec = self.precision
+        _gemm_raw(prec, x_ptr, w["wq"], w["bq"], 0, q.data_ptr(), N, C, C, C, C, 0, batch=B, sA=N1 * C, sC=N * C)
         kv = torch.empty(B * J, 2 * C, dtype=torch.float32, device=dev)
-        ops.gemm_raw(sparse.data_ptr() + C * f, w["wkv"].data_ptr(), w["bkv"], 0, kv.data_ptr(), J, 2 * C, C, C, C, 2 * C, 0,
-                     batch=B, sA=(J + 1) * C, sC=J * 2 * C)
+        _gemm_raw(prec, sparse.data_ptr() + C * f, w["wkv"], w["bkv"], 0, kv.data_ptr(), J, 2 * C, C, C, 2 * C, 0, batch=B,
+                  sA=(J + 1) * C, sC=J * 2 * C)
         ops.focus_rows_raw(q.data_ptr(), (B * N, 0, C), q.data_ptr(), (B * N, 0, C), w["sp_scale"], B * N, C)
         ops.focus_rows_raw(kv.data_ptr(), (B * J, 0, 2 * C), kv.data_ptr(), (B * J, 0, 2 * C), w["sp_scale"], B * J, C)
         KV = torch.empty(B, NUM_HEADS, 64, 64, dtype=torch.float32, device=dev)
@@ -491,11 +543,11 @@ class SparseToDenseTransformer(nn.Module):
         ops.linattn_apply_raw(q.data_ptr(), N, N * C, C, KV, KS, B, NUM_HEADS, x_att.data_ptr(), N * C, C)
         t = w["tail"]
         y = torch.empty(B * N, C, dtype=torch.float32, device=dev)
-        ops.gemm_raw(x_att.data_ptr(), t["wo"].data_ptr(), t["bo"], x_ptr, y.data_ptr(), N, C, C, C, C, C, C, batch=B,
-                     sA=N * C, sC=N * C, sR=N1 * C)
+        _gemm_raw(prec, x_att.data_ptr(), t["wo"], t["bo"], x_ptr, y.data_ptr(), N, C, C, C, C, C, batch=B, sA=N * C, sC=N * C,
+                  sR=N1 * C)
         y = ops.layernorm(y, t["g1"], t["b1"])
-        h = ops.gemm(y, t["we"], t["be"], relu=True)
-        z = ops.gemm(h, t["ws"], t["bs"], residual=y)
+        h = _gemm(prec, y, t["we"], t["be"], relu=True)
+        z = _gemm(prec, h, t["ws"], t["bs"], residual=y)
         out = torch.empty(B, N1, C, dtype=torch.float32, device=dev)
         ops.layernorm_raw(z.data_ptr(), (B * N, 0, C), out.data_ptr() + C * f, (N, N1 * C, C), t["g2"], t["b2"], B * N, C)
         out[:, 0, :] = sparse[:, 0, :]                                      # replaced bg token (transformer.py:660-668)
@@ -526,22 +578,32 @@ class FinePointMatching(nn.Module):
         self.out_proj = nn.Linear(self.cfg.hidden_dim, self.cfg.out_dim)
         self.bg_token = nn.Parameter(torch.randn(1, 1, self.cfg.hidden_dim) * .02)
         self.PE = PositionalEncoding(self.cfg.hidden_dim, r1=self.cfg.pe_radius1, r2=self.cfg.pe_radius2)
+        self._packed = _Packed()
+        self.precision = "fp32"
         self.transformers = nn.ModuleList([
             SparseToDenseTransformer(self.cfg.hidden_dim, num_heads=4, sparse_blocks=['self', 'cross'], dropout=None,
                                      activation_fn='ReLU', focusing_factor=self.cfg.focusing_factor, with_bg_token=True,
                                      replace_bg_token=True) for _ in range(self.nblock)])
 
+    def _weights(self):
+        key = _param_key(self.in_proj) + _param_key(self.out_proj)
+        if self._packed.key != key:
+            self._packed.w = dict(w_in=_W(self.in_proj.weight), b_in=_f32(self.in_proj.bias), w_out=_W(self.out_proj.weight),
+                                  b_out=_f32(self.out_proj.bias))
+            self._packed.key = key
+        return self._packed.w
+
     def _embed(self, f, pts):
         """[bg_token ; in_proj(f) + PE(pts)] as one (B,N+1,H) sequence (fine_point_matching.py:46-50)"""
         B, N, C = f.shape
         H = self.cfg.hidden_dim
-        pw = self.PE._weights()
+        w, pw = self._weights(), self.PE._weights()
         local = self.PE.local_features(pts)                                         # (B,N,256)
-        tmp = ops.gemm(f.reshape(B * N, C), _f32(self.in_proj.weight), _f32(self.in_proj.bias))
+        tmp = _gemm(self.precision, f.reshape(B * N, C), w["w_in"], w["b_in"])
         out = torch.empty(B, N + 1, H, dtype=torch.float32, device=f.device)
         out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
-        ops.gemm_raw(local.data_ptr(), pw["w3"].data_ptr(), pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 4, N, H, 256, 256, 256,
-                     H, H, batch=B, sA=N * 256, sW=0, sC=(N + 1) * H, sR=N * H)
+        _gemm_raw(self.precision, local.data_ptr(), pw["w3"], pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 4, N, H, 256, 256, H, H,
+                  batch=B, sA=N * 256, sC=(N + 1) * H, sR=N * H)
         return out
 
     @torch.no_grad()
@@ -555,10 +617,10 @@ class FinePointMatching(nn.Module):
         for blk in self.transformers:
             f1, f2 = blk(f1, geo1, fps_idx1, f2, geo2, fps_idx2)
         B, S, H = f1.shape
-        wo, bo = _f32(self.out_proj.weight), _f32(self.out_proj.bias)
-        o1 = ops.gemm(f1.reshape(B * S, H), wo, bo).view(B, S, -1)
-        o2 = ops.gemm(f2.reshape(B * S, H), wo, bo).view(B, S, -1)
-        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat)
+        w = self._weights()
+        o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
         pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
         end_points['pred_R'] = pred_R
@@ -589,7 +651,7 @@ class Net(nn.Module):
     `feature_extraction`, or put the per-point features into end_points['dense_fm'] (B,N,256) directly.
     """
 
-    def __init__(self, cfg=None, feature_extraction: Optional[nn.Module] = None):
+    def __init__(self, cfg=None, feature_extraction: Optional[nn.Module] = None, precision: str = "fp32"):
         super().__init__()
         cfg = _cfg(cfg if cfg is not None else DEFAULT_MODEL_CFG)
         self.cfg = cfg
@@ -600,6 +662,17 @@ class Net(nn.Module):
         self.geo_embedding = GeometricStructureEmbedding(cfg.geo_embedding)
         self.coarse_point_matching = CoarsePointMatching(cfg.coarse_point_matching)
         self.fine_point_matching = FinePointMatching(cfg.fine_point_matching)
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str):
+        """'fp32' (CUDA-core kernels, exact path) or 'bf16' (tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate)"""
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.precision = precision
+        for m in self.modules():
+            if hasattr(m, "precision") and m is not self:
+                m.precision = precision
+        return self
 
     def _features(self, end_points):
         """ViTEncoder.forward, inference branch (feature_extraction.py:128-142)"""

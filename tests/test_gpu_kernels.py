@@ -367,3 +367,54 @@ def test_template_score(ops, P, O, T):
     assert torch.equal(g_t.cpu(), best_t)                         # bit-exact argmax template indices
     assert g_t.dtype == torch.int64 and g_obj.dtype == torch.int64
     torch.testing.assert_close(g_sem.cpu(), sem, atol=2e-6, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------- tcgen05 GEMM
+@pytest.mark.parametrize("M,N,K", [(197 * 3, 1792, 256), (1000, 512, 256), (4096, 256, 512), (130, 40, 64), (2049, 2049, 256)])
+@pytest.mark.parametrize("adt,wdt,odt", [(torch.float32, torch.bfloat16, torch.float32), (torch.float32, torch.float32, torch.float32),
+                                         (torch.bfloat16, torch.bfloat16, torch.bfloat16)])
+def test_gemm_tc(ops, M, N, K, adt, wdt, odt):
+    A = torch.randn(M, K, generator=G(1))
+    W = torch.randn(N, K, generator=G(2)) / math.sqrt(K)
+    bias = torch.randn(N, generator=G(3))
+    R = torch.randn(M, N, generator=G(4))
+    # the kernel rounds both operands to bf16 and accumulates in fp32: compare with exactly that arithmetic
+    ref = torch.relu(A.bfloat16().double() @ W.bfloat16().double().t() * 0.5 + bias.double()) + R.double()
+    got = ops.gemm_tc(A.cuda().to(adt), W.cuda().to(wdt), bias.cuda(), residual=R.cuda(), relu=True, alpha=0.5, out_dtype=odt).cpu()
+    assert got.dtype == odt
+    tol = 2e-5 if odt == torch.float32 else 2e-2
+    torch.testing.assert_close(got.double(), ref, atol=tol, rtol=1e-5 if odt == torch.float32 else 1e-2)
+
+
+def test_gemm_tc_batched_strided(ops):
+    B, N, M, C = 3, 300, 257, 256
+    f1 = torch.randn(B, N, C, generator=G(1))
+    f2 = torch.randn(B, M, C, generator=G(2))
+    out = torch.empty(B, N, M).cuda()
+    a, w = f1.cuda(), f2.cuda()
+    ops.gemm_tc_raw(a.data_ptr(), 0, w.data_ptr(), 0, None, 0, out.data_ptr(), 0, N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
+                    sC=N * M, alpha=10.0)
+    ref = 10.0 * f1.bfloat16().double() @ f2.bfloat16().double().transpose(1, 2)
+    torch.testing.assert_close(out.cpu().double(), ref, atol=2e-4, rtol=1e-5)
+
+
+@pytest.mark.parametrize("S,edt", [(64, torch.float32), (197, torch.bfloat16), (197, torch.float32), (33, torch.bfloat16)])
+def test_geo_embed_tc(ops, S, edt):
+    """tcgen05 geometric embedding: bf16 operands (sin/cos and weights), fp32 accumulation, E in fp32 or bf16"""
+    sd = po.make_state_dict(seed=2)
+    pts = _sparse_cloud(3, S, 9)
+    ref = exact_geo_embedding(sd, pts)
+    T = ops.geo_indices(pts.cuda(), po.SIGMA_D, 180.0 / (po.SIGMA_A * math.pi))
+    E = ops.geo_embed_tc(T, sd["geo_embedding.embedding.div_term"].cuda(), sd["geo_embedding.proj_a.weight"].cuda().bfloat16().contiguous(),
+                         sd["geo_embedding.proj_d.weight"].cuda().bfloat16().contiguous(),
+                         (sd["geo_embedding.proj_a.bias"] + sd["geo_embedding.proj_d.bias"]).cuda(), out_dtype=edt).float().cpu()
+    assert E.shape == ref.shape and torch.isfinite(E).all()
+    err = (E - ref).abs()
+    # bf16 rounding of 256-term dot products of O(1) values: ~3e-3 typical, a few 1e-2 worst case
+    assert err.median().item() < 4e-3, err.median().item()
+    assert (err > 6e-2).float().mean().item() < 2e-3
+    # and it must agree with the fp32 CUDA-core kernel within the same budget (same indices, so no knn-tie outliers)
+    E32 = ops.geo_embed_f32(T, sd["geo_embedding.embedding.div_term"].cuda(), sd["geo_embedding.proj_a.weight"].t().contiguous().cuda(),
+                            sd["geo_embedding.proj_d.weight"].t().contiguous().cuda(),
+                            (sd["geo_embedding.proj_a.bias"] + sd["geo_embedding.proj_d.bias"]).cuda()).cpu()
+    torch.testing.assert_close(E, E32, atol=6e-2, rtol=0)

@@ -194,3 +194,24 @@ def test_batch_32_properties():
     # the synthetic scenes have a known pose: the estimate lands near it
     err = (R - inp["gt_R"]).abs().amax(dim=(1, 2))
     assert err.median().item() < 0.1
+
+
+def test_bf16_tensor_core_mode_matches_reference_golden(golden_dir):
+    """precision='bf16' (tcgen05 kernels: bf16 operands, fp32 accumulation, bf16 geometric embedding): same poses within the
+    north-star tolerance on the proposals whose reference pose is well defined."""
+    from sam6d_b200.pem import Net
+    gold = torch.load(os.path.join(golden_dir, "pem_full.pt"), weights_only=False)
+    m = gold["meta"]
+    net = Net(precision="bf16").cuda().eval()
+    net.load_state_dict(po.make_state_dict(seed=m["seed"]), strict=True)
+    inputs = po.make_inputs(B=m["B"], n=m["n"], seed=m["seed"])
+    torch.manual_seed(1)
+    rand = torch.rand(m["B"], po.N_PROPOSAL1 * 3)
+    out = net({k: inputs[k].cuda() for k in ("pts", "dense_fm", "dense_po", "dense_fo", "model")}, rand=rand.cuda())
+    well = ~gold["init_degenerate"]
+    report = {k: (out[k].cpu() - gold[k]).abs().reshape(m["B"], -1).amax(dim=1).tolist() for k in ("init_R", "pred_R", "pred_t")}
+    print("bf16 mode |gpu - reference| per proposal:", report, "well-defined:", well.tolist())
+    torch.testing.assert_close(out["pred_R"].cpu()[well], gold["pred_R"][well], atol=R_TOL, rtol=0)
+    torch.testing.assert_close(out["pred_t"].cpu()[well], gold["pred_t"][well], atol=T_TOL, rtol=0)
+    R = out["pred_R"].cpu()
+    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand_as(R), atol=1e-5, rtol=0)
