@@ -121,6 +121,10 @@ int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, int n2, 
 int sam6d_pe_mlp_max(const float* pts, const int* idx, const int* cnt, int B, int N, int ns, const float* W1,
                      const float* B1, const float* W2, const float* B2, const float* W3, const float* B3, float* out,
                      int out_ld, int out_off, void* stream);
+/* tensor-core version: layers 2 and 3 on tcgen05 (W2 (64,32), W3 (128,64) bf16), max-pool in the TMEM epilogue */
+int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, const float* W1, const float* B1,
+                        const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
+                        int out_off, void* stream);
 /* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls */
 int sam6d_fine_assign(const float* A, int B, int S, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
                       int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream);

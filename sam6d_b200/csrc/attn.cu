@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(256) rpe_scores_kernel(const ET* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// mha.  grid = (ceil(Sq/QT), B*H); K_h, V_h of the cloud staged in shared memory (padded rows).
+// mha.  grid = (ceil(Sq/32), B*H); K_h, V_h of the cloud staged once per 32 queries in shared memory.
+// Each warp owns 4 queries at a time: a lane holds one key (QK^T) / two output channels (PV) for all four, so every K / V
+// word read from shared memory feeds 4 FMAs and the query / probability operands arrive as one broadcast LDS.128.
 // ------------------------------------------------------------------------------------------
-constexpr int MHA_QT = 16;    // queries per CTA (2 per warp)
+constexpr int MHA_QT = 32;    // queries per CTA (4 per warp)
 constexpr int MHA_MAXK = 256; // keys per cloud supported by the register tile (8 per lane)
+constexpr int MHA_KP = 68;    // padded K row (floats): 16-byte aligned, conflict-free for LDS.128 across lanes
 
 __global__ void __launch_bounds__(256) mha_kernel(const float* __restrict__ Q, long long q_ld, long long q_bs,
                                                   const float* __restrict__ K, long long k_ld, long long k_bs,
@@ -105,12 +108,12 @@ __global__ void __launch_bounds__(256) mha_kernel(const float* __restrict__ Q, l
                                                   const float* __restrict__ bias,  // (B,H,Sq,Sk) or null
                                                   int H, int Sq, int Sk, float scale, float* __restrict__ O, long long o_ld,
                                                   long long o_bs) {
-  extern __shared__ float sm[];
-  constexpr int D = 64, DP = 65;
-  float* ks = sm;                 // Sk * DP
-  float* vs = ks + Sk * DP;       // Sk * DP
-  float* qs = vs + Sk * DP;       // MHA_QT * D
-  float* ps = qs + MHA_QT * D;    // 8 warps * MHA_MAXK
+  extern __shared__ __align__(16) float sm[];
+  constexpr int D = 64;
+  float* ks = sm;                       // Sk * MHA_KP
+  float* vs = ks + Sk * MHA_KP;         // Sk * D
+  float* qs = vs + Sk * D;              // 8 warps * [D][4]   (4 queries interleaved per channel)
+  float* ps = qs + 8 * D * 4;           // 8 warps * [MHA_MAXK][4]
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int q0 = blockIdx.x * MHA_QT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -118,68 +121,89 @@ __global__ void __launch_bounds__(256) mha_kernel(const float* __restrict__ Q, l
   const float* Vb = V + (size_t)b * v_bs + h * D;
   for (int e = tid; e < Sk * (D / 4); e += 256) {
     int m = e / (D / 4), c4 = (e - m * (D / 4)) * 4;
-    float4 kv = *reinterpret_cast<const float4*>(Kb + (size_t)m * k_ld + c4);
-    float4 vv = *reinterpret_cast<const float4*>(Vb + (size_t)m * v_ld + c4);
-    float* kd = ks + m * DP + c4;
-    float* vd = vs + m * DP + c4;
-    kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-    vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    *reinterpret_cast<float4*>(ks + m * MHA_KP + c4) = *reinterpret_cast<const float4*>(Kb + (size_t)m * k_ld + c4);
+    *reinterpret_cast<float4*>(vs + m * D + c4) = *reinterpret_cast<const float4*>(Vb + (size_t)m * v_ld + c4);
   }
-  for (int e = tid; e < MHA_QT * D; e += 256) {
-    int qi = e / D, c = e - qi * D;
-    int n = q0 + qi;
-    qs[e] = (n < Sq) ? Q[(size_t)b * q_bs + (size_t)n * q_ld + h * D + c] : 0.f;
+  float* qw = qs + warp * D * 4;
+  float* pw = ps + warp * MHA_MAXK * 4;
+  const int n0 = q0 + warp * 4;
+  for (int e = lane; e < D * 4; e += 32) {
+    int c = e >> 2, qi = e & 3;
+    int n = n0 + qi;
+    qw[e] = (n < Sq) ? Q[(size_t)b * q_bs + (size_t)n * q_ld + h * D + c] : 0.f;
   }
   __syncthreads();
-  float* pw = ps + warp * MHA_MAXK;
-  for (int qi = warp; qi < MHA_QT; qi += 8) {
-    const int n = q0 + qi;
-    if (n >= Sq) break;
-    const float* qv = qs + qi * D;
-    float s[MHA_MAXK / 32];
-    float mx = -INFINITY;
+  if (n0 >= Sq) return;
+  float s[MHA_MAXK / 32][4];
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int t = 0; t < MHA_MAXK / 32; ++t) {
-      int m = lane + 32 * t;
-      float a = -INFINITY;
-      if (m < Sk) {
-        const float* kr = ks + m * DP;
-        float d = 0.f;
-#pragma unroll 16
-        for (int c = 0; c < D; ++c) d = fmaf(qv[c], kr[c], d);
-        if (bias) d += bias[(((size_t)b * H + h) * Sq + n) * Sk + m];
-        a = d * scale;
+  for (int t = 0; t < MHA_MAXK / 32; ++t) {
+    const int m = lane + 32 * t;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < Sk) {
+      const float* kr = ks + m * MHA_KP;
+#pragma unroll 4
+      for (int c = 0; c < D; c += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kr + c);
+        const float4 qa = *reinterpret_cast<const float4*>(qw + (c + 0) * 4);
+        const float4 qb = *reinterpret_cast<const float4*>(qw + (c + 1) * 4);
+        const float4 qc = *reinterpret_cast<const float4*>(qw + (c + 2) * 4);
+        const float4 qd = *reinterpret_cast<const float4*>(qw + (c + 3) * 4);
+        a[0] = fmaf(kv.x, qa.x, a[0]); a[1] = fmaf(kv.x, qa.y, a[1]); a[2] = fmaf(kv.x, qa.z, a[2]); a[3] = fmaf(kv.x, qa.w, a[3]);
+        a[0] = fmaf(kv.y, qb.x, a[0]); a[1] = fmaf(kv.y, qb.y, a[1]); a[2] = fmaf(kv.y, qb.z, a[2]); a[3] = fmaf(kv.y, qb.w, a[3]);
+        a[0] = fmaf(kv.z, qc.x, a[0]); a[1] = fmaf(kv.z, qc.y, a[1]); a[2] = fmaf(kv.z, qc.z, a[2]); a[3] = fmaf(kv.z, qc.w, a[3]);
+        a[0] = fmaf(kv.w, qd.x, a[0]); a[1] = fmaf(kv.w, qd.y, a[1]); a[2] = fmaf(kv.w, qd.z, a[2]); a[3] = fmaf(kv.w, qd.w, a[3]);
       }
-      s[t] = a;
-      mx = fmaxf(mx, a);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
 #pragma unroll
-    for (int t = 0; t < MHA_MAXK / 32; ++t) {
-      int m = lane + 32 * t;
-      float e = (m < Sk) ? __expf(s[t] - mx) : 0.f;
-      s[t] = e;
-      sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
+      for (int qi = 0; qi < 4; ++qi) {
+        const int n = min(n0 + qi, Sq - 1);
+        if (bias) a[qi] += bias[(((size_t)b * H + h) * Sq + n) * Sk + m];
+        a[qi] *= scale;
+      }
+    } else {
 #pragma unroll
-    for (int t = 0; t < MHA_MAXK / 32; ++t) {
-      int m = lane + 32 * t;
-      if (m < Sk) pw[m] = s[t] * inv;
+      for (int qi = 0; qi < 4; ++qi) a[qi] = -INFINITY;
     }
-    __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
-    for (int m = 0; m < Sk; ++m) {
-      float p = pw[m];
-      o0 = fmaf(p, vs[m * DP + lane], o0);
-      o1 = fmaf(p, vs[m * DP + lane + 32], o1);
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) { s[t][qi] = a[qi]; mx[qi] = fmaxf(mx[qi], a[qi]); }
+  }
+  float sum[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) mx[qi] = warp_max(mx[qi]);
+#pragma unroll
+  for (int t = 0; t < MHA_MAXK / 32; ++t) {
+    const int m = lane + 32 * t;
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      float e = (m < Sk) ? __expf(s[t][qi] - mx[qi]) : 0.f;
+      s[t][qi] = e;
+      sum[qi] += e;
     }
-    float* op = O + (size_t)b * o_bs + (size_t)n * o_ld + h * D;
-    op[lane] = o0;
-    op[lane + 32] = o1;
-    __syncwarp();
+  }
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) sum[qi] = 1.f / warp_sum(sum[qi]);
+#pragma unroll
+  for (int t = 0; t < MHA_MAXK / 32; ++t) {
+    const int m = lane + 32 * t;
+    if (m < Sk) *reinterpret_cast<float4*>(pw + m * 4) = make_float4(s[t][0] * sum[0], s[t][1] * sum[1], s[t][2] * sum[2], s[t][3] * sum[3]);
+  }
+  __syncwarp();
+  float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int m = 0; m < Sk; ++m) {
+    const float4 p = *reinterpret_cast<const float4*>(pw + m * 4);
+    const float v0 = vs[m * D + lane], v1 = vs[m * D + lane + 32];
+    o0[0] = fmaf(p.x, v0, o0[0]); o0[1] = fmaf(p.y, v0, o0[1]); o0[2] = fmaf(p.z, v0, o0[2]); o0[3] = fmaf(p.w, v0, o0[3]);
+    o1[0] = fmaf(p.x, v1, o1[0]); o1[1] = fmaf(p.y, v1, o1[1]); o1[2] = fmaf(p.z, v1, o1[2]); o1[3] = fmaf(p.w, v1, o1[3]);
+  }
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) {
+    const int n = n0 + qi;
+    if (n < Sq) {
+      float* op = O + (size_t)b * o_bs + (size_t)n * o_ld + h * D;
+      op[lane] = o0[qi];
+      op[lane + 32] = o1[qi];
+    }
   }
 }
 
@@ -276,7 +300,7 @@ S6_API int sam6d_mha(const float* Q, long long q_ld, long long q_bs, const float
   S6_REQUIRE(Q && K && V && O && B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= MHA_MAXK);
   S6_REQUIRE((k_ld % 4 == 0) && (v_ld % 4 == 0) && (k_bs % 4 == 0) && (v_bs % 4 == 0));
   if (B == 0) return 0;
-  size_t smem = ((size_t)2 * Sk * 65 + MHA_QT * 64 + 8 * MHA_MAXK) * sizeof(float);
+  size_t smem = ((size_t)Sk * (MHA_KP + 64) + 8 * 64 * 4 + 8 * MHA_MAXK * 4) * sizeof(float);
   S6_CHECK(cudaFuncSetAttribute(mha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(s6_cdiv(Sq, MHA_QT), B * H);
   mha_kernel<<<grid, 256, smem, s6_stream(stream)>>>(Q, q_ld, q_bs, K, k_ld, k_bs, V, v_ld, v_bs, bias, H, Sq, Sk, scale, O,

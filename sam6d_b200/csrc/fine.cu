@@ -4,7 +4,7 @@
 // A = F1 F2^T / temp with L2-normalised features, so |A| <= 1/temp and softmax can use the fixed shift
 // `shift` = 1/temp instead of a per-row/column maximum: e_ij = exp(A_ij - shift),
 //   P_ij = (e_ij / sum_j e_ij) * (e_ij / sum_i e_ij).
-// Three streaming passes over A (row/col sums; row/col argmax of P; masked weighted sums), then a per-proposal
+// Three streaming passes over A (row/col sums; column argmax of P; row argmax + masked weighted sums), then a per-proposal
 // weighted Procrustes and the inlier score against the CAD samples.
 #include "common.cuh"
 #include "svd3.cuh"
@@ -47,47 +47,34 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ cpart, int tiles,
   csum[(size_t)b * S + j] = s;
 }
 
-// pass 2: lab1[b,i] = argmax_j P_ij (first max); per-tile column argmax partials
-__global__ void __launch_bounds__(256) fine_labels_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
-                                                          const float* __restrict__ csum, int* __restrict__ lab1,
-                                                          float* __restrict__ cpv, int* __restrict__ cpi) {
-  __shared__ float rv[RT][8];
-  __shared__ int ri[RT][8];
-  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// pass 2: column labels lab2[b,j] = argmax_i P_ij (first max) as per-tile partials.  Along a column the factor
+// e_ij / csum_j ... is shared, so P_ij is ordered like e_ij * (e_ij / rsum_i); we evaluate the full product like the reference.
+__global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
+                                                             const float* __restrict__ csum, float* __restrict__ cpv,
+                                                             int* __restrict__ cpi) {
+  __shared__ float rinv[RT];
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const int i0 = tile * RT;
+  if (tid < RT) rinv[tid] = (i0 + tid < S) ? 1.f / rsum[(size_t)b * S + i0 + tid] : 0.f;
+  __syncthreads();
   const float* Ab = A + (size_t)b * S * S;
-  float rbv[RT];
-  int rbi[RT];
-#pragma unroll
-  for (int r = 0; r < RT; ++r) { rbv[r] = -INFINITY; rbi[r] = 0x7fffffff; }
   for (int j0 = 0; j0 < S; j0 += 256) {
     const int j = j0 + tid;
-    const float cs = (j < S) ? csum[(size_t)b * S + j] : 1.f;
+    if (j >= S) break;
+    const float cinv = 1.f / csum[(size_t)b * S + j];
     float cbv = -INFINITY;
     int cbi = 0;
-#pragma unroll
+#pragma unroll 8
     for (int r = 0; r < RT; ++r) {
       const int i = i0 + r;
-      if (i < S && j < S) {
+      if (i < S) {
         float e = __expf(Ab[(size_t)i * S + j] - shift);
-        float p = (e / rsum[(size_t)b * S + i]) * (e / cs);
+        float p = (e * rinv[r]) * (e * cinv);
         if (p > cbv) { cbv = p; cbi = i; }                     // ascending i: first max wins
-        if (p > rbv[r]) { rbv[r] = p; rbi[r] = j; }            // ascending j within this thread
       }
     }
-    if (j < S) { cpv[((size_t)b * gridDim.x + tile) * S + j] = cbv; cpi[((size_t)b * gridDim.x + tile) * S + j] = cbi; }
-  }
-#pragma unroll
-  for (int r = 0; r < RT; ++r) {
-    float v = rbv[r]; int ix = rbi[r];
-    warp_argmax_first(v, ix);
-    if (lane == 0) { rv[r][warp] = v; ri[r][warp] = ix; }
-  }
-  __syncthreads();
-  if (tid < RT && i0 + tid < S) {
-    float v = rv[tid][0]; int ix = ri[tid][0];
-    for (int w = 1; w < 8; ++w) argmax_first(v, ix, rv[tid][w], ri[tid][w]);
-    lab1[(size_t)b * S + i0 + tid] = ix;
+    cpv[((size_t)b * gridDim.x + tile) * S + j] = cbv;
+    cpi[((size_t)b * gridDim.x + tile) * S + j] = cbi;
   }
 }
 
@@ -103,23 +90,35 @@ __global__ void collab_reduce_kernel(const float* __restrict__ cpv, const int* _
   lab2[(size_t)b * S + j] = bi;
 }
 
-// pass 3: for dense point i (row i+1): w_i = sum_j P'_ij, pred_i = sum_j P'_ij pts2_j / (w_i + 1e-6)
+// pass 3, one warp per row i >= 1: lab1_i = argmax_j P_ij (first max); if it is not the background column,
+//   w_i = sum_{j>=1, lab2_j>0} P_ij,  pred_i = sum_j P_ij pts2_j / (w_i + 1e-6)      (second sweep hits L1/L2)
 __global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
-                                                            const float* __restrict__ csum, const int* __restrict__ lab1,
+                                                            const float* __restrict__ csum, int* __restrict__ lab1,
                                                             const int* __restrict__ lab2, const float* __restrict__ pts2,
                                                             float* __restrict__ wts, float* __restrict__ pred) {
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);   // dense index 0..N-1
   const int N = S - 1;
   if (i >= N) return;
+  const float* row = A + ((size_t)b * S + i + 1) * S;
+  const float rinv = 1.f / rsum[(size_t)b * S + i + 1];
+  const float* cs = csum + (size_t)b * S;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = lane; j < S; j += 32) {
+    float e = __expf(row[j] - shift);
+    float p = (e * rinv) * (e / cs[j]);
+    if (p > bv) { bv = p; bi = j; }
+  }
+  warp_argmax_first(bv, bi);
+  if (lane == 0) lab1[(size_t)b * S + i + 1] = bi;
   float w = 0.f, px = 0.f, py = 0.f, pz = 0.f;
-  if (lab1[(size_t)b * S + i + 1] > 0) {
-    const float* row = A + ((size_t)b * S + i + 1) * S;
-    const float rs = rsum[(size_t)b * S + i + 1];
+  if (bi > 0) {
+    const int* l2 = lab2 + (size_t)b * S;
     for (int j = 1 + lane; j < S; j += 32) {
-      if (lab2[(size_t)b * S + j] > 0) {
+      if (l2[j] > 0) {
         float e = __expf(row[j] - shift);
-        float p = (e / rs) * (e / csum[(size_t)b * S + j]);
+        float p = (e * rinv) * (e / cs[j]);
         const float* q = pts2 + ((size_t)b * N + (j - 1)) * 3;
         w += p; px = fmaf(p, q[0], px); py = fmaf(p, q[1], py); pz = fmaf(p, q[2], pz);
       }
@@ -250,7 +249,7 @@ S6_API int sam6d_fine_assign(const float* A, int B, int S, float shift, const fl
   S6_LAUNCH_CHECK();
   colsum_reduce_kernel<<<gc, 256, 0, st>>>(cpart, tiles, S, csum);
   S6_LAUNCH_CHECK();
-  fine_labels_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, csum, lab1, cpart, cpi);
+  fine_collabels_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, csum, cpart, cpi);
   S6_LAUNCH_CHECK();
   collab_reduce_kernel<<<gc, 256, 0, st>>>(cpart, cpi, tiles, S, lab2);
   S6_LAUNCH_CHECK();

@@ -1,0 +1,232 @@
+// pe_tc.cu -- PositionalEncoding shared MLP on the tensor cores (PEM/model/fine_point_matching.py:101-121).
+//
+// Rows are (point, sample) pairs of the ball-query groups, 128 rows per tile (4 points at nsample 32, 2 at nsample 64).
+// Per tile, in one CTA of 128 worker threads (thread <-> row) + 1 MMA warp:
+//   layer 1 (6 -> 32)   CUDA cores, fp32: x = [p_j - p_i, p_j]; h1 = relu(W1 x + b1) -> bf16 row of the A1 slab
+//   layer 2 (32 -> 64)  tcgen05.mma M128 N64 (2 x K16) into TMEM; workers read it back, + b2, ReLU, bf16 -> A2 slab
+//   layer 3 (64 -> 128) tcgen05.mma M128 N128 (4 x K16) into the same TMEM columns
+//   max-pool            tcgen05.ld + 31-shuffle transpose-reduce per 32-column chunk: lane c ends with max over the point's
+//                       rows of column c; + b3, ReLU (monotone, commutes with max); coalesced 128-byte stores
+// BatchNorm is folded into the 1x1 convs on the host.  The (B,6,N,ns) grouped tensor and the (B,128,N,ns) activations of the
+// reference are never materialised; padded duplicate samples are simply recomputed (they cannot change a max).
+// Four CTAs share an SM (56 KB smem, 128 TMEM columns each), so one tile's serial chain hides behind the others'.
+#include "tc.cuh"
+
+namespace {
+
+constexpr int ROWS = 128;
+constexpr int SLAB = ROWS * 128;            // [128 rows][64 bf16]
+constexpr int W2_SLAB = 64 * 128;           // [64 out][64 k] (k >= 32 unused)
+constexpr int W3_SLAB = 128 * 128;          // [128 out][64 k]
+constexpr int SMEM_BYTES = 2 * SLAB + W2_SLAB + W3_SLAB + 1024;
+constexpr int NUM_THREADS = 160;
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int NS>
+__global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __restrict__ pts, const int* __restrict__ idx, int N,
+                                                               long long total_points,
+                                                               const float* __restrict__ W1, const float* __restrict__ B1,
+                                                               const __nv_bfloat16* __restrict__ W2, const float* __restrict__ B2,
+                                                               const __nv_bfloat16* __restrict__ W3, const float* __restrict__ B3,
+                                                               float* __restrict__ out, int out_ld, int out_off) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* a1 = smem;
+  uint8_t* a2 = a1 + SLAB;
+  uint8_t* w2s = a2 + SLAB;
+  uint8_t* w3s = w2s + W2_SLAB;
+  __shared__ __align__(16) float w1s[32 * 8];
+  __shared__ float b1s[32], b2s[64], b3s[128];
+  __shared__ float red[2][32];
+  __shared__ __align__(8) uint64_t a1_full, d2_full, a2_full, d3_full;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int PPT = ROWS / NS;                                  // points per tile
+  const long long ntiles = (total_points + PPT - 1) / PPT;
+
+  for (int e = tid; e < 32 * 8; e += NUM_THREADS) { int r = e >> 3, c = e & 7; w1s[e] = (c < 6) ? W1[r * 6 + c] : 0.f; }
+  if (tid < 32) b1s[tid] = B1[tid];
+  if (tid < 64) b2s[tid] = B2[tid];
+  if (tid < 128) b3s[tid] = B3[tid];
+  // W2 (64 x 32) and W3 (128 x 64) bf16 -> K-major swizzled slabs
+  for (int u = tid; u < 64 * 4; u += NUM_THREADS) {
+    const int n = u >> 2, c = (u & 3) << 3;
+    *reinterpret_cast<uint4*>(w2s + tc::sw128_offset(n, c)) = *reinterpret_cast<const uint4*>(W2 + n * 32 + c);
+  }
+  for (int u = tid; u < 128 * 8; u += NUM_THREADS) {
+    const int n = u >> 3, c = (u & 7) << 3;
+    *reinterpret_cast<uint4*>(w3s + tc::sw128_offset(n, c)) = *reinterpret_cast<const uint4*>(W3 + n * 64 + c);
+  }
+  if (tid == 0) {
+    tc::mbar_init(&a1_full, 128); tc::mbar_init(&a2_full, 128);
+    tc::mbar_init(&d2_full, 1); tc::mbar_init(&d3_full, 1);
+    tc::mbar_fence_init();
+  }
+  tc::fence_proxy_async_smem();
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, 128);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = tc::umma_idesc_bf16(128, 64), idesc3 = tc::umma_idesc_bf16(128, 128);
+      const uint32_t a1_addr = tc::smem_u32(a1), a2_addr = tc::smem_u32(a2), w2_addr = tc::smem_u32(w2s), w3_addr = tc::smem_u32(w3s);
+      uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+        tc::mbar_wait(&a1_full, ph);
+        tc::tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          tc::umma_bf16(tmem_base, tc::umma_desc_sw128(a1_addr + k * 32), tc::umma_desc_sw128(w2_addr + k * 32), idesc2, k ? 1u : 0u);
+        tc::umma_commit(&d2_full);
+        tc::mbar_wait(&a2_full, ph);
+        tc::tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::umma_bf16(tmem_base, tc::umma_desc_sw128(a2_addr + k * 32), tc::umma_desc_sw128(w3_addr + k * 32), idesc3, k ? 1u : 0u);
+        tc::umma_commit(&d3_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ workers: thread <-> row of the tile
+    const int r = tid;
+    const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t ph = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
+      const long long gp = tile * PPT + r / NS;                 // global point index b*N + i
+      const bool valid = gp < total_points;
+      // ---- layer 1
+      {
+        float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) {
+          const long long b = gp / N;
+          const int j = idx[gp * NS + (r % NS)];
+          const float* pi = pts + gp * 3;
+          const float* pj = pts + (b * N + j) * 3;
+          const float jx = pj[0], jy = pj[1], jz = pj[2];
+          x[0] = jx - pi[0]; x[1] = jy - pi[1]; x[2] = jz - pi[2]; x[3] = jx; x[4] = jy; x[5] = jz;
+        }
+        uint8_t* row_ptr = a1 + r * 128;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float h[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int o = c * 8 + q * 2 + e;
+              const float4 wa = *reinterpret_cast<const float4*>(&w1s[o * 8]);
+              const float2 wb = *reinterpret_cast<const float2*>(&w1s[o * 8 + 4]);
+              float a = b1s[o];
+              a = fmaf(wa.x, x[0], a); a = fmaf(wa.y, x[1], a); a = fmaf(wa.z, x[2], a);
+              a = fmaf(wa.w, x[3], a); a = fmaf(wb.x, x[4], a); a = fmaf(wb.y, x[5], a);
+              h[e] = fmaxf(a, 0.f);
+            }
+            w[q] = tc::pack_bf16(h[0], h[1]);
+          }
+          *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a1_full);
+      }
+      // ---- layer 2 epilogue -> A2
+      tc::mbar_wait(&d2_full, ph);
+      tc::tc_fence_after_sync();
+      {
+        uint8_t* row_ptr = a2 + r * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float v[32];
+          tc::tmem_ld32(t_addr + half * 32, v);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int o = c * 8 + q * 2;
+              w[q] = tc::pack_bf16(fmaxf(v[o] + b2s[half * 32 + o], 0.f), fmaxf(v[o + 1] + b2s[half * 32 + o + 1], 0.f));
+            }
+            *reinterpret_cast<uint4*>(row_ptr + (((half * 4 + c) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        tc::tc_fence_before_sync();          // our TMEM reads are done before the issuer overwrites the columns
+        tc::fence_proxy_async_smem();
+        tc::mbar_arrive(&a2_full);
+      }
+      // ---- layer 3 epilogue: max over the rows of each point
+      tc::mbar_wait(&d3_full, ph);
+      tc::tc_fence_after_sync();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tc::tmem_ld32(t_addr + c * 32, v);
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
+        }
+        // transpose-reduce: after the 5 steps lane l holds max over the warp's 32 rows of column l
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+          const int o = 16 >> step, half = 16 >> step;
+          const bool up = (lane & o) != 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < half) {
+              float keep = up ? v[i + half] : v[i], send = up ? v[i] : v[i + half];
+              v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+            }
+          }
+        }
+        float m = v[0];
+        if (NS == 64) {
+          if (warp & 1) red[warp >> 1][lane] = m;
+          worker_bar();
+          if (!(warp & 1)) m = fmaxf(m, red[warp >> 1][lane]);
+          worker_bar();
+        }
+        const long long p_out = tile * PPT + (NS == 64 ? (warp >> 1) : warp);
+        if ((NS == 32 || !(warp & 1)) && p_out < total_points)
+          out[p_out * out_ld + out_off + c * 32 + lane] = fmaxf(m + b3s[c * 32 + lane], 0.f);
+      }
+      tc::tc_fence_before_sync();
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+
+// Same contract as sam6d_pe_mlp_max, with W2 (64,32) and W3 (128,64) in bf16 (W1 / biases fp32); cnt is not needed.
+S6_API int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, const float* W1, const float* B1,
+                               const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
+                               int out_off, void* stream) {
+  S6_REQUIRE(pts && idx && W1 && B1 && W2_bf16 && B2 && W3_bf16 && B3 && out && B >= 0 && N > 0);
+  S6_REQUIRE(ns == 32 || ns == 64);
+  if (B == 0) return 0;
+  int dev = 0, sms = 0;
+  S6_CHECK(cudaGetDevice(&dev));
+  S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long total = (long long)B * N;
+  const long long ntiles = (total + (128 / ns) - 1) / (128 / ns);
+  const int grid = (int)(ntiles < (long long)sms * 4 ? ntiles : (long long)sms * 4);
+  cudaStream_t st = s6_stream(stream);
+  const __nv_bfloat16* W2 = reinterpret_cast<const __nv_bfloat16*>(W2_bf16);
+  const __nv_bfloat16* W3 = reinterpret_cast<const __nv_bfloat16*>(W3_bf16);
+  if (ns == 32) {
+    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    pe_tc_kernel<32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3, out, out_ld, out_off);
+  } else {
+    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    pe_tc_kernel<64><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3, out, out_ld, out_off);
+  }
+  S6_LAUNCH_CHECK();
+  return 0;
+}

@@ -339,6 +339,19 @@ def pe_mlp_max(pts: Tensor, idx: Tensor, cnt: Tensor, weights, out: Tensor, out_
               _p(out), out.shape[-1], int(out_off), _s())
 
 
+def pe_mlp_max_tc(pts: Tensor, idx: Tensor, weights, out: Tensor, out_off: int):
+    """tensor-core PE MLP; weights = (W1 f32, B1, W2 bf16, B2, W3 bf16, B3)"""
+    _check(pts, torch.float32, "pts", 3)
+    _check(idx, torch.int32, "idx", 3)
+    B, N, _ = pts.shape
+    ns = idx.shape[2]
+    W1, B1, W2, B2, W3, B3 = weights
+    _check(W2, torch.bfloat16, "W2", 2)
+    _check(W3, torch.bfloat16, "W3", 2)
+    _lib.call("sam6d_pe_mlp_max_tc", _p(pts), _p(idx), B, N, ns, _p(W1), _p(B1), _p(W2), _p(B2), _p(W3), _p(B3), _p(out),
+              out.shape[-1], int(out_off), _s())
+
+
 def fine_assign(A: Tensor, pts2: Tensor, shift: float):
     _check(A, torch.float32, "atten", 3)
     _check(pts2, torch.float32, "pts2", 3)

@@ -433,6 +433,8 @@ class PositionalEncoding(nn.Module):
                     wj, bj = getattr(mlp, f"layer{j}").folded()
                     packed += [wj, bj]
                 w[name] = tuple(packed)
+                w[name + "_tc"] = (packed[0], packed[1], packed[2].to(torch.bfloat16).contiguous(), packed[3],
+                                   packed[4].to(torch.bfloat16).contiguous(), packed[5])
             w["w3"] = _W(_f32(self.mlp3.conv.weight).reshape(self.mlp3.conv.out_channels, -1))
             w["b3"] = _f32(self.mlp3.conv.bias)
             self._packed.w, self._packed.key = w, key
@@ -447,7 +449,10 @@ class PositionalEncoding(nn.Module):
         feat = torch.empty(B, N, 256, dtype=torch.float32, device=pts.device)
         for r, ns, name, off in ((self.r1, self.ns1, "m1", 0), (self.r2, self.ns2, "m2", 128)):
             idx, cnt = ops.ball_query(pts, pts, r, ns, return_count=True)
-            ops.pe_mlp_max(pts, idx, cnt, w[name], feat, off)
+            if self.precision == "bf16":
+                ops.pe_mlp_max_tc(pts, idx, w[name + "_tc"], feat, off)
+            else:
+                ops.pe_mlp_max(pts, idx, cnt, w[name], feat, off)
         return feat
 
     @torch.no_grad()

@@ -418,3 +418,33 @@ def test_geo_embed_tc(ops, S, edt):
                             sd["geo_embedding.proj_d.weight"].t().contiguous().cuda(),
                             (sd["geo_embedding.proj_a.bias"] + sd["geo_embedding.proj_d.bias"]).cuda()).cpu()
     torch.testing.assert_close(E, E32, atol=6e-2, rtol=0)
+
+
+def test_positional_encoding_tensor_core(ops):
+    """layers 2/3 of the PE shared MLP on tcgen05 (bf16 operands) against the fp32 oracle"""
+    from sam6d_b200.pem import PositionalEncoding
+    sd = po.make_state_dict(seed=5)
+    pe = PositionalEncoding(256).cuda().eval()
+    pe.load_state_dict({k[len("fine_point_matching.PE."):]: v for k, v in sd.items() if k.startswith("fine_point_matching.PE.")})
+    inp = po.make_inputs(B=3, n=2048, seed=5)
+    pts = inp["dense_po"] / (torch.norm(inp["dense_po"], dim=2).max(1)[0].reshape(-1, 1, 1) + 1e-6)
+    ref_local = torch.cat([po._shared_mlp(sd, "fine_point_matching.PE.mlp1", po._query_and_group(pts, po.PE_R1, po.PE_NS1)).max(dim=3)[0],
+                           po._shared_mlp(sd, "fine_point_matching.PE.mlp2", po._query_and_group(pts, po.PE_R2, po.PE_NS2)).max(dim=3)[0]],
+                          dim=1).transpose(1, 2)
+    pe.precision = "fp32"
+    l32 = pe.local_features(pts.cuda()).cpu()
+    torch.testing.assert_close(l32, ref_local, atol=2e-4, rtol=1e-4)
+    pe.precision = "bf16"
+    l16 = pe.local_features(pts.cuda()).cpu()
+    err = (l16 - ref_local).abs()
+    scale = ref_local.abs().mean().item()
+    print("PE tc: mean |ref|", scale, "median err", err.median().item(), "max err", err.max().item())
+    assert err.median().item() < 1e-2 * max(scale, 1.0)
+    torch.testing.assert_close(l16, ref_local, atol=8e-2 * max(scale, 1.0), rtol=5e-2)
+    # odd sizes: N not a multiple of the points-per-tile
+    pts2 = pts[:, :1023].contiguous()
+    pe.precision = "fp32"
+    a = pe.local_features(pts2.cuda()).cpu()
+    pe.precision = "bf16"
+    b = pe.local_features(pts2.cuda()).cpu()
+    torch.testing.assert_close(b, a, atol=8e-2 * max(scale, 1.0), rtol=5e-2)
