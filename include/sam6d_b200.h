@@ -30,7 +30,7 @@ int sam6d_fps(const float* xyz, int b, int n, int m, float* temp, int* idx, void
 /* _ext.gather_points (PN2/_ext_src/src/sampling.cpp:18-41, sampling_gpu.cu:13-25): points (b,c,n), idx (b,m) -> (b,c,m) */
 int sam6d_gather_points(const float* points, const int* idx, int b, int c, int n, int m, float* out, void* stream);
 
-/* channel-last form used inside the model: out[b,j,:] = src[b, idx[b,j], :], src batch stride in elements
+/* channel-last form used inside the model: out[b,j,:] = src[b, idx[b,j], :] (zeros where idx < 0), src batch stride in elements
  * (sample_pts_feats PEM/utils/model_utils.py:53-66; SparseToDenseTransformer._sample_feats PEM/model/transformer.py:651-658) */
 int sam6d_gather_rows(const float* src, const int* idx, int b, int n, int m, int c, long long src_bstride, float* out,
                       void* stream);
@@ -46,7 +46,7 @@ int sam6d_group_points(const float* points, const int* idx, int b, int c, int n,
 
 /* ---- dense linear algebra ------------------------------------------------------------------------------------ */
 
-/* C[z] = alpha * A[z] W[z]^T (+ bias) (ReLU) (+ R[z]) for z < batch.  A (M,K) lda; W (N,K) ldw (nn.Linear layout);
+/* C[z] = alpha * A[z] W[z]^T (+ bias) (act) (+ R[z]) for z < batch; `relu` is the activation code 0 none / 1 ReLU / 2 GELU(erf).  A (M,K) lda; W (N,K) ldw (nn.Linear layout);
  * C (M,N) ldc; R (M,N) ldr or NULL; sA..sR batch strides in elements (0 = shared).  fp32 CUDA-core path
  * (every nn.Linear / 1x1 conv of PEM/model/transformer.py, coarse/fine_point_matching.py; the score matrix
  * compute_feature_similarity PEM/utils/model_utils.py:114-136 as a batched call with alpha = 1/temp). */
@@ -132,6 +132,12 @@ int sam6d_weighted_procrustes(const float* src, const float* ref, const float* w
                               float eps, float* R, float* t, void* stream);
 int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const float* R, const float* t, const float* model,
                      int nm, float dis_thres, const float* radius, float* score, float* t_scaled, void* stream);
+
+/* ---- SAM ViT image encoder attention (ISM/segment_anything/modeling/image_encoder.py:224-240,325-361) ---------------- */
+/* softmax((q*scale) k^T + q.Rh + q.Rw) v per window and head (head_dim 80), flash-style.  qkv: (nW*Hs*Ws, 3*nH*80) rows
+ * [q|k|v], rel_h (2Hs-1,80), rel_w (2Ws-1,80), out (nW*Hs*Ws, nH*80).  Hs, Ws <= 64. */
+int sam6d_attn_relpos(const float* qkv, long long tok_ld, int nW, int Hs, int Ws, int nH, int head_dim, const float* rel_h,
+                      const float* rel_w, float scale, float* out, long long out_ld, void* stream);
 
 /* ---- ISM template scoring (ISM/model/loss.py:21-44, ISM/model/detector.py:198-207,260-296) ------------------------ */
 int sam6d_template_score(const float* Qn, const float* Rn, int P, int O, int T, int C, float* sim_out, float* obj_score,

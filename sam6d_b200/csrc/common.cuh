@@ -60,4 +60,11 @@ __device__ __forceinline__ void warp_argmax_first(float& v, int& i) {
 __device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
 __device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
+// activation codes of the GEMM epilogues: 0 none, 1 ReLU, 2 GELU (exact erf form, nn.GELU default)
+__device__ __forceinline__ float s6_act(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return x;
+}
+
 static inline int s6_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

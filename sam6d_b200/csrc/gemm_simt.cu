@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(GemmArgs g) {
       if (c >= g.N) continue;
       float v = acc[i][j] * g.alpha;
       if (g.bias) v += g.bias[c];
-      if (g.relu) v = fmaxf(v, 0.f);
+      v = s6_act(v, g.relu);
       if (R) v += R[(size_t)r * g.ldr + c];
       C[(size_t)r * g.ldc + c] = v;
     }

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(TcArgs g) {
           if (col < g.N) {
             float x = v[j] * g.alpha;
             if (g.bias) x += g.bias[col];
-            if (g.relu) x = fmaxf(x, 0.f);
+            x = s6_act(x, g.relu);
             if (Rrow) x += Rrow[col];
             v[j] = x;
           }

@@ -192,8 +192,9 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __r
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int j = (int)(i / c4), q = (int)(i - (long long)j * c4);
     int a = idx[(size_t)b * m + j];
-    const float4* s = reinterpret_cast<const float4*>(src + (size_t)b * src_bstride + (size_t)a * c);
-    reinterpret_cast<float4*>(out + ((size_t)b * m + j) * c)[q] = s[q];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);            // negative index = padding row (zeros)
+    if (a >= 0) v = reinterpret_cast<const float4*>(src + (size_t)b * src_bstride + (size_t)a * c)[q];
+    reinterpret_cast<float4*>(out + ((size_t)b * m + j) * c)[q] = v;
   }
 }
 __global__ void gather_rows_scalar_kernel(const float* __restrict__ src, const int* __restrict__ idx, int n, int m, int c,
@@ -203,7 +204,7 @@ __global__ void gather_rows_scalar_kernel(const float* __restrict__ src, const i
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int j = (int)(i / c), q = (int)(i - (long long)j * c);
     int a = idx[(size_t)b * m + j];
-    out[((size_t)b * m + j) * c + q] = src[(size_t)b * src_bstride + (size_t)a * c + q];
+    out[((size_t)b * m + j) * c + q] = (a >= 0) ? src[(size_t)b * src_bstride + (size_t)a * c + q] : 0.f;
   }
 }
 

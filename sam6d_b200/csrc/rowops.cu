@@ -1,4 +1,4 @@
-// rowops.cu -- one-warp-per-token kernels over C-channel rows (C = 256 in the model, any multiple of 32 up to 1024):
+// rowops.cu -- one-warp-per-token kernels over C-channel rows (C = 256 in PEM, 1280 in SAM ViT-H; any multiple of 32 up to 2048):
 // LayerNorm, L2 normalisation, the focused-linear-attention feature map, and the rigid warp of a point cloud.
 //
 // Rows are addressed as  base + (r / rows_per_batch) * batch_stride + (r % rows_per_batch) * ld  so that the
@@ -15,9 +15,10 @@ struct RowView {
   }
 };
 
-constexpr int MAXV = 32;  // per-lane values: C / 32 <= 32
+constexpr int MAXV_LIMIT = 64;  // per-lane values: C / 32 <= 64 (C <= 2048); kernels are instantiated for 8 / 32 / 64
 
 // LayerNorm(x) * gamma + beta, eps as nn.LayerNorm (PEM/model/transformer.py:156,188: nn.LayerNorm(d_model)).
+template <int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long long rows, int C, float eps) {
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
+template <int MAXV>
 __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
                                                      long long rows, int C) {
   const int lane = threadIdx.x & 31;
@@ -65,6 +67,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x
 
 // Focused linear attention feature map (PEM/model/transformer.py:541-550):
 //   q = relu(x) + 1e-6;  q = q / softplus(scale);  n = ||q||;  q = q^3;  q = q / ||q|| * n
+template <int MAXV>
 __global__ void __launch_bounds__(256) focus_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
                                                     const float* __restrict__ sp_scale, long long rows, int C) {
   const int lane = threadIdx.x & 31;
@@ -132,15 +135,21 @@ __global__ void scale_by_radius_kernel(const float* __restrict__ src, const floa
 
 }  // namespace
 
-#define ROW_ARGS_OK(C) ((C) % 32 == 0 && (C) <= 32 * MAXV && (C) > 0)
+#define ROW_ARGS_OK(C) ((C) % 32 == 0 && (C) <= 32 * MAXV_LIMIT && (C) > 0)
+#define ROW_DISPATCH(C, KERNEL, ...)                                   \
+  do {                                                                 \
+    if ((C) <= 256) KERNEL<8> __VA_ARGS__;                             \
+    else if ((C) <= 1024) KERNEL<32> __VA_ARGS__;                      \
+    else KERNEL<64> __VA_ARGS__;                                       \
+  } while (0)
 
 S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                            long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
                            float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  layernorm_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
-                                                                    RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
+  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+               RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps));
   S6_LAUNCH_CHECK();
   return 0;
 }
@@ -149,8 +158,8 @@ S6_API int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstrid
                              long long y_bstride, long long y_ld, long long rows, int C, void* stream) {
   S6_REQUIRE(x && y && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  l2norm_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
-                                                                 RowView{y_rpb, y_bstride, y_ld}, rows, C);
+  ROW_DISPATCH(C, l2norm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+               RowView{y_rpb, y_bstride, y_ld}, rows, C));
   S6_LAUNCH_CHECK();
   return 0;
 }
@@ -160,8 +169,8 @@ S6_API int sam6d_focus_rows(const float* x, long long x_rpb, long long x_bstride
                             void* stream) {
   S6_REQUIRE(x && y && softplus_scale && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  focus_kernel<<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
-                                                                RowView{y_rpb, y_bstride, y_ld}, softplus_scale, rows, C);
+  ROW_DISPATCH(C, focus_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
+               RowView{y_rpb, y_bstride, y_ld}, softplus_scale, rows, C));
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -103,8 +103,9 @@ def group_points(points: Tensor, idx: Tensor) -> Tensor:
 
 # ---------------------------------------------------------------------------------------------- dense algebra
 def gemm(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None,
-         out: Optional[Tensor] = None, relu: bool = False, alpha: float = 1.0) -> Tensor:
-    """out = alpha * A @ W^T (+bias) (relu) (+residual); A (M,K), W (N,K) contiguous f32."""
+         out: Optional[Tensor] = None, relu=False, alpha: float = 1.0) -> Tensor:
+    """out = alpha * A @ W^T (+bias) (act) (+residual); A (M,K), W (N,K) contiguous f32.  relu: False/True or the activation
+    code (0 none, 1 ReLU, 2 GELU)."""
     _check(A, torch.float32, "A", 2)
     _check(W, torch.float32, "W", 2)
     M, K = A.shape
@@ -391,6 +392,22 @@ def pose_score(pts1: Tensor, lab1: Tensor, R: Tensor, t: Tensor, model: Tensor, 
     _lib.call("sam6d_pose_score", _p(pts1), _p(lab1), B, N, _p(R), _p(t), _p(model), model.shape[1], _f(dis_thres),
               _p(radius), _p(score), _p(ts), _s())
     return score, ts
+
+
+# ---------------------------------------------------------------------------------------------- SAM encoder attention
+def attn_relpos(qkv: Tensor, nW: int, Hs: int, Ws: int, nH: int, rel_h: Tensor, rel_w: Tensor, scale: float) -> Tensor:
+    """qkv (nW*Hs*Ws, 3*nH*80) f32 -> (nW*Hs*Ws, nH*80) f32"""
+    _check(qkv, torch.float32, "qkv", 2)
+    _check(rel_h, torch.float32, "rel_pos_h", 2)
+    _check(rel_w, torch.float32, "rel_pos_w", 2)
+    T, C3 = qkv.shape
+    C = C3 // 3
+    if T != nW * Hs * Ws or rel_h.shape[0] != 2 * Hs - 1 or rel_w.shape[0] != 2 * Ws - 1:
+        raise RuntimeError("attn_relpos: shape mismatch")
+    out = torch.empty(T, C, dtype=torch.float32, device=qkv.device)
+    _lib.call("sam6d_attn_relpos", _p(qkv), _ll(C3), int(nW), int(Hs), int(Ws), int(nH), C // nH, _p(rel_h), _p(rel_w), _f(scale),
+              _p(out), _ll(C), _s())
+    return out
 
 
 # ---------------------------------------------------------------------------------------------- ISM scoring

@@ -136,6 +136,33 @@ def run_case(mods, tag, B, n, coarse_npoint, seed, out_dir, store_inputs):
     print(f"  wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def run_sam_case(out_dir):
+    """SAM image encoder: the vendored reference module against oracle/sam_oracle.py (2 blocks of ViT-H width: one windowed,
+    one global, 1024^2 input -- every code path of the 32-block model)."""
+    from oracle import sam_oracle as so
+    sys.path.insert(0, os.path.join(REF, "Instance_Segmentation_Model"))
+    from functools import partial
+    from segment_anything.modeling.image_encoder import ImageEncoderViT
+    cfg = dict(embed_dim=1280, depth=2, num_heads=16, global_attn_indexes=(1,))
+    print("case sam_small:", cfg)
+    sd = so.make_state_dict(seed=1, **cfg)
+    ref = ImageEncoderViT(depth=cfg["depth"], embed_dim=cfg["embed_dim"], img_size=1024, mlp_ratio=4,
+                          norm_layer=partial(torch.nn.LayerNorm, eps=1e-6), num_heads=cfg["num_heads"], patch_size=16,
+                          qkv_bias=True, use_rel_pos=True, global_attn_indexes=cfg["global_attn_indexes"], window_size=14,
+                          out_chans=256).eval()
+    print("  reference ImageEncoderViT accepted the oracle state_dict (strict):", ref.load_state_dict(sd, strict=True))
+    img = so.make_images(B=1, seed=1)
+    with torch.no_grad():
+        r = ref(img)
+    o = so.image_encoder(sd, img, cfg["num_heads"], cfg["global_attn_indexes"])
+    check("image_encoder output", r, o, 1e-4)
+    gold = dict(meta=dict(cfg=cfg, seed=1, img_seed=1, source="segment_anything ImageEncoderViT imported from /root/reference"),
+                out_sub=r[:, :, ::4, ::4].clone(), out_sum=r.double().sum().item(), out_abs_mean=r.abs().mean().item())
+    path = os.path.join(out_dir, "sam_small.pt")
+    torch.save(gold, path)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
@@ -145,6 +172,7 @@ def main():
     run_case(mods, "small", B=2, n=256, coarse_npoint=32, seed=3, out_dir=out_dir, store_inputs=True)
     # full BASELINE shapes for one proposal pair: inputs regenerated from the seed
     run_case(mods, "full", B=4, n=2048, coarse_npoint=196, seed=1, out_dir=out_dir, store_inputs=False)
+    run_sam_case(out_dir)
 
 
 if __name__ == "__main__":
