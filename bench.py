@@ -102,6 +102,79 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_ism(args):
+    """BASELINE.json config #3: SAM ViT-H image encoder + 42-template cosine scoring on a batch of synthetic frames.
+    Secondary line (the headline metric of the repo is the PEM poses/s line): python bench.py --workload ism"""
+    from oracle import sam_oracle as so, ism_oracle as io
+    from sam6d_b200 import _lib, ism
+    from sam6d_b200.sam import build_image_encoder
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    F_, P, O, T = args.batch if args.batch != B_PER_GPU else 16, 64, 8, 42
+    enc = build_image_encoder("vit_h", precision=args.precision).to(dev).eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for prm in enc.parameters():                           # seeded random weights of the ViT-H architecture
+            prm.copy_(torch.randn(prm.shape, generator=g) * (0.02 if prm.dim() > 1 else 0.05))
+        for m in enc.modules():
+            if isinstance(m, torch.nn.LayerNorm) or m.__class__.__name__ == "LayerNorm2d":
+                m.weight.fill_(1.0); m.bias.zero_()
+    host = [so.make_images(B=F_, seed=10 + s).pin_memory() for s in range(2)]
+    resident = [h.to(dev) for h in host]
+    q, r = io.make_descriptors(P=F_ * P, O=O, T=T, C=1024, seed=3)
+    qd, rd = q.to(dev), r.to(dev)
+    qh = q.pin_memory()
+
+    def step(i, e2e=False):
+        img = host[i % 2].to(dev, non_blocking=True) if e2e else resident[i % 2]
+        emb = enc(img)
+        sel = ism.compute_semantic_score(qh.to(dev, non_blocking=True) if e2e else qd, rd)
+        if e2e:
+            return emb[:, :, 0, 0].cpu(), sel[3].cpu()
+        return emb, sel
+
+    def timed(steps, e2e):
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i, e2e)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), _lib.launch_count() - l0
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    ms, launches = timed(args.steps, False)
+    ms_e2e, _ = timed(args.steps, True)
+    pk = peaks()
+    flops = 5.96e12 * F_                                          # SURVEY.md 8d: 5.96 TFLOP per 1024^2 frame
+    ach = flops * args.steps / (ms * 1e-3) / 1e12
+    line = dict(metric="frames/sec", value=F_ * args.steps / (ms * 1e-3), unit="frames/s", n_gpus=1, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                config=dict(workload="ism_sam_vith_encoder_plus_template_scoring", frames_per_step=F_, image="1024x1024 (640x480 frame resized+padded)",
+                            proposals_per_frame=P, objects=O, templates=T, cache="activations per step (>3 GB) exceed L2"),
+                e2e=dict(value=F_ * args.steps / (ms_e2e * 1e-3), unit="frames/s", h2d_bytes_per_step=host[0].numel() * 4 + qh.numel() * 4,
+                         d2h_bytes_per_step=F_ * 256 * 4 + F_ * P * 8),
+                gpu_launches=launches,
+                roofline=dict(kernel="whole encoder (tcgen05 GEMMs + attention)", bound="tensor", achieved=ach, peak=pk["tensor"], unit="TFLOP/s",
+                              frac=ach / pk["tensor"], traffic=None, peak_source=pk["source"] + " bf16_tflops_sustained"))
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            so.image_encoder(sd, host[0][:1].clone(), 16, (7, 15, 23, 31))
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = dict(value=1.0 / dt, unit="frames/s", cores=threads, kind="port",
+                                    sample=f"1 of the {F_} frames through the full 32-block ViT-H encoder, one pass, {dt:.1f} s, torch fp32")
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -112,9 +185,13 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core exact path")
+    ap.add_argument("--workload", default="pem", choices=["pem", "ism"],
+                    help="pem: BASELINE config #2 (headline); ism: config #3, SAM ViT-H encoder + template scoring")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "ism":
+        return run_ism(args)
 
     import torch.distributed as dist
     from oracle import pem_oracle as po           # synthetic inputs + seeded weights only (generator, not a compute path)

@@ -60,12 +60,21 @@ int sam6d_gemm_bf16(const void* A, int a_dtype, const void* W, int w_dtype, cons
                     int c_dtype, int M, int N, int K, long long lda, long long ldw, long long ldc, long long ldr, int batch,
                     long long sA, long long sW, long long sC, long long sR, float alpha, int relu, void* stream);
 
+/* Persistent TMA-fed version for plain (non-batched) bf16 operands: cp.async.bulk.tensor boxes with SWIZZLE_128B feed a
+ * 4-stage ring, two TMEM accumulators overlap epilogue and MMA.  A (M,K) bf16, W (N,K) bf16, C fp32 (0) / bf16 (1). */
+int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const float* R, void* C, int c_dtype, int M, int N, int K,
+                   long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream);
+
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
 
 /* nn.LayerNorm(C) (PEM/model/transformer.py:156,188,423,572) */
 int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                     long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
                     float eps, void* stream);
+/* same, writing bf16 rows (the A operand of the next tensor-core GEMM) */
+int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                         long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                         float eps, void* stream);
 /* F.normalize(x, p=2, dim=-1) (PEM/utils/model_utils.py:124-126; ISM/model/loss.py:32-33) */
 int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                       long long y_bstride, long long y_ld, long long rows, int C, void* stream);
@@ -137,7 +146,7 @@ int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const flo
 /* softmax((q*scale) k^T + q.Rh + q.Rw) v per window and head (head_dim 80), flash-style.  qkv: (nW*Hs*Ws, 3*nH*80) rows
  * [q|k|v], rel_h (2Hs-1,80), rel_w (2Ws-1,80), out (nW*Hs*Ws, nH*80).  Hs, Ws <= 64. */
 int sam6d_attn_relpos(const float* qkv, long long tok_ld, int nW, int Hs, int Ws, int nH, int head_dim, const float* rel_h,
-                      const float* rel_w, float scale, float* out, long long out_ld, void* stream);
+                      const float* rel_w, float scale, void* out, int out_is_bf16, long long out_ld, void* stream);
 
 /* ---- ISM template scoring (ISM/model/loss.py:21-44, ISM/model/detector.py:198-207,260-296) ------------------------ */
 int sam6d_template_score(const float* Qn, const float* Rn, int P, int O, int T, int C, float* sim_out, float* obj_score,

@@ -8,6 +8,7 @@
 //   warp  8    MMA issuer: one thread issues 4 x tcgen05.mma (M128 N256 K16) per 64-wide k-block, tcgen05.commit frees the stage
 //   warps 0-3  epilogue  : tcgen05.ld 32 lanes x 32 columns -> bias / ReLU / residual -> global
 // Two CTAs fit per SM (2 x 98 KB smem, 2 x 256 TMEM columns) so one tile's epilogue overlaps the other's loads and MMAs.
+#include "epilogue.cuh"
 #include "tc.cuh"
 
 namespace {
@@ -71,7 +72,7 @@ __device__ __forceinline__ void stage_tile(const T* __restrict__ base, long long
   }
 }
 
-template <typename AT, typename WT, typename OT>
+template <typename AT, typename WT, typename OT, int ACT, bool HAS_BIAS, bool HAS_RES>
 __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(TcArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -130,50 +131,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(TcArgs g) {
     // ------------------------------------------------------------------ epilogue (warps 0-3 <-> TMEM lanes 32w..32w+31)
     tc::mbar_wait(&tmem_full_bar, 0);
     tc::tc_fence_after_sync();
-    const int row = m0 + warp * 32 + lane;
-    const bool row_ok = row < g.M;
-    OT* Crow = reinterpret_cast<OT*>(g.C) + (size_t)z * g.sC + (size_t)row * g.ldc;
-    const float* Rrow = g.R ? g.R + (size_t)z * g.sR + (size_t)row * g.ldr : nullptr;
+    // all MMAs of this (single) tile have completed, so the operand ring is free: reuse it as the store-transpose staging
+    float* stage = reinterpret_cast<float*>(smem) + warp * epi::WARP_STAGE_FLOATS;
+    OT* Cz = reinterpret_cast<OT*>(g.C) + (size_t)z * g.sC;
+    const float* Rz = g.R ? g.R + (size_t)z * g.sR : nullptr;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       const int col0 = n0 + c * 32;
       if (col0 >= g.N) break;
       float v[32];
       tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-      if (row_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = col0 + j;
-          if (col < g.N) {
-            float x = v[j] * g.alpha;
-            if (g.bias) x += g.bias[col];
-            x = s6_act(x, g.relu);
-            if (Rrow) x += Rrow[col];
-            v[j] = x;
-          }
-        }
-        if constexpr (sizeof(OT) == 4) {
-          if (col0 + 32 <= g.N && (g.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(Crow + col0) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(Crow) + col0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) reinterpret_cast<float*>(Crow)[col0 + j] = v[j];
-          }
-        } else {
-          if (col0 + 32 <= g.N && (g.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(Crow + col0) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(Crow) + col0 + j) =
-                  make_uint4(tc::pack_bf16(v[j], v[j + 1]), tc::pack_bf16(v[j + 2], v[j + 3]), tc::pack_bf16(v[j + 4], v[j + 5]),
-                             tc::pack_bf16(v[j + 6], v[j + 7]));
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < g.N) reinterpret_cast<__nv_bfloat16*>(Crow)[col0 + j] = __float2bfloat16(v[j]);
-          }
-        }
-      }
+      epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES>(v, stage, lane, m0 + warp * 32, g.M, col0, g.N, g.alpha, g.bias, Rz, g.ldr, Cz, g.ldc);
     }
   }
   tc::tc_fence_before_sync();
@@ -184,11 +152,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 2) gemm_tc_kernel(TcArgs g) {
 template <typename AT, typename WT, typename OT>
 int launch(const TcArgs& g, int batch, cudaStream_t st) {
   const size_t smem = STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tc_kernel<AT, WT, OT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
   dim3 grid(s6_cdiv(g.N, BN), s6_cdiv(g.M, BM), batch);
-  kern<<<grid, NUM_THREADS, smem, st>>>(g);
+  cudaError_t e = cudaSuccess;
+#define LAUNCH_TC(ACT, HB, HR)                                                                    \
+  do {                                                                                            \
+    auto kern = gemm_tc_kernel<AT, WT, OT, ACT, HB, HR>;                                          \
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (e != cudaSuccess) return (int)e;                                                          \
+    kern<<<grid, NUM_THREADS, smem, st>>>(g);                                                     \
+  } while (0)
+  EPI_DISPATCH(g.relu, g.bias, g.R, LAUNCH_TC);
+#undef LAUNCH_TC
   e = cudaGetLastError();
   return (int)e;
 }
@@ -199,7 +173,7 @@ int launch(const TcArgs& g, int batch, cudaStream_t st) {
 S6_API int sam6d_gemm_bf16(const void* A, int a_dtype, const void* W, int w_dtype, const float* bias, const float* R, void* C,
                            int c_dtype, int M, int N, int K, long long lda, long long ldw, long long ldc, long long ldr, int batch,
                            long long sA, long long sW, long long sC, long long sR, float alpha, int relu, void* stream) {
-  S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && batch >= 0 && (K % 8) == 0);
+  S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && batch >= 0 && (K % 8) == 0 && relu >= 0 && relu <= 2);
   if (M == 0 || batch == 0) return 0;
   S6_REQUIRE(batch <= 65535 && s6_cdiv(M, BM) <= 65535);
   const int am = a_dtype ? 8 : 4, wm = w_dtype ? 8 : 4;

@@ -1,0 +1,196 @@
+// gemm_tma.cu -- persistent, TMA-fed bf16 GEMM on tcgen05:   C = act(A W^T + bias) (+ R),   A (M,K) bf16, W (N,K) bf16.
+//
+// One CTA per SM loops over 128 x 256 output tiles (m fastest, so CTAs running together share the same W tile in L2):
+//   warp 0   TMA producer : cp.async.bulk.tensor 2-D boxes {64 k, 128 rows} of A and {64 k, 256 rows} of W, SWIZZLE_128B,
+//                           straight into the UMMA K-major slabs of a 4-stage ring (48 KB per stage); out-of-range rows /
+//                           columns are zero-filled by the TMA unit
+//   warp 1   MMA issuer   : 4 x tcgen05.mma M128 N256 K16 per stage into one of two 256-column TMEM accumulators,
+//                           tcgen05.commit releases the stage / publishes the accumulator
+//   warps 2-5 epilogue    : tcgen05.ld -> alpha, bias, activation, residual -> fp32 or bf16, transposed through shared memory
+//                           into full-line global stores (epilogue.cuh); overlaps the next tile's loads and MMAs through
+//                           the second accumulator
+// No register staging and no LSU traffic for the operands: the CUDA-core staged kernel (gemm_tc.cu) tops out near 8 GB/s per
+// CTA of operand traffic, this one is bounded by L2 -> SM bandwidth and the tensor pipe.
+#include <cuda.h>
+
+#include "epilogue.cuh"
+#include "tc.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+
+struct Args {
+  const float* bias; const float* R; void* C;
+  int M, N, K;
+  long long ldc, ldr;
+  float alpha;
+  int act;
+};
+
+template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmW, Args g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
+  const long long ntiles = (long long)m_tiles * n_tiles;
+  const int nkb = (g.K + BK - 1) / BK;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 128); }
+    tc::mbar_fence_init();
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  tc::tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      long long gk = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (int)(tile % m_tiles) * BM, n0 = (int)(tile / m_tiles) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++gk) {
+          const int s = (int)(gk % STAGES);
+          tc::mbar_wait(&empty_bar[s], (uint32_t)(((gk / STAGES) & 1) ^ 1));
+          tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+          uint8_t* a_slab = smem + s * STAGE_BYTES;
+          tc::tma_load_2d(&tmA, &full_bar[s], a_slab, kb * BK, m0);
+          tc::tma_load_2d(&tmW, &full_bar[s], a_slab + A_BYTES, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
+      long long gk = 0, it = 0;
+      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        tc::mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc::tc_fence_after_sync();
+        const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++gk) {
+          const int s = (int)(gk % STAGES);
+          tc::mbar_wait(&full_bar[s], (uint32_t)((gk / STAGES) & 1));
+          tc::tc_fence_after_sync();
+          const uint32_t a_addr = tc::smem_u32(smem + s * STAGE_BYTES), b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16(d_addr, tc::umma_desc_sw128(a_addr + k * 32), tc::umma_desc_sw128(b_addr + k * 32), idesc, (kb | k) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);
+        }
+        tc::umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: warp w -> TMEM lanes 32*(w%4) ..
+    const int quad = warp & 3;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + quad * epi::WARP_STAGE_FLOATS;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const int m0 = (int)(tile % m_tiles) * BM, n0 = (int)(tile / m_tiles) * BN;
+      tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+      tc::tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= g.N) break;
+        float v[32];
+        tc::tmem_ld32(t_addr + c * 32, v);
+        epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias, g.R, g.ldr,
+                                                       reinterpret_cast<OT*>(g.C), g.ldc);
+      }
+      tc::tc_fence_before_sync();
+      tc::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  tc::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major (rows, K) tensor with row stride ld (elements); box = {64, box_rows}, 128-byte swizzle
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long K, long long ld, int box_rows) {
+  EncodeFn enc = get_encode();
+  if (!enc) return 999;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
+}
+
+}  // namespace
+
+// A (M,K) bf16 lda, W (N,K) bf16 ldw, C (M,N) fp32 (c_dtype 0) or bf16 (1), bias (N) fp32 or NULL, R (M,N) fp32 or NULL.
+// K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, 16-byte aligned bases.  act: 0 none, 1 ReLU, 2 GELU(erf).
+S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const float* R, void* C, int c_dtype, int M, int N, int K,
+                          long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream) {
+  S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && act >= 0 && act <= 2);
+  S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  if (M == 0) return 0;
+  CUtensorMap tmA, tmW;
+  int rc = make_map(&tmA, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_map(&tmW, W, N, K, ldw, BN);
+  if (rc) return rc;
+  int dev = 0, sms = 0;
+  S6_CHECK(cudaGetDevice(&dev));
+  S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const long long ntiles = (long long)s6_cdiv(M, BM) * s6_cdiv(N, BN);
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act};
+  cudaStream_t st = s6_stream(stream);
+#define LAUNCH_TMA(ACT, HB, HR)                                                                                        \
+  do {                                                                                                                 \
+    if (c_dtype) {                                                                                                     \
+      auto k = gemm_tma_kernel<__nv_bfloat16, ACT, HB, HR>;                                                            \
+      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                      \
+      k<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmW, g);                                                           \
+    } else {                                                                                                           \
+      auto k = gemm_tma_kernel<float, ACT, HB, HR>;                                                                    \
+      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                      \
+      k<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmW, g);                                                           \
+    }                                                                                                                  \
+  } while (0)
+  EPI_DISPATCH(act, bias, R, LAUNCH_TMA);
+#undef LAUNCH_TMA
+  S6_LAUNCH_CHECK();
+  return 0;
+}

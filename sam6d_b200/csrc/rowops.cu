@@ -18,15 +18,18 @@ struct RowView {
 constexpr int MAXV_LIMIT = 64;  // per-lane values: C / 32 <= 64 (C <= 2048); kernels are instantiated for 8 / 32 / 64
 
 // LayerNorm(x) * gamma + beta, eps as nn.LayerNorm (PEM/model/transformer.py:156,188: nn.LayerNorm(d_model)).
-template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
+__device__ __forceinline__ void st_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <int MAXV, typename OT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const float* xp = x + xv.off(r);
-  float* yp = y + yv.off(r);
+  OT* yp = y + yv.off(r);
   const int nv = C >> 5;
   float v[MAXV];
   float s = 0.f;
@@ -41,7 +44,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
-    if (i < nv) { int c = lane + 32 * i; yp[c] = (v[i] - mean) * rstd * gamma[c] + beta[c]; }
+    if (i < nv) { int c = lane + 32 * i; st_out(yp + c, (v[i] - mean) * rstd * gamma[c] + beta[c]); }
 }
 
 // F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
@@ -138,11 +141,12 @@ __global__ void scale_by_radius_kernel(const float* __restrict__ src, const floa
 #define ROW_ARGS_OK(C) ((C) % 32 == 0 && (C) <= 32 * MAXV_LIMIT && (C) > 0)
 #define ROW_DISPATCH(C, KERNEL, ...)                                   \
   do {                                                                 \
-    if ((C) <= 256) KERNEL<8> __VA_ARGS__;                             \
-    else if ((C) <= 1024) KERNEL<32> __VA_ARGS__;                      \
-    else KERNEL<64> __VA_ARGS__;                                       \
+    if ((C) <= 256) KERNEL<8 ROW_EXTRA> __VA_ARGS__;                   \
+    else if ((C) <= 1024) KERNEL<32 ROW_EXTRA> __VA_ARGS__;            \
+    else KERNEL<64 ROW_EXTRA> __VA_ARGS__;                             \
   } while (0)
 
+#define ROW_EXTRA , float
 S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                            long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
                            float eps, void* stream) {
@@ -153,6 +157,22 @@ S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride,
   S6_LAUNCH_CHECK();
   return 0;
 }
+
+#undef ROW_EXTRA
+#define ROW_EXTRA , __nv_bfloat16
+// same, writing bf16 rows (the A operand of the next tensor-core GEMM)
+S6_API int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                                long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                                float eps, void* stream) {
+  S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld},
+               reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps));
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+#undef ROW_EXTRA
+#define ROW_EXTRA
 
 S6_API int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                              long long y_bstride, long long y_ld, long long rows, int C, void* stream) {

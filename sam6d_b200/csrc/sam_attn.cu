@@ -14,9 +14,13 @@ namespace {
 
 constexpr int D = 80, DP = 84, KT = 64, QT = 32, MAXS = 64;
 
+__device__ __forceinline__ void st_o(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_o(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename OT>
 __global__ void __launch_bounds__(256) sam_attn_kernel(const float* __restrict__ qkv, long long tok_ld, int Hs, int Ws, int nH,
                                                        const float* __restrict__ rel_h, const float* __restrict__ rel_w,
-                                                       float scale, float* __restrict__ out, long long out_ld) {
+                                                       float scale, OT* __restrict__ out, long long out_ld) {
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;                         // KT * DP
   float* vs = ks + KT * DP;               // KT * D
@@ -141,10 +145,10 @@ __global__ void __launch_bounds__(256) sam_attn_kernel(const float* __restrict__
     const int n = n0 + qi;
     const float inv = 1.f / warp_sum(lrun[qi]);
     if (n < L) {
-      float* op = out + ((size_t)win * L + n) * out_ld + head * D;
-      op[lane] = o0[qi] * inv;
-      op[lane + 32] = o1[qi] * inv;
-      if (lane < 16) op[64 + lane] = o2[qi] * inv;
+      OT* op = out + ((size_t)win * L + n) * out_ld + head * D;
+      st_o(op + lane, o0[qi] * inv);
+      st_o(op + lane + 32, o1[qi] * inv);
+      if (lane < 16) st_o(op + 64 + lane, o2[qi] * inv);
     }
   }
 }
@@ -154,15 +158,22 @@ __global__ void __launch_bounds__(256) sam_attn_kernel(const float* __restrict__
 // qkv: (nW * Hs*Ws tokens, 3 * nH * 80) fp32 rows [q | k | v] with head-major channels (the output layout of the qkv Linear),
 // row stride tok_ld; rel_h (2*Hs-1, 80), rel_w (2*Ws-1, 80); out (nW * Hs*Ws, nH*80) with row stride out_ld.  Hs, Ws <= 64.
 S6_API int sam6d_attn_relpos(const float* qkv, long long tok_ld, int nW, int Hs, int Ws, int nH, int head_dim, const float* rel_h,
-                             const float* rel_w, float scale, float* out, long long out_ld, void* stream) {
+                             const float* rel_w, float scale, void* out, int out_is_bf16, long long out_ld, void* stream) {
   S6_REQUIRE(qkv && rel_h && rel_w && out && nW >= 0 && Hs > 0 && Ws > 0 && Hs <= MAXS && Ws <= MAXS && nH > 0);
   S6_REQUIRE(head_dim == D && (tok_ld % 4) == 0);
   if (nW == 0) return 0;
   S6_REQUIRE(nW <= 65535 && nH <= 65535);
   const size_t smem = ((size_t)KT * DP + KT * D + 8 * D * 4 + 8 * KT * 4 + 2 * 8 * MAXS * 4) * sizeof(float);
-  S6_CHECK(cudaFuncSetAttribute(sam_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(s6_cdiv(Hs * Ws, QT), nH, nW);
-  sam_attn_kernel<<<grid, 256, smem, s6_stream(stream)>>>(qkv, tok_ld, Hs, Ws, nH, rel_h, rel_w, scale, out, out_ld);
+  if (out_is_bf16) {
+    S6_CHECK(cudaFuncSetAttribute(sam_attn_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sam_attn_kernel<__nv_bfloat16><<<grid, 256, smem, s6_stream(stream)>>>(qkv, tok_ld, Hs, Ws, nH, rel_h, rel_w, scale,
+                                                                           reinterpret_cast<__nv_bfloat16*>(out), out_ld);
+  } else {
+    S6_CHECK(cudaFuncSetAttribute(sam_attn_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sam_attn_kernel<float><<<grid, 256, smem, s6_stream(stream)>>>(qkv, tok_ld, Hs, Ws, nH, rel_h, rel_w, scale,
+                                                                   reinterpret_cast<float*>(out), out_ld);
+  }
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -156,6 +156,24 @@ def gemm_tc(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Optio
     return out
 
 
+def gemm_tma(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, out: Optional[Tensor] = None,
+             act: int = 0, alpha: float = 1.0, out_dtype=torch.float32) -> Tensor:
+    """persistent TMA-fed tcgen05 GEMM: A (M,K) bf16, W (N,K) bf16 -> (M,N) fp32|bf16"""
+    _check(A, torch.bfloat16, "A", 2)
+    _check(W, torch.bfloat16, "W", 2)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K:
+        raise RuntimeError("gemm: inner dimensions differ")
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=A.device)
+    if residual is not None:
+        _check(residual, torch.float32, "residual", 2)
+    _lib.call("sam6d_gemm_tma", _p(A), _p(W), _p(bias), _p(residual), _p(out), _DT[out.dtype], M, N, K, _ll(K), _ll(K), _ll(N), _ll(N),
+              _f(alpha), int(act), _s())
+    return out
+
+
 def layernorm_raw(x_ptr, x_view, y_ptr, y_view, gamma: Tensor, beta: Tensor, rows: int, C: int, eps: float = 1e-5):
     _lib.call("sam6d_layernorm", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
               ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(gamma), _p(beta), _ll(rows), int(C),
@@ -169,6 +187,28 @@ def layernorm(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Op
     if out is None:
         out = torch.empty_like(x)
     layernorm_raw(x.data_ptr(), (rows, 0, C), out.data_ptr(), (rows, 0, C), gamma, beta, rows, C, eps)
+    return out
+
+
+def layernorm_bf16(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    """LayerNorm with bf16 output rows (feeds the TMA GEMM directly)"""
+    _check(x, torch.float32, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("sam6d_layernorm_bf16", _p(x), _ll(rows), _ll(0), _ll(C), _p(out), _ll(rows), _ll(0), _ll(C), _p(gamma), _p(beta),
+              _ll(rows), int(C), _f(eps), _s())
+    return out
+
+
+def gather_rows_bf16(src: Tensor, idx: Tensor) -> Tensor:
+    """channel-last gather of bf16 rows (C even): moved as C/2 32-bit words by the fp32 gather kernel"""
+    _check(src, torch.bfloat16, "src", 3)
+    _check(idx, torch.int32, "idx", 2)
+    b, n, c = src.shape
+    m = idx.shape[1]
+    out = torch.empty(b, m, c, dtype=torch.bfloat16, device=src.device)
+    _lib.call("sam6d_gather_rows", _p(src), _p(idx), b, n, m, c // 2, _ll(n * c // 2), _p(out), _s())
     return out
 
 
@@ -395,8 +435,9 @@ def pose_score(pts1: Tensor, lab1: Tensor, R: Tensor, t: Tensor, model: Tensor, 
 
 
 # ---------------------------------------------------------------------------------------------- SAM encoder attention
-def attn_relpos(qkv: Tensor, nW: int, Hs: int, Ws: int, nH: int, rel_h: Tensor, rel_w: Tensor, scale: float) -> Tensor:
-    """qkv (nW*Hs*Ws, 3*nH*80) f32 -> (nW*Hs*Ws, nH*80) f32"""
+def attn_relpos(qkv: Tensor, nW: int, Hs: int, Ws: int, nH: int, rel_h: Tensor, rel_w: Tensor, scale: float,
+                out_dtype=torch.float32) -> Tensor:
+    """qkv (nW*Hs*Ws, 3*nH*80) f32 -> (nW*Hs*Ws, nH*80) f32|bf16"""
     _check(qkv, torch.float32, "qkv", 2)
     _check(rel_h, torch.float32, "rel_pos_h", 2)
     _check(rel_w, torch.float32, "rel_pos_w", 2)
@@ -404,9 +445,9 @@ def attn_relpos(qkv: Tensor, nW: int, Hs: int, Ws: int, nH: int, rel_h: Tensor, 
     C = C3 // 3
     if T != nW * Hs * Ws or rel_h.shape[0] != 2 * Hs - 1 or rel_w.shape[0] != 2 * Ws - 1:
         raise RuntimeError("attn_relpos: shape mismatch")
-    out = torch.empty(T, C, dtype=torch.float32, device=qkv.device)
+    out = torch.empty(T, C, dtype=out_dtype, device=qkv.device)
     _lib.call("sam6d_attn_relpos", _p(qkv), _ll(C3), int(nW), int(Hs), int(Ws), int(nH), C // nH, _p(rel_h), _p(rel_w), _f(scale),
-              _p(out), _ll(C), _s())
+              _p(out), int(out_dtype == torch.bfloat16), _ll(C), _s())
     return out
 
 

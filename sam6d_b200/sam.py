@@ -180,6 +180,9 @@ class ImageEncoderViT(nn.Module):
         ws = max((b.window_size for b in self.blocks), default=0) or 14
         maps = self._index_maps(B, G, ws, x.device)
         for blk, bw in zip(self.blocks, w["blocks"]):
+            if prec == "bf16":
+                tok = self._block_bf16(blk, bw, tok, B, L, C, G, maps)
+                continue
             xn = ops.layernorm(tok, bw["n1w"], bw["n1b"], eps=bw["eps1"])
             if blk.window_size > 0:
                 xw = ops.gather_rows(xn.view(B, L, C), maps["part"]).view(-1, C)            # zero rows at the padding
@@ -206,6 +209,28 @@ class ImageEncoderViT(nn.Module):
             acc = _gemm(prec, shifted, Wt, None, residual=acc)
         out = ops.layernorm(acc, w["ln2"][0], w["ln2"][1], eps=w["ln2"][2])
         return out.view(B, G, G, oc).permute(0, 3, 1, 2).contiguous()
+
+
+def _block_bf16(self, blk, bw, tok, B, L, C, G, maps):
+    """one Block with bf16 operands everywhere the tensor cores read them (the residual stream `tok` stays fp32):
+    LayerNorm -> bf16 rows -> TMA GEMM; attention writes bf16; the GELU hidden activations live in bf16."""
+    xn = ops.layernorm_bf16(tok, bw["n1w"], bw["n1b"], eps=bw["eps1"])
+    if blk.window_size > 0:
+        xw = ops.gather_rows_bf16(xn.view(B, L, C), maps["part"]).view(-1, C)
+        nW, Hs = B * maps["nwin"] * maps["nwin"], blk.window_size
+    else:
+        xw, nW, Hs = xn, B, G
+    qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"])                                      # fp32: the attention kernel's input
+    att = ops.attn_relpos(qkv, nW, Hs, Hs, self.num_heads, bw["rh"], bw["rw"], blk.attn.scale, out_dtype=torch.bfloat16)
+    if blk.window_size > 0:
+        att = ops.gather_rows_bf16(att.view(B, -1, C), maps["unpart"]).view(-1, C)
+    tok = ops.gemm_tma(att, bw["proj"].bf16, bw["proj_b"], residual=tok)
+    xn = ops.layernorm_bf16(tok, bw["n2w"], bw["n2b"], eps=bw["eps2"])
+    h = ops.gemm_tma(xn, bw["l1"].bf16, bw["l1b"], act=_ACT_GELU, out_dtype=torch.bfloat16)
+    return ops.gemm_tma(h, bw["l2"].bf16, bw["l2b"], residual=tok)
+
+
+ImageEncoderViT._block_bf16 = _block_bf16
 
 
 def build_image_encoder(name: str = "vit_h", precision: str = "bf16") -> ImageEncoderViT:

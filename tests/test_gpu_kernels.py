@@ -448,3 +448,19 @@ def test_positional_encoding_tensor_core(ops):
     pe.precision = "bf16"
     b = pe.local_features(pts2.cuda()).cpu()
     torch.testing.assert_close(b, a, atol=8e-2 * max(scale, 1.0), rtol=5e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 3840, 1280), (1000, 512, 256), (130, 40, 64), (2049, 2049, 256), (300, 1280, 5120)])
+@pytest.mark.parametrize("odt", [torch.float32, torch.bfloat16])
+def test_gemm_tma(ops, M, N, K, odt):
+    A = torch.randn(M, K, generator=G(1))
+    W = torch.randn(N, K, generator=G(2)) / math.sqrt(K)
+    bias = torch.randn(N, generator=G(3))
+    R = torch.randn(M, N, generator=G(4))
+    ref = torch.nn.functional.gelu(A.bfloat16().double() @ W.bfloat16().double().t() * 0.5 + bias.double()) + R.double()
+    got = ops.gemm_tma(A.cuda().bfloat16(), W.cuda().bfloat16(), bias.cuda(), residual=R.cuda(), act=2, alpha=0.5, out_dtype=odt).cpu()
+    assert got.dtype == odt
+    if odt == torch.float32:
+        torch.testing.assert_close(got.double(), ref, atol=1e-4, rtol=1e-5)     # fp32 accumulation order over K <= 5120
+    else:
+        torch.testing.assert_close(got.double(), ref, atol=3e-2, rtol=1e-2)
