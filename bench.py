@@ -299,7 +299,7 @@ def main():
         traffic = None
         prof = os.path.join(ROOT, "profiles", "rpe_scores_traffic.json")
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            traffic = json.load(open(prof)).get("bf16" if args.precision == "bf16" else "fp32", {}).get("dram_bytes_per_launch")
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
