@@ -109,6 +109,16 @@ int sam6d_rpe_scores(const void* E, int e_is_bf16, const float* U, long long u_l
 int sam6d_mha(const float* Q, long long q_ld, long long q_bs, const float* K, long long k_ld, long long k_bs, const float* V,
               long long v_ld, long long v_bs, const float* bias, int B, int H, int Sq, int Sk, float scale, float* O,
               long long o_ld, long long o_bs, void* stream);
+/* Tensor-core attention for <= 256 keys (tcgen05 QK^T and PV, TMA-fed, whole score row in TMEM; csrc/attn_tc.cu):
+ * Q / K bf16 column slices of row-major matrices, Vt = V^T per (batch, head) as bf16 (B*H*D, vt_ld) rows; bias_mode 0 none,
+ * 1 dense fp32 (B,H,Sq,Sk) [PEM rel-pos scores], 2 decomposed rel-pos [SAM windows; rel_h = both tables pre-packed as bf16
+ * UMMA slabs, see ops.pack_rel_pos]; bv value bias (H*D) or NULL. */
+int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                  long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
+                  const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
+                  int out_is_bf16, long long out_ld, void* stream);
+/* V (tokens x channels, bf16 column slice at col0 of a (nB*L, ld) matrix) -> V^T (nB*C rows, N1 >= L keys), zero padded */
+int sam6d_transpose_tokens_bf16(const void* src, long long ld, int col0, int C, int nB, int L, int N1, void* out, void* stream);
 /* LinearAttention kv-first branch (PEM/model/transformer.py:552-559) */
 int sam6d_linattn_kv(const float* Kf, long long k_ld, long long k_bs, const float* V, long long v_ld, long long v_bs, int B,
                      int H, int J, float* KV, float* KS, void* stream);
@@ -135,7 +145,7 @@ int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, 
                         const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
                         int out_off, void* stream);
 /* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls */
-int sam6d_fine_assign(const float* A, int B, int S, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
+int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
                       int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream);
 int sam6d_weighted_procrustes(const float* src, const float* ref, const float* wts, int B, int N, float weight_thresh,
                               float eps, float* R, float* t, void* stream);

@@ -14,21 +14,21 @@ namespace {
 constexpr int RT = 32;  // rows per tile in the column-reducing passes
 
 // pass 1: rsum (B,S); column partial sums cpart (B,tiles,S)
-__global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict__ A, int S, float shift, float* __restrict__ rsum,
+__global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict__ A, int S, int ld, float shift, float* __restrict__ rsum,
                                                         float* __restrict__ cpart) {
   __shared__ float racc[RT];
   const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int i0 = tile * RT;
   if (tid < RT) racc[tid] = 0.f;
   __syncthreads();
-  const float* Ab = A + (size_t)b * S * S;
+  const float* Ab = A + (size_t)b * S * ld;
   for (int j0 = 0; j0 < S; j0 += 256) {
     const int j = j0 + tid;
     float cacc = 0.f;
     for (int r = 0; r < RT; ++r) {
       const int i = i0 + r;
       if (i >= S) break;
-      float e = (j < S) ? __expf(Ab[(size_t)i * S + j] - shift) : 0.f;
+      float e = (j < S) ? __expf(Ab[(size_t)i * ld + j] - shift) : 0.f;
       cacc += e;
       float rs = warp_sum(e);
       if (lane == 0) atomicAdd(&racc[r], rs);
@@ -49,7 +49,7 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ cpart, int tiles,
 
 // pass 2: column labels lab2[b,j] = argmax_i P_ij (first max) as per-tile partials.  Along a column the factor
 // e_ij / csum_j ... is shared, so P_ij is ordered like e_ij * (e_ij / rsum_i); we evaluate the full product like the reference.
-__global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
+__global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rsum,
                                                              const float* __restrict__ csum, float* __restrict__ cpv,
                                                              int* __restrict__ cpi) {
   __shared__ float rinv[RT];
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __rest
   const int i0 = tile * RT;
   if (tid < RT) rinv[tid] = (i0 + tid < S) ? 1.f / rsum[(size_t)b * S + i0 + tid] : 0.f;
   __syncthreads();
-  const float* Ab = A + (size_t)b * S * S;
+  const float* Ab = A + (size_t)b * S * ld;
   for (int j0 = 0; j0 < S; j0 += 256) {
     const int j = j0 + tid;
     if (j >= S) break;
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __rest
     for (int r = 0; r < RT; ++r) {
       const int i = i0 + r;
       if (i < S) {
-        float e = __expf(Ab[(size_t)i * S + j] - shift);
+        float e = __expf(Ab[(size_t)i * ld + j] - shift);
         float p = (e * rinv[r]) * (e * cinv);
         if (p > cbv) { cbv = p; cbi = i; }                     // ascending i: first max wins
       }
@@ -92,7 +92,7 @@ __global__ void collab_reduce_kernel(const float* __restrict__ cpv, const int* _
 
 // pass 3, one warp per row i >= 1: lab1_i = argmax_j P_ij (first max); if it is not the background column,
 //   w_i = sum_{j>=1, lab2_j>0} P_ij,  pred_i = sum_j P_ij pts2_j / (w_i + 1e-6)      (second sweep hits L1/L2)
-__global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, float shift, const float* __restrict__ rsum,
+__global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rsum,
                                                             const float* __restrict__ csum, int* __restrict__ lab1,
                                                             const int* __restrict__ lab2, const float* __restrict__ pts2,
                                                             float* __restrict__ wts, float* __restrict__ pred) {
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restr
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);   // dense index 0..N-1
   const int N = S - 1;
   if (i >= N) return;
-  const float* row = A + ((size_t)b * S + i + 1) * S;
+  const float* row = A + ((size_t)b * S + i + 1) * ld;
   const float rinv = 1.f / rsum[(size_t)b * S + i + 1];
   const float* cs = csum + (size_t)b * S;
   float bv = -INFINITY;
@@ -235,26 +235,26 @@ __global__ void __launch_bounds__(1024) pose_score_kernel(const float* __restric
 
 }  // namespace
 
-// A (B,S,S) f32 score matrix (row/col 0 = background), pts2 (B,S-1,3).
+// A (B,S,S) f32 score matrix with row stride ld >= S (row/col 0 = background), pts2 (B,S-1,3).
 // Outputs: lab1 (B,S) i32 (row argmax of P; entry 0 unused), lab2 (B,S) i32, wts (B,S-1), pred (B,S-1,3).
 // Scratch: rsum (B,S), csum (B,S), cpart (B,tiles,S) f32, cpi (B,tiles,S) i32, tiles = ceil(S/32).
-S6_API int sam6d_fine_assign(const float* A, int B, int S, float shift, const float* pts2, float* rsum, float* csum,
+S6_API int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum,
                              float* cpart, int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream) {
-  S6_REQUIRE(A && pts2 && rsum && csum && cpart && cpi && lab1 && lab2 && wts && pred && B >= 0 && S >= 2);
+  S6_REQUIRE(A && pts2 && rsum && csum && cpart && cpi && lab1 && lab2 && wts && pred && B >= 0 && S >= 2 && ld >= S);
   if (B == 0) return 0;
   cudaStream_t st = s6_stream(stream);
   const int tiles = s6_cdiv(S, RT);
   dim3 gt(tiles, B), gc(s6_cdiv(S, 256), B);
-  fine_sums_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, cpart);
+  fine_sums_kernel<<<gt, 256, 0, st>>>(A, S, ld, shift, rsum, cpart);
   S6_LAUNCH_CHECK();
   colsum_reduce_kernel<<<gc, 256, 0, st>>>(cpart, tiles, S, csum);
   S6_LAUNCH_CHECK();
-  fine_collabels_kernel<<<gt, 256, 0, st>>>(A, S, shift, rsum, csum, cpart, cpi);
+  fine_collabels_kernel<<<gt, 256, 0, st>>>(A, S, ld, shift, rsum, csum, cpart, cpi);
   S6_LAUNCH_CHECK();
   collab_reduce_kernel<<<gc, 256, 0, st>>>(cpart, cpi, tiles, S, lab2);
   S6_LAUNCH_CHECK();
   dim3 gw(s6_cdiv(S - 1, 8), B);
-  fine_weighted_kernel<<<gw, 256, 0, st>>>(A, S, shift, rsum, csum, lab1, lab2, pts2, wts, pred);
+  fine_weighted_kernel<<<gw, 256, 0, st>>>(A, S, ld, shift, rsum, csum, lab1, lab2, pts2, wts, pred);
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -9,9 +9,10 @@
 //                           the swizzled A slab of a 4-deep k-block ring (16 KB per 128x64 slab)
 //   MMA issuer (warp 8)   : 4 x tcgen05.mma M128 N256 K16 per k-block into one of two 256-column TMEM accumulators
 //   epilogue (warps 0-3)  : tcgen05.ld; pass ANGLE: rows are (pair, k) quadruples (k = 3 unused), max over k by a 24-shuffle
-//                           transpose-reduce, each lane stores its 8-column share -> E ; pass DIST: rows are pairs,
-//                           E += acc + bias (read-modify-write of the ANGLE result).
+//                           transpose-reduce, each lane adds its 8-column share into E ; pass DIST (runs first): rows are
+//                           pairs, E = acc + bias with full-line stores (epilogue.cuh).
 // E is fp32 or bf16.  Accuracy: operands rounded to bf16 (sin/cos via MUFU), fp32 accumulation.
+#include "epilogue.cuh"
 #include "tc.cuh"
 
 namespace {
@@ -20,7 +21,8 @@ constexpr int BM = 128, BN = 256, BK = 64, KBLOCKS = 4, ASTAGES = 4;
 constexpr int A_SLAB = BM * BK * 2;          // 16 KB
 constexpr int W_SLAB = BN * BK * 2;          // 32 KB
 constexpr int NUM_THREADS = 288;
-constexpr int SMEM_BYTES = KBLOCKS * W_SLAB + ASTAGES * A_SLAB + 1024;
+constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
+constexpr int SMEM_BYTES = KBLOCKS * W_SLAB + ASTAGES * A_SLAB + EPI_BYTES + 1024;
 
 template <typename ET>
 __device__ __forceinline__ void store8(ET* p, const float v[8]);
@@ -147,14 +149,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
     long long it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
+      const int r = warp * 32 + lane;
+      // angle pass: E already holds proj_d(...) + biases from the distance pass; fetch this lane's 8 x 8 columns of it before
+      // waiting for the accumulator so the read-modify-write latency hides behind the MMAs of the tile
+      constexpr int RAW = (MODE == 0) ? 8 : 1;
+      uint4 raw[RAW][sizeof(ET) == 4 ? 2 : 1];
+      if (MODE == 0) {
+        const long long pair = tile * 32 + (r >> 2);
+        if (pair < npairs) {
+          const uint4* src = reinterpret_cast<const uint4*>(E + pair * 256 + (r & 3) * 8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[c * (sizeof(ET) == 4 ? 8 : 4) + u];
+        }
+      }
       tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
-      const int r = warp * 32 + lane;
       const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
       if (MODE == 0) {
         const long long pair = tile * 32 + (r >> 2);
         const int q = r & 3;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < 8; ++c) {
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
@@ -177,25 +193,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
             float keep = up1 ? m[8 + i] : m[i], send = up1 ? m[i] : m[8 + i];
             o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
           }
-          if (pair < npairs) store8<ET>(E + pair * 256 + c * 32 + q * 8, o);
+          if (pair < npairs) {
+            float e[8];
+            load8<ET>(reinterpret_cast<const ET*>(&raw[c][0]), e);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] += o[i];
+            store8<ET>(E + pair * 256 + c * 32 + q * 8, e);
+          }
         }
       } else {
-        const long long pair = tile * 128 + r;
+        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * A_SLAB) + warp * epi::WARP_STAGE_FLOATS;
+        const long long row0 = tile * 128 + warp * 32;
+        (void)raw;
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
-          if (pair < npairs) {
-            ET* dst = E + pair * 256 + c * 32;
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float e[8];
-              load8<ET>(dst + h * 8, e);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) e[i] += v[h * 8 + i] + bias[c * 32 + h * 8 + i];
-              store8<ET>(dst + h * 8, e);
-            }
-          }
+          // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch)
+          epi::process_chunk<ET, 0, true, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, bias, nullptr, 0, E, 256);
         }
       }
       tc::tc_fence_before_sync();
@@ -226,7 +241,7 @@ int launch_pass(const float* T, long long npairs, const float* div_term, const _
 // bias = proj_a.bias + proj_d.bias (fp32); div_term: the module buffer (128 frequencies).  Two persistent launches.
 S6_API int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div_term, const void* Wa_bf16, const void* Wd_bf16,
                               const float* bias, void* E, int e_is_bf16, void* stream) {
-  S6_REQUIRE(T && div_term && Wa_bf16 && Wd_bf16 && bias && E && npairs >= 0);
+  S6_REQUIRE(T && div_term && Wa_bf16 && Wd_bf16 && bias && E && npairs >= 0 && npairs < 2000000000LL);
   if (npairs == 0) return 0;
   int dev = 0, sms = 0;
   S6_CHECK(cudaGetDevice(&dev));
@@ -236,13 +251,13 @@ S6_API int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div
   const __nv_bfloat16* Wd = reinterpret_cast<const __nv_bfloat16*>(Wd_bf16);
   int rc;
   if (e_is_bf16) {
-    rc = launch_pass<0, __nv_bfloat16>(T, npairs, div_term, Wa, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
-    if (rc) return rc;
     rc = launch_pass<1, __nv_bfloat16>(T, npairs, div_term, Wd, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
-  } else {
-    rc = launch_pass<0, float>(T, npairs, div_term, Wa, bias, reinterpret_cast<float*>(E), sms, st);
     if (rc) return rc;
+    rc = launch_pass<0, __nv_bfloat16>(T, npairs, div_term, Wa, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
+  } else {
     rc = launch_pass<1, float>(T, npairs, div_term, Wd, bias, reinterpret_cast<float*>(E), sms, st);
+    if (rc) return rc;
+    rc = launch_pass<0, float>(T, npairs, div_term, Wa, bias, reinterpret_cast<float*>(E), sms, st);
   }
   return rc;
 }

@@ -302,6 +302,53 @@ def mha_raw(q_ptr, q_ld, q_bs, k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, bias: Optio
               ctypes.c_void_p(o_ptr), _ll(o_ld), _ll(o_bs), _s())
 
 
+def pack_rel_pos(rel_h: Tensor, rel_w: Tensor) -> Tensor:
+    """rel_pos_h / rel_pos_w ((2S-1, D) fp32, S <= 16) -> the bf16 image attn_tc bulk-copies into shared memory: for each table
+    ceil(D/64) slabs of [32 rows][64 channels], K-major with the 128-byte swizzle (16-byte chunk index XOR (row % 8))."""
+    D = rel_h.shape[1]
+    DS = (D + 63) // 64
+    blob = torch.zeros(2 * DS * 32 * 64, dtype=torch.bfloat16, device=rel_h.device)
+    j = torch.arange(32, device=rel_h.device).view(32, 1)
+    c = torch.arange(D, device=rel_h.device).view(1, D)
+    off = j * 64 + ((((c % 64) // 8) ^ (j % 8)) * 8) + (c % 8)                     # element offset inside a slab
+    for t, tab in enumerate((rel_h, rel_w)):
+        n = tab.shape[0]
+        idx = ((t * DS + c // 64) * 32 * 64 + off)[:n]
+        blob[idx.reshape(-1)] = tab.to(torch.bfloat16).reshape(-1)
+    return blob
+
+
+def attn_tc(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, Vt: Tensor, B: int, H: int, Sq: int, Sk: int, D: int, scale: float,
+            bias: Optional[Tensor] = None, rel: Optional[tuple] = None, bv: Optional[Tensor] = None,
+            out_dtype=torch.float32, bias_variant: int = 1) -> Tensor:
+    """tensor-core attention (<= 256 keys).  Q, K: bf16 2-D matrices (rows = batch*tokens); Vt: bf16 (B*H*D, >= ceil16(Sk));
+    bias: dense fp32 (B,H,Sq,Sk); rel = (rel_h, rel_w, Hs, Ws) for the decomposed rel-pos bias.  -> (B*Sq, H*D) fp32"""
+    _check(Q, torch.bfloat16, "Q", 2)
+    _check(K, torch.bfloat16, "K", 2)
+    _check(Vt, torch.bfloat16, "Vt", 2)
+    mode, rh, rw, Hs, Ws = 0, None, None, 0, 0
+    if bias is not None:
+        _check(bias, torch.float32, "bias", 4)
+        mode = bias_variant
+    elif rel is not None:
+        rh, Hs, Ws = rel                     # rh: pack_rel_pos(rel_pos_h, rel_pos_w)
+        mode = 2
+    out = torch.empty(B * Sq, H * D, dtype=out_dtype, device=Q.device)
+    _lib.call("sam6d_attn_tc", _p(Q), _ll(Q.shape[1]), int(q_col0), _p(K), _ll(K.shape[1]), int(k_col0), _p(Vt), _ll(Vt.shape[1]),
+              int(B), int(H), int(Sq), int(Sk), int(D), mode, _p(bias), _p(rh), _p(rw), int(Hs), int(Ws), _p(bv), _f(scale), _p(out),
+              int(out_dtype == torch.bfloat16), _ll(H * D), _s())
+    return out
+
+
+def transpose_tokens(src: Tensor, col0: int, C: int, nB: int, L: int) -> Tensor:
+    """V^T for attn_tc: src bf16 (nB*L, ld) -> (nB*C, ceil16(L)) bf16, zero padded keys"""
+    _check(src, torch.bfloat16, "src", 2)
+    N1 = (L + 15) // 16 * 16
+    out = torch.empty(nB * C, N1, dtype=torch.bfloat16, device=src.device)
+    _lib.call("sam6d_transpose_tokens_bf16", _p(src), _ll(src.shape[1]), int(col0), int(C), int(nB), int(L), int(N1), _p(out), _s())
+    return out
+
+
 def linattn_kv_raw(k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, B, H, J, KV: Tensor, KS: Tensor):
     _lib.call("sam6d_linattn_kv", ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs), ctypes.c_void_p(v_ptr), _ll(v_ld), _ll(v_bs),
               int(B), int(H), int(J), _p(KV), _p(KS), _s())
@@ -394,9 +441,12 @@ def pe_mlp_max_tc(pts: Tensor, idx: Tensor, weights, out: Tensor, out_off: int):
 
 
 def fine_assign(A: Tensor, pts2: Tensor, shift: float):
-    _check(A, torch.float32, "atten", 3)
+    """A: (B,S,S) fp32, contiguous or a [:, :, :S] view of a (B,S,ld) allocation (padded rows for aligned stores)"""
+    if A.dim() != 3 or A.dtype != torch.float32 or not A.is_cuda or A.stride(2) != 1 or A.stride(0) != A.shape[1] * A.stride(1):
+        raise RuntimeError("atten must be a CUDA fp32 (B,S,S) tensor with dense rows")
     _check(pts2, torch.float32, "pts2", 3)
     B, S, _ = A.shape
+    ld = A.stride(1)
     dev = A.device
     tiles = (S + 31) // 32
     rsum = torch.empty(B, S, dtype=torch.float32, device=dev)
@@ -407,7 +457,7 @@ def fine_assign(A: Tensor, pts2: Tensor, shift: float):
     lab2 = torch.zeros(B, S, dtype=torch.int32, device=dev)
     wts = torch.empty(B, S - 1, dtype=torch.float32, device=dev)
     pred = torch.empty(B, S - 1, 3, dtype=torch.float32, device=dev)
-    _lib.call("sam6d_fine_assign", _p(A), B, S, _f(shift), _p(pts2), _p(rsum), _p(csum), _p(cpart), _p(cpi), _p(lab1),
+    _lib.call("sam6d_fine_assign", _p(A), B, S, int(ld), _f(shift), _p(pts2), _p(rsum), _p(csum), _p(cpart), _p(cpi), _p(lab1),
               _p(lab2), _p(wts), _p(pred), _s())
     return lab1, lab2, wts, pred
 

@@ -115,6 +115,17 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
+def _stack2(a: torch.Tensor, b: torch.Tensor) -> Optional[torch.Tensor]:
+    """The scene cloud and the template cloud go through the same weights in most layers.  When their tensors are the two
+    halves of one allocation (Net.forward builds them that way) return the (2B, ...) view so one launch serves both clouds;
+    otherwise None and the caller makes two calls (the reference API passes them as separate arguments)."""
+    if (a.shape == b.shape and a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous() and a.device == b.device
+            and a.untyped_storage().data_ptr() == b.untyped_storage().data_ptr()
+            and b.storage_offset() == a.storage_offset() + a.numel()):
+        return torch.as_strided(a, (2 * a.shape[0],) + tuple(a.shape[1:]), a.stride(), a.storage_offset())
+    return None
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # shared token-layer math
 # ---------------------------------------------------------------------------------------------------------------------
@@ -169,6 +180,9 @@ class GeometricTransformer(nn.Module):
             ca = self.layers[1].attention.attention
             self._packed.w = dict(
                 w_self=_W(w_self), b_self=b_self.contiguous(), tail_self=_pack_tail(self.layers[0]),
+                # tensor-core attention path: q|k|v as one bf16 GEMM, the folded rel-pos queries u as a second (fp32) one
+                w_qkv=_W(w_self[:3 * C]), b_qkv=b_self[:3 * C].contiguous(), w_u=_W(w_self[3 * C:]), b_u=b_self[3 * C:].contiguous(),
+                wq_only=_W(ca.proj_q.weight),
                 wq_c=_W(ca.proj_q.weight), bq_c=_f32(ca.proj_q.bias),
                 wkv_c=_W(torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_v.weight)], dim=0)),
                 bkv_c=torch.cat([_f32(ca.proj_k.bias), _f32(ca.proj_v.bias)], dim=0).contiguous(),
@@ -179,6 +193,14 @@ class GeometricTransformer(nn.Module):
     def _self_layer(self, x: torch.Tensor, emb: torch.Tensor, w) -> torch.Tensor:
         B, S, C = x.shape
         x2d = x.reshape(B * S, C)
+        if self.precision == "bf16" and S <= 256:
+            d = C // NUM_HEADS
+            qkv = ops.gemm_tc(x2d, w["w_qkv"].bf16, w["b_qkv"], out_dtype=torch.bfloat16)          # (B*S, q|k|v) bf16
+            u = ops.gemm_tc(x2d, w["w_u"].bf16, w["b_u"])                                            # (B*S, 4*C) fp32
+            sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
+            vt = ops.transpose_tokens(qkv, 2 * C, C, B, S)
+            hid = ops.attn_tc(qkv, 0, qkv, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp)
+            return _attn_tail(self.precision, x2d, hid, w["tail_self"]).view(B, S, C)
         ld = 3 * C + NUM_HEADS * C
         qkvu = _gemm(self.precision, x2d, w["w_self"], w["b_self"])              # (B*S, q|k|v|u0..u3)
         base, f = qkvu.data_ptr(), 4
@@ -192,6 +214,13 @@ class GeometricTransformer(nn.Module):
         B, S, C = x.shape
         Sm = mem.shape[1]
         x2d = x.reshape(B * S, C)
+        if self.precision == "bf16" and Sm <= 256:
+            d = C // NUM_HEADS
+            q = ops.gemm_tc(x2d, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
+            kv = ops.gemm_tc(mem.reshape(B * Sm, C), w["wkv_c"].bf16, w["bkv_c"], out_dtype=torch.bfloat16)
+            vt = ops.transpose_tokens(kv, C, C, B, Sm)
+            hid = ops.attn_tc(q, 0, kv, 0, vt, B, NUM_HEADS, S, Sm, d, 1.0 / math.sqrt(d))
+            return _attn_tail(self.precision, x2d, hid, w["tail_cross"]).view(B, S, C)
         q = _gemm(self.precision, x2d, w["wq_c"], w["bq_c"])
         kv = _gemm(self.precision, mem.reshape(B * Sm, C), w["wkv_c"], w["bkv_c"])
         hid = torch.empty(B * S, C, dtype=torch.float32, device=x.device)
@@ -204,8 +233,16 @@ class GeometricTransformer(nn.Module):
         if masks0 is not None or masks1 is not None:
             raise NotImplementedError("key masks are never used on the SAM-6D inference path")
         w = self._weights()
-        feats0 = self._self_layer(feats0.contiguous(), embeddings0, w)
-        feats1 = self._self_layer(feats1.contiguous(), embeddings1, w)
+        emb = _stack2(embeddings0, embeddings1) if feats0.shape == feats1.shape else None
+        if emb is not None:
+            # both clouds share the self-attention weights: one batch of 2B through every kernel of the layer
+            B = feats0.shape[0]
+            f = _stack2(feats0, feats1)
+            f = self._self_layer(f if f is not None else torch.cat([feats0, feats1], dim=0), emb, w)
+            feats0, feats1 = f[:B], f[B:]
+        else:
+            feats0 = self._self_layer(feats0.contiguous(), embeddings0, w)
+            feats1 = self._self_layer(feats1.contiguous(), embeddings1, w)
         feats0 = self._cross_layer(feats0, feats1, w)
         feats1 = self._cross_layer(feats1, feats0, w)      # sequential: sees the updated feats0 (transformer.py:505-507)
         return feats0, feats1
@@ -279,14 +316,15 @@ def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_
     M = feat2.shape[1]
     f1 = ops.l2norm_rows(feat1.contiguous()) if normalize_feat else feat1.contiguous()
     f2 = ops.l2norm_rows(feat2.contiguous()) if normalize_feat else feat2.contiguous()
-    A = torch.empty(B, N, M, dtype=torch.float32, device=feat1.device)
+    ld = (M + 3) // 4 * 4                      # rows padded to 16 bytes so the epilogue can use full-line vector stores
+    store = torch.empty(B, N, ld, dtype=torch.float32, device=feat1.device)
     if precision == "bf16":
-        ops.gemm_tc_raw(f1.data_ptr(), 0, f2.data_ptr(), 0, None, 0, A.data_ptr(), 0, N, M, C, C, C, M, 0, batch=B, sA=N * C,
-                        sW=M * C, sC=N * M, alpha=1.0 / temp)
+        ops.gemm_tc_raw(f1.data_ptr(), 0, f2.data_ptr(), 0, None, 0, store.data_ptr(), 0, N, M, C, C, C, ld, 0, batch=B, sA=N * C,
+                        sW=M * C, sC=N * ld, alpha=1.0 / temp)
     else:
-        ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, A.data_ptr(), N, M, C, C, C, M, 0, batch=B, sA=N * C, sW=M * C,
-                     sC=N * M, alpha=1.0 / temp)
-    return A
+        ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, store.data_ptr(), N, M, C, C, C, ld, 0, batch=B, sA=N * C, sW=M * C,
+                     sC=N * ld, alpha=1.0 / temp)
+    return store[:, :, :M]                     # (B,N,M) like the reference; dense rows, row stride ld
 
 
 def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_proposal2=300, rand=None, return_scores=False):
@@ -296,7 +334,7 @@ def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_pro
     B = pts1.shape[0]
     if model_pts is None:
         model_pts = pts2
-    W, w1 = ops.coarse_assign(atten.contiguous())
+    W, w1 = ops.coarse_assign(atten.contiguous())   # (B,197,197): the copy out of the padded rows is 5 MB
     if rand is None:
         rand = torch.rand(B, n_proposal1 * 3, device=pts1.device)
     idx = ops.coarse_sample(W, rand.contiguous())
@@ -313,7 +351,7 @@ def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, temp=0.1,
     if model_pts is None:
         model_pts = pts2
     pts1, pts2 = pts1.contiguous(), pts2.contiguous()
-    lab1, _, wts, pred = ops.fine_assign(atten.contiguous(), pts2, shift=1.0 / temp)
+    lab1, _, wts, pred = ops.fine_assign(atten, pts2, shift=1.0 / temp)
     R, t = ops.weighted_procrustes(pred, pts1, wts, 0.0, 1e-5)
     rad = radius if radius is not None else torch.ones(pts1.shape[0], device=pts1.device) - 1e-6
     score, t_scaled = ops.pose_score(pts1, lab1, R, t, model_pts.contiguous(), rad.contiguous(), dis_thres)
@@ -360,8 +398,13 @@ class CoarsePointMatching(nn.Module):
     def forward(self, p1, f1, geo1, p2, f2, geo2, radius, end_points, rand=None):
         if self.training:
             raise NotImplementedError("sam6d_b200 implements the inference path (model.eval())")
-        f1 = self._embed(f1.contiguous())
-        f2 = self._embed(f2.contiguous())
+        f12 = _stack2(f1, f2)
+        if f12 is not None:
+            e = self._embed(f12)
+            f1, f2 = e[:f1.shape[0]], e[f1.shape[0]:]
+        else:
+            f1 = self._embed(f1.contiguous())
+            f2 = self._embed(f2.contiguous())
         for blk in self.transformers:
             f1, f2 = blk(f1, geo1, f2, geo2)
         B, S, H = f1.shape
@@ -563,6 +606,14 @@ class SparseToDenseTransformer(nn.Module):
         w = self._weights()
         ext0 = torch.cat([torch.zeros_like(fps_idx0[:, :1]), fps_idx0], dim=1).contiguous()
         ext1 = torch.cat([torch.zeros_like(fps_idx1[:, :1]), fps_idx1], dim=1).contiguous()
+        dense = _stack2(dense_feats0, dense_feats1)
+        if dense is not None:
+            # one batch of 2B clouds through the gather, the (shared-weight) dense linear-attention layer and its FFN
+            B = dense_feats0.shape[0]
+            feats = self._sample_feats(dense, torch.cat([ext0, ext1], dim=0))
+            feats0, feats1 = self.sparse_layer(feats[:B], embeddings0, feats[B:], embeddings1, masks0, masks1)
+            out = self._dense_layer(dense, torch.cat([feats0, feats1], dim=0), w)
+            return out[:B], out[B:]
         feats0 = self._sample_feats(dense_feats0.contiguous(), ext0)
         feats1 = self._sample_feats(dense_feats1.contiguous(), ext1)
         feats0, feats1 = self.sparse_layer(feats0, embeddings0, feats1, embeddings1, masks0, masks1)
@@ -617,14 +668,24 @@ class FinePointMatching(nn.Module):
             raise NotImplementedError("sam6d_b200 implements the inference path (model.eval())")
         p1, p2 = p1.contiguous(), p2.contiguous()
         p1_ = ops.rigid_warp(p1, end_points['init_R'].contiguous(), end_points['init_t'].contiguous())
-        f1 = self._embed(f1.contiguous(), p1_)
-        f2 = self._embed(f2.contiguous(), p2)
+        f12 = _stack2(f1, f2) if p1.shape == p2.shape else None
+        if f12 is not None:
+            e = self._embed(f12, torch.cat([p1_, p2], dim=0))              # both clouds: one PE pass, one in_proj GEMM
+            f1, f2 = e[:p1.shape[0]], e[p1.shape[0]:]
+        else:
+            f1 = self._embed(f1.contiguous(), p1_)
+            f2 = self._embed(f2.contiguous(), p2)
         for blk in self.transformers:
             f1, f2 = blk(f1, geo1, fps_idx1, f2, geo2, fps_idx2)
         B, S, H = f1.shape
         w = self._weights()
-        o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
-        o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        f12 = _stack2(f1, f2)
+        if f12 is not None:
+            o = _gemm(self.precision, f12.reshape(2 * B * S, H), w["w_out"], w["b_out"]).view(2 * B, S, -1)
+            o1, o2 = o[:B], o[B:]
+        else:
+            o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+            o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
         atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
         pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
@@ -701,11 +762,24 @@ class Net(nn.Module):
             raise NotImplementedError("sam6d_b200 implements the inference path: call model.eval()")
         dense_pm, dense_fm, dense_po, dense_fo, radius = self._features(end_points)
         B = dense_pm.size(0)
-        bg_point = torch.ones(B, 1, 3, dtype=torch.float32, device=dense_pm.device) * 100
-        sparse_pm, sparse_fm, fps_idx_m = sample_pts_feats(dense_pm, dense_fm, self.coarse_npoint, return_index=True)
-        geo_embedding_m = self.geo_embedding(torch.cat([bg_point, sparse_pm], dim=1))
-        sparse_po, sparse_fo, fps_idx_o = sample_pts_feats(dense_po, dense_fo, self.coarse_npoint, return_index=True)
-        geo_embedding_o = self.geo_embedding(torch.cat([bg_point, sparse_po], dim=1))
+        if dense_pm.shape == dense_po.shape and dense_fm.shape == dense_fo.shape:
+            # Scene and template clouds share every weight up to the cross-attention, so they travel as the two halves of
+            # one (2B, ...) allocation: FPS, the geometric embedding, PE, the self-attention and dense layers each run once
+            # on 2B clouds; the views below keep the reference's two-argument interfaces.
+            pts2 = torch.cat([dense_pm, dense_po], dim=0)
+            fts2 = torch.cat([dense_fm, dense_fo], dim=0)
+            dense_pm, dense_po, dense_fm, dense_fo = pts2[:B], pts2[B:], fts2[:B], fts2[B:]
+            sp, sf, idx = sample_pts_feats(pts2, fts2, self.coarse_npoint, return_index=True)
+            bg_point = torch.ones(2 * B, 1, 3, dtype=torch.float32, device=pts2.device) * 100
+            geo = self.geo_embedding(torch.cat([bg_point, sp], dim=1))
+            sparse_pm, sparse_po, sparse_fm, sparse_fo = sp[:B], sp[B:], sf[:B], sf[B:]
+            fps_idx_m, fps_idx_o, geo_embedding_m, geo_embedding_o = idx[:B], idx[B:], geo[:B], geo[B:]
+        else:
+            bg_point = torch.ones(B, 1, 3, dtype=torch.float32, device=dense_pm.device) * 100
+            sparse_pm, sparse_fm, fps_idx_m = sample_pts_feats(dense_pm, dense_fm, self.coarse_npoint, return_index=True)
+            geo_embedding_m = self.geo_embedding(torch.cat([bg_point, sparse_pm], dim=1))
+            sparse_po, sparse_fo, fps_idx_o = sample_pts_feats(dense_po, dense_fo, self.coarse_npoint, return_index=True)
+            geo_embedding_o = self.geo_embedding(torch.cat([bg_point, sparse_po], dim=1))
         end_points = self.coarse_point_matching(sparse_pm, sparse_fm, geo_embedding_m, sparse_po, sparse_fo, geo_embedding_o,
                                                 radius, end_points, rand=rand)
         end_points = self.fine_point_matching(dense_pm, dense_fm, geo_embedding_m, fps_idx_m, dense_po, dense_fo,

@@ -119,6 +119,8 @@ class ImageEncoderViT(nn.Module):
                     n1w=_f32(blk.norm1.weight), n1b=_f32(blk.norm1.bias), eps1=blk.norm1.eps,
                     qkv=_W(blk.attn.qkv.weight), qkv_b=_f32(blk.attn.qkv.bias), proj=_W(blk.attn.proj.weight),
                     proj_b=_f32(blk.attn.proj.bias), rh=_f32(blk.attn.rel_pos_h), rw=_f32(blk.attn.rel_pos_w),
+                    rel_blob=(ops.pack_rel_pos(_f32(blk.attn.rel_pos_h), _f32(blk.attn.rel_pos_w))
+                              if blk.attn.rel_pos_h.shape[0] <= 31 and blk.attn.rel_pos_h.is_cuda else None),
                     n2w=_f32(blk.norm2.weight), n2b=_f32(blk.norm2.bias), eps2=blk.norm2.eps,
                     l1=_W(blk.mlp.lin1.weight), l1b=_f32(blk.mlp.lin1.bias), l2=_W(blk.mlp.lin2.weight), l2b=_f32(blk.mlp.lin2.bias)))
             oc = self.neck[0].out_channels
@@ -220,8 +222,16 @@ def _block_bf16(self, blk, bw, tok, B, L, C, G, maps):
         nW, Hs = B * maps["nwin"] * maps["nwin"], blk.window_size
     else:
         xw, nW, Hs = xn, B, G
-    qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"])                                      # fp32: the attention kernel's input
-    att = ops.attn_relpos(qkv, nW, Hs, Hs, self.num_heads, bw["rh"], bw["rw"], blk.attn.scale, out_dtype=torch.bfloat16)
+    if Hs * Hs <= 256:
+        # windowed blocks: tensor-core attention (QK^T and PV on tcgen05, decomposed rel-pos bias in the softmax warps)
+        qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"], out_dtype=torch.bfloat16)
+        vt = ops.transpose_tokens(qkv, 2 * C, C, nW, Hs * Hs)
+        att = ops.attn_tc(qkv, 0, qkv, C, vt, nW, self.num_heads, Hs * Hs, Hs * Hs, C // self.num_heads, blk.attn.scale,
+                          rel=(bw["rel_blob"], Hs, Hs), out_dtype=torch.bfloat16)
+    else:
+        # global blocks (4096 keys): flash-style CUDA-core kernel with online softmax
+        qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"])
+        att = ops.attn_relpos(qkv, nW, Hs, Hs, self.num_heads, bw["rh"], bw["rw"], blk.attn.scale, out_dtype=torch.bfloat16)
     if blk.window_size > 0:
         att = ops.gather_rows_bf16(att.view(B, -1, C), maps["unpart"]).view(-1, C)
     tok = ops.gemm_tma(att, bw["proj"].bf16, bw["proj_b"], residual=tok)

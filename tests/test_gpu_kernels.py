@@ -464,3 +464,66 @@ def test_gemm_tma(ops, M, N, K, odt):
         torch.testing.assert_close(got.double(), ref, atol=1e-4, rtol=1e-5)     # fp32 accumulation order over K <= 5120
     else:
         torch.testing.assert_close(got.double(), ref, atol=3e-2, rtol=1e-2)
+
+
+def _dense_attention(q, k, v, H, scale, bias=None):
+    B, Sq, C = q.shape
+    Sk = k.shape[1]
+    d = C // H
+    qh, kh, vh = (t.view(B, -1, H, d).permute(0, 2, 1, 3) for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    if bias is not None:
+        s = s + bias
+    att = torch.softmax(s * scale, dim=-1)
+    return (att @ vh).permute(0, 2, 1, 3).reshape(B * Sq, C)
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H,D,with_bias", [(3, 197, 197, 4, 64, True), (2, 197, 150, 4, 64, False), (5, 196, 196, 2, 80, False),
+                                                    (1, 33, 256, 1, 64, True)])
+def test_attn_tc_dense(ops, B, Sq, Sk, H, D, with_bias):
+    """tcgen05 attention against fp64 softmax attention on the bf16-rounded operands"""
+    g = G(Sq + Sk)
+    q = torch.randn(B, Sq, H * D, generator=g)
+    k = torch.randn(B, Sk, H * D, generator=g)
+    v = torch.randn(B, Sk, H * D, generator=g)
+    bias = torch.randn(B, H, Sq, Sk, generator=g) if with_bias else None
+    bv = torch.randn(H * D, generator=g)
+    qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+    ref = _dense_attention(qb.double(), kb.double(), vb.double(), H, D ** -0.5, bias.double() if with_bias else None) + bv.double()
+    N1 = (Sk + 15) // 16 * 16
+    vt = torch.zeros(B * H * D, N1, dtype=torch.bfloat16)
+    vt[:, :Sk] = vb.view(B, Sk, H, D).permute(0, 2, 3, 1).reshape(B * H * D, Sk)
+    qk = torch.cat([qb.view(B * Sq, -1), torch.zeros(B * Sq, 8, dtype=torch.bfloat16)], dim=1).contiguous()   # odd leading dim
+    got = ops.attn_tc(qk.cuda(), 0, kb.view(B * Sk, -1).contiguous().cuda(), 0, vt.cuda(), B, H, Sq, Sk, D, D ** -0.5,
+                      bias=bias.cuda() if with_bias else None, bv=bv.cuda()).cpu()
+    # P is rounded to bf16 before the PV product: ~2^-9 relative on O(1) outputs
+    torch.testing.assert_close(got.double(), ref, atol=2e-2, rtol=2e-2)
+    assert (got.double() - ref).abs().mean().item() < 3e-3
+
+
+def test_attn_tc_sam_window(ops):
+    """decomposed rel-pos bias mode against the reference formula (image_encoder.py:325-361)"""
+    from oracle import sam_oracle as so
+    nW, S, H, D = 4, 14, 2, 80
+    g = G(77)
+    qkv = torch.randn(nW * S * S, 3 * H * D, generator=g)
+    rel_h = torch.randn(2 * S - 1, D, generator=g) * 0.1
+    rel_w = torch.randn(2 * S - 1, D, generator=g) * 0.1
+    qkv_b = qkv.bfloat16()
+    x = qkv_b.float().view(nW, S * S, 3, H, D).permute(2, 0, 3, 1, 4).reshape(3, nW * H, S * S, D)
+    q, k, v = x.unbind(0)
+    attn = (q * D ** -0.5) @ k.transpose(-2, -1)
+    Rh, Rw = so.rel_pos_table(S, rel_h), so.rel_pos_table(S, rel_w)
+    rq = q.reshape(nW * H, S, S, D)
+    attn = (attn.view(-1, S, S, S, S) + torch.einsum("bhwc,hkc->bhwk", rq, Rh)[:, :, :, :, None] +
+            torch.einsum("bhwc,wkc->bhwk", rq, Rw)[:, :, :, None, :]).view(-1, S * S, S * S).softmax(dim=-1)
+    ref = (attn @ v).view(nW, H, S * S, D).permute(0, 2, 1, 3).reshape(nW * S * S, H * D)
+    L = S * S
+    N1 = (L + 15) // 16 * 16
+    vt = torch.zeros(nW * H * D, N1, dtype=torch.bfloat16)
+    vt[:, :L] = qkv_b[:, 2 * H * D:].view(nW, L, H, D).permute(0, 2, 3, 1).reshape(nW * H * D, L)
+    qk = qkv_b[:, :2 * H * D].contiguous()
+    got = ops.attn_tc(qk.cuda(), 0, qk.cuda(), H * D, vt.cuda(), nW, H, L, L, D, D ** -0.5,
+                      rel=(ops.pack_rel_pos(rel_h.cuda(), rel_w.cuda()), S, S)).cpu()
+    torch.testing.assert_close(got, ref, atol=2e-2, rtol=2e-2)
+    assert (got - ref).abs().mean().item() < 3e-3
