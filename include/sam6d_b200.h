@@ -34,6 +34,9 @@ int sam6d_gather_points(const float* points, const int* idx, int b, int c, int n
  * (sample_pts_feats PEM/utils/model_utils.py:53-66; SparseToDenseTransformer._sample_feats PEM/model/transformer.py:651-658) */
 int sam6d_gather_rows(const float* src, const int* idx, int b, int n, int m, int c, long long src_bstride, float* out,
                       void* stream);
+/* same gather from a bf16 token matrix, widened to fp32 (c % 8 == 0) */
+int sam6d_gather_rows_bf16_f32(const void* src, const int* idx, int b, int n, int m, int c, long long src_bstride, float* out,
+                               void* stream);
 
 /* _ext.ball_query (PN2/_ext_src/src/ball_query.cpp:11-35, ball_query_gpu.cu:14-49): new_xyz (b,m,3), xyz (b,n,3)
  * -> idx (b,m,nsample): first nsample hits with d2 < r*r in ascending index order, padded with the first hit,
@@ -62,7 +65,7 @@ int sam6d_gemm_bf16(const void* A, int a_dtype, const void* W, int w_dtype, cons
 
 /* Persistent TMA-fed version for plain (non-batched) bf16 operands: cp.async.bulk.tensor boxes with SWIZZLE_128B feed a
  * 4-stage ring, two TMEM accumulators overlap epilogue and MMA.  A (M,K) bf16, W (N,K) bf16, C fp32 (0) / bf16 (1). */
-int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const float* R, void* C, int c_dtype, int M, int N, int K,
+int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                    long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream);
 
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
@@ -75,6 +78,10 @@ int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long l
 int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
                          long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
                          float eps, void* stream);
+/* bf16 rows in and out, statistics in fp32 */
+int sam6d_layernorm_bf16io(const void* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                           long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                           float eps, void* stream);
 /* F.normalize(x, p=2, dim=-1) (PEM/utils/model_utils.py:124-126; ISM/model/loss.py:32-33) */
 int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                       long long y_bstride, long long y_ld, long long rows, int C, void* stream);
@@ -124,6 +131,14 @@ int sam6d_linattn_kv(const float* Kf, long long k_ld, long long k_bs, const floa
                      int H, int J, float* KV, float* KS, void* stream);
 int sam6d_linattn_apply(const float* Qf, long long q_rpb, long long q_bs, long long q_ld, const float* KV, const float* KS,
                         int B, int H, float* X, long long x_bs, long long x_ld, void* stream);
+/* The same branch for the dense tokens on tcgen05 (bf16 tokens).  linattn_kv_pack: focused keys Kf and values V ((B,J,256)
+ * fp32 views) -> blob = per cloud the bf16 UMMA image of KV_h^T (4 x [64][64], 128-byte swizzle; B x 32 KB) and KS (B,4,64).
+ * linattn_tc: Q = B clouds x rpb rows x 256 bf16 (row stride q_ld, cloud stride q_bs), the raw query projection; applies the focusing feature map (transformer.py:541-550),
+ * X[b,i,h] = (q'_h KV_h) / (q'_h . KS_h + 1e-6), bf16. */
+int sam6d_linattn_kv_pack(const float* Kf, long long k_ld, long long k_bs, const float* V, long long v_ld, long long v_bs, int B,
+                          int J, void* blob, float* KS, void* stream);
+int sam6d_linattn_tc(const void* Q, long long q_ld, long long q_bs, const void* blob, const float* KS,
+                     const float* softplus_scale, int B, int rpb, void* X, long long x_ld, long long x_bs, void* stream);
 
 /* ---- coarse pose (compute_coarse_Rt, PEM/utils/model_utils.py:187-246) -------------------------------------------- */
 int sam6d_coarse_assign(const float* A, int B, int S, float* W, float* w1, void* stream);

@@ -24,13 +24,44 @@ __device__ __forceinline__ float act_fn(float x) {
 
 // v[32]: this thread's row of the chunk.  stage: this warp's WARP_STAGE_FLOATS floats of shared memory.
 // row0: global row of lane 0; col0: first global column of the chunk.  Partial chunks (col0 + 32 > N) take a scalar path.
-template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES>
+template <typename T>
+struct ident { using type = T; };   // keeps RT out of template argument deduction (callers pass nullptr)
+__device__ __forceinline__ float ld_res(const float* p) { return *p; }
+__device__ __forceinline__ float ld_res(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+// RT: residual element type (fp32, or bf16 for the all-bf16 activation flow).
+template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, typename RT = float>
 __device__ __forceinline__ void process_chunk(float v[32], float* stage, int lane, int row0, int M, int col0, int N, float alpha,
-                                              const float* __restrict__ bias, const float* __restrict__ R, long long ldr,
+                                              const float* __restrict__ bias, const typename ident<RT>::type* __restrict__ R, long long ldr,
                                               OT* __restrict__ C, long long ldc) {
   const bool full = (col0 + 32 <= N);
-  const bool vec_ok = full && ((ldc & (sizeof(OT) == 4 ? 3 : 7)) == 0) && (!HAS_RES || (ldr & 3) == 0);
+  const bool vec_ok = full && ((ldc & (sizeof(OT) == 4 ? 3 : 7)) == 0) && (!HAS_RES || (ldr & (sizeof(RT) == 4 ? 3 : 7)) == 0);
   if (vec_ok) {
+    if constexpr (HAS_RES && sizeof(RT) == 2) {
+      // bf16 residual tile: a row of the chunk is 64 bytes; lane l reads 16 B of row (i*8 + l/4), piece l%4
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2), q = lane & 3;
+        uint4 t = make_uint4(0u, 0u, 0u, 0u);
+        if (row0 + r < M) t = *reinterpret_cast<const uint4*>(R + (size_t)(row0 + r) * ldr + col0 + q * 8);
+        *reinterpret_cast<uint4*>(stage + r * TILE_LD + q * 4) = t;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 t = *reinterpret_cast<const uint4*>(stage + lane * TILE_LD + q * 4);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+        float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+        if constexpr (HAS_BIAS) { b0 = __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * q); b1 = __ldg(reinterpret_cast<const float4*>(bias + col0) + 2 * q + 1); }
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[q * 8 + 2 * e] = act_fn<ACT>(fmaf(v[q * 8 + 2 * e], alpha, bb[2 * e])) + __uint_as_float(w[e] << 16);
+          v[q * 8 + 2 * e + 1] = act_fn<ACT>(fmaf(v[q * 8 + 2 * e + 1], alpha, bb[2 * e + 1])) + __uint_as_float(w[e] & 0xffff0000u);
+        }
+      }
+      __syncwarp();
+    } else {
     if constexpr (HAS_RES) {
       // coalesced residual tile -> smem: lane l reads 16 B of row (i*4 + l/8), float4 column l%8
 #pragma unroll
@@ -53,6 +84,7 @@ __device__ __forceinline__ void process_chunk(float v[32], float* stage, int lan
       v[q * 4 + 3] = act_fn<ACT>(fmaf(v[q * 4 + 3], alpha, b4.w)) + r4.w;
     }
     if constexpr (HAS_RES) __syncwarp();
+    }
     if constexpr (sizeof(OT) == 4) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
@@ -91,7 +123,7 @@ __device__ __forceinline__ void process_chunk(float v[32], float* stage, int lan
           float x = v[j] * alpha;
           if constexpr (HAS_BIAS) x += bias[col];
           x = act_fn<ACT>(x);
-          if constexpr (HAS_RES) x += R[(size_t)row * ldr + col];
+          if constexpr (HAS_RES) x += ld_res(R + (size_t)row * ldr + col);
           if constexpr (sizeof(OT) == 4) reinterpret_cast<float*>(C)[(size_t)row * ldc + col] = x;
           else reinterpret_cast<__nv_bfloat16*>(C)[(size_t)row * ldc + col] = __float2bfloat16(x);
         }

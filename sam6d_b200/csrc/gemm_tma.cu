@@ -25,7 +25,7 @@ constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 
 struct Args {
-  const float* bias; const float* R; void* C;
+  const float* bias; const void* R; void* C;   // R has the element type of C
   int M, N, K;
   long long ldc, ldr;
   float alpha;
@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_c
         if (col0 >= g.N) break;
         float v[32];
         tc::tmem_ld32(t_addr + c * 32, v);
-        epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias, g.R, g.ldr,
-                                                       reinterpret_cast<OT*>(g.C), g.ldc);
+        epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
+                                                           reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C), g.ldc);
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&tmem_empty_bar[acc]);
@@ -158,9 +158,10 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long K, lon
 
 }  // namespace
 
-// A (M,K) bf16 lda, W (N,K) bf16 ldw, C (M,N) fp32 (c_dtype 0) or bf16 (1), bias (N) fp32 or NULL, R (M,N) fp32 or NULL.
+// A (M,K) bf16 lda, W (N,K) bf16 ldw, C (M,N) fp32 (c_dtype 0) or bf16 (1), bias (N) fp32 or NULL, R (M,N) or NULL: the
+// residual has the element type of C (fp32 stream with fp32 output, bf16 stream with bf16 output).
 // K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, 16-byte aligned bases.  act: 0 none, 1 ReLU, 2 GELU(erf).
-S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const float* R, void* C, int c_dtype, int M, int N, int K,
+S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                           long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream) {
   S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && act >= 0 && act <= 2);
   S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);

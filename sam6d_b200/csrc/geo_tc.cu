@@ -5,9 +5,12 @@
 // The reference materialises sin_emb for 4 scalars per pair (3.8 GB at B=32) and runs two 256x256 Linears over them
 // (651 GFLOP per cloud).  Here one persistent, warp-specialised kernel per projection keeps the 256x256 bf16 weight
 // resident in shared memory (128 KB, UMMA K-major SWIZZLE_128B slabs) and never materialises the embeddings:
-//   producers (warps 4-7) : one thread per token row: x*omega_f -> __sincosf -> bf16 (sin,cos) pairs written straight into
-//                           the swizzled A slab of a 4-deep k-block ring (16 KB per 128x64 slab)
-//   MMA issuer (warp 8)   : 4 x tcgen05.mma M128 N256 K16 per k-block into one of two 256-column TMEM accumulators
+//   producers (warps 4-11): a thread owns one 16-byte chunk column (4 frequencies, kept in registers) of 3-4 token rows:
+//                           x*omega_f -> __sincosf -> bf16 (sin,cos) pairs written straight into the swizzled A slab of a
+//                           4-deep k-block ring (16 KB per 128x64 slab).  Two producer warps per scheduler: one warp alone
+//                           issued an instruction every ~7 cycles (dependent-latency bound), a third of the MUFU rate.
+//                           The angle pass skips the unused 4th row of every pair (the slab rows stay zero).
+//   MMA issuer (warp 12)  : 4 x tcgen05.mma M128 N256 K16 per k-block into one of two 256-column TMEM accumulators
 //   epilogue (warps 0-3)  : tcgen05.ld; pass ANGLE: rows are (pair, k) quadruples (k = 3 unused), max over k by a 24-shuffle
 //                           transpose-reduce, each lane adds its 8-column share into E ; pass DIST (runs first): rows are
 //                           pairs, E = acc + bias with full-line stores (epilogue.cuh).
@@ -20,7 +23,9 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, KBLOCKS = 4, ASTAGES = 4;
 constexpr int A_SLAB = BM * BK * 2;          // 16 KB
 constexpr int W_SLAB = BN * BK * 2;          // 32 KB
-constexpr int NUM_THREADS = 288;
+constexpr int NUM_PRODUCERS = 256;                  // warps 4-11
+constexpr int MMA_WARP = 12;
+constexpr int NUM_THREADS = 128 + NUM_PRODUCERS + 32;
 constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
 constexpr int SMEM_BYTES = KBLOCKS * W_SLAB + ASTAGES * A_SLAB + EPI_BYTES + 1024;
 
@@ -70,7 +75,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
   const long long ntiles = (npairs + PAIRS_PER_TILE - 1) / PAIRS_PER_TILE;
 
   if (tid == 0) {
-    for (int s = 0; s < ASTAGES; ++s) { tc::mbar_init(&full_bar[s], 128); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ASTAGES; ++s) { tc::mbar_init(&full_bar[s], NUM_PRODUCERS / 32); tc::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 128); }
     tc::mbar_fence_init();
   }
@@ -81,46 +86,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
     const uint4 v = *reinterpret_cast<const uint4*>(Wb + (size_t)n * 256 + c);
     *reinterpret_cast<uint4*>(w_smem + (c >> 6) * W_SLAB + tc::sw128_offset(n, c & 63)) = v;
   }
+  for (int u = tid; u < ASTAGES * A_SLAB / 16; u += NUM_THREADS)       // rows the angle pass never writes must be finite
+    reinterpret_cast<uint4*>(a_smem)[u] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async_smem();
-  if (warp == 8) tc::tmem_alloc(&tmem_slot, 512);
+  if (warp == MMA_WARP) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
-    // ------------------------------------------------------------------ producers: thread <-> token row
-    const int r = tid - 128;
+  if (warp >= 4 && warp < MMA_WARP) {
+    // ------------------------------------------------------------------ producers: thread <-> (chunk column, NT token rows)
+    const int pt = tid - 128;
+    const int c = pt & 7;                               // 16-byte chunk of the 128-byte slab row: frequencies 32 kb + 4c .. + 3
+    constexpr int NT = (MODE == 0) ? 3 : 4;             // tasks per thread per k-block
+    int row[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const int u = (j * NUM_PRODUCERS + pt) >> 3;      // MODE 0: useful row index 0..95 -> row (u/3)*4 + u%3
+      row[j] = (MODE == 0) ? (u / 3) * 4 + (u % 3) : u;
+    }
+    float om[KBLOCKS][4];
+#pragma unroll
+    for (int kb = 0; kb < KBLOCKS; ++kb)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) om[kb][q] = omega[kb * 32 + c * 4 + q];
+    const uint32_t a_base = tc::smem_u32(a_smem);
     long long g = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      float x;
-      if (MODE == 0) {
-        const long long pair = tile * 32 + (r >> 2);
-        x = (pair < npairs && (r & 3) < 3) ? T[pair * 4 + (r & 3)] : 0.f;
-      } else {
-        const long long pair = tile * 128 + r;
-        x = (pair < npairs) ? T[pair * 4 + 3] : 0.f;
+      float x[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        if (MODE == 0) {
+          const long long pair = tile * 32 + (row[j] >> 2);
+          x[j] = (pair < npairs) ? T[pair * 4 + (row[j] & 3)] : 0.f;
+        } else {
+          const long long pair = tile * 128 + row[j];
+          x[j] = (pair < npairs) ? T[pair * 4 + 3] : 0.f;
+        }
       }
+#pragma unroll
       for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
         const int s = (int)(g % ASTAGES);
         tc::mbar_wait(&empty_bar[s], (uint32_t)(((g / ASTAGES) & 1) ^ 1));
-        uint8_t* row_ptr = a_smem + s * A_SLAB + r * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {       // 16-byte chunk c = frequencies 32 kb + 4c .. + 3, (sin, cos) interleaved
+        for (int j = 0; j < NT; ++j) {
           uint32_t w[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float sv, cv;
-            __sincosf(x * omega[kb * 32 + c * 4 + q], &sv, &cv);
+            __sincosf(x[j] * om[kb][q], &sv, &cv);
             w[q] = tc::pack_bf16(sv, cv);
           }
-          *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          const uint32_t addr = a_base + s * A_SLAB + row[j] * 128 + ((c ^ (row[j] & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&full_bar[s]);
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&full_bar[s]);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = tc::umma_idesc_bf16(BM, BN);
@@ -219,7 +245,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
 }
 
 template <int MODE, typename ET>

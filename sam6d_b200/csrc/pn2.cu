@@ -208,6 +208,37 @@ __global__ void gather_rows_scalar_kernel(const float* __restrict__ src, const i
   }
 }
 
+// bf16 source rows widened to fp32 (the sparse tokens picked out of the bf16 dense sequence); c % 8 == 0
+__global__ void gather_rows_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ idx, int m, int c,
+                                            long long src_bstride, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int c8 = c >> 3;
+  const long long total = (long long)m * c8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i / c8), q = (int)(i - (long long)j * c8);
+    int a = idx[(size_t)b * m + j];
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (a >= 0) v = reinterpret_cast<const uint4*>(src + (size_t)b * src_bstride + (size_t)a * c)[q];
+    float4* o = reinterpret_cast<float4*>(out + ((size_t)b * m + j) * c + q * 8);
+    o[0] = make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                       __uint_as_float(v.y & 0xffff0000u));
+    o[1] = make_float4(__uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16),
+                       __uint_as_float(v.w & 0xffff0000u));
+  }
+}
+S6_API int sam6d_gather_rows_bf16_f32(const void* src, const int* idx, int b, int n, int m, int c, long long src_bstride,
+                                      float* out, void* stream) {
+  S6_REQUIRE(src && idx && out && b >= 0 && n > 0 && m >= 0 && c > 0 && (c % 8) == 0 && (src_bstride % 8) == 0);
+  S6_REQUIRE((((uintptr_t)src | (uintptr_t)out) % 16) == 0);
+  if (b == 0 || m == 0) return 0;
+  long long total = (long long)m * (c / 8);
+  dim3 grid((unsigned)min((long long)1024, (total + 255) / 256), b);
+  gather_rows_bf16_f32_kernel<<<grid, 256, 0, s6_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), idx, m, c,
+                                                                   src_bstride, out);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
 // src (b,n,c) f32 with batch stride src_bstride (elements), idx (b,m) i32 -> out (b,m,c)
 S6_API int sam6d_gather_rows(const float* src, const int* idx, int b, int n, int m, int c, long long src_bstride,
                              float* out, void* stream) {

@@ -21,21 +21,24 @@ constexpr int MAXV_LIMIT = 64;  // per-lane values: C / 32 <= 64 (C <= 2048); ke
 __device__ __forceinline__ void st_out(float* p, float v) { *p = v; }
 __device__ __forceinline__ void st_out(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 
-template <int MAXV, typename OT>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
+__device__ __forceinline__ float ld_in(const float* p) { return *p; }
+__device__ __forceinline__ float ld_in(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+
+template <int MAXV, typename OT, typename IT = float>
+__global__ void __launch_bounds__(256) layernorm_kernel(const IT* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
-  const float* xp = x + xv.off(r);
+  const IT* xp = x + xv.off(r);
   OT* yp = y + yv.off(r);
   const int nv = C >> 5;
   float v[MAXV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
-    if (i < nv) { v[i] = xp[lane + 32 * i]; s += v[i]; }
+    if (i < nv) { v[i] = ld_in(xp + lane + 32 * i); s += v[i]; }
   const float mean = warp_sum(s) / (float)C;
   float q = 0.f;
 #pragma unroll
@@ -168,6 +171,20 @@ S6_API int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bst
   if (rows == 0) return 0;
   ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld},
                reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps));
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+#undef ROW_EXTRA
+#define ROW_EXTRA , __nv_bfloat16, __nv_bfloat16
+// bf16 rows in, bf16 rows out (statistics in fp32): the all-bf16 activation flow of the dense PEM layers
+S6_API int sam6d_layernorm_bf16io(const void* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                                  long long y_bstride, long long y_ld, const float* gamma, const float* beta, long long rows, int C,
+                                  float eps, void* stream) {
+  S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+               RowView{x_rpb, x_bstride, x_ld}, reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta,
+               rows, C, eps));
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -168,7 +168,7 @@ def gemm_tma(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Opti
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=A.device)
     if residual is not None:
-        _check(residual, torch.float32, "residual", 2)
+        _check(residual, out.dtype, "residual", 2)          # the residual stream has the element type of the output
     _lib.call("sam6d_gemm_tma", _p(A), _p(W), _p(bias), _p(residual), _p(out), _DT[out.dtype], M, N, K, _ll(K), _ll(K), _ll(N), _ll(N),
               _f(alpha), int(act), _s())
     return out
@@ -198,6 +198,29 @@ def layernorm_bf16(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) ->
     out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
     _lib.call("sam6d_layernorm_bf16", _p(x), _ll(rows), _ll(0), _ll(C), _p(out), _ll(rows), _ll(0), _ll(C), _p(gamma), _p(beta),
               _ll(rows), int(C), _f(eps), _s())
+    return out
+
+
+def layernorm_bf16io(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, out: Optional[Tensor] = None) -> Tensor:
+    """LayerNorm over the last dim of contiguous bf16 rows, bf16 result (statistics in fp32)"""
+    _check(x, torch.bfloat16, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.call("sam6d_layernorm_bf16io", _p(x), _ll(max(rows, 1)), _ll(0), _ll(C), _p(out), _ll(max(rows, 1)), _ll(0), _ll(C),
+              _p(gamma), _p(beta), _ll(rows), int(C), _f(eps), _s())
+    return out
+
+
+def gather_rows_bf16_f32(src: Tensor, idx: Tensor) -> Tensor:
+    """out[b,j,:] = float(src[b, idx[b,j], :]) for a bf16 (b,n,c) token matrix; negative index -> zero row"""
+    _check(src, torch.bfloat16, "src", 3)
+    _check(idx, torch.int32, "idx", 2)
+    b, n, c = src.shape
+    m = idx.shape[1]
+    out = torch.empty(b, m, c, dtype=torch.float32, device=src.device)
+    _lib.call("sam6d_gather_rows_bf16_f32", _p(src), _p(idx), b, n, m, c, _ll(n * c), _p(out), _s())
     return out
 
 
@@ -360,6 +383,21 @@ def linattn_apply_raw(q_ptr, q_rpb, q_bs, q_ld, KV: Tensor, KS: Tensor, B, H, x_
 
 
 # ---------------------------------------------------------------------------------------------- coarse pose
+def linattn_kv_pack_raw(k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, B, J, device):
+    """focused keys / values ((B,J,256) fp32 views) -> (blob: B x 32 KB bf16 UMMA image of KV_h^T, KS (B,4,64) fp32)"""
+    blob = torch.empty(B, 4 * 64 * 64, dtype=torch.bfloat16, device=device)
+    KS = torch.empty(B, 4, 64, dtype=torch.float32, device=device)
+    _lib.call("sam6d_linattn_kv_pack", ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs), ctypes.c_void_p(v_ptr), _ll(v_ld), _ll(v_bs),
+              int(B), int(J), _p(blob), _p(KS), _s())
+    return blob, KS
+
+
+def linattn_tc_raw(q_ptr, q_ld, q_bs, blob: Tensor, KS: Tensor, sp_scale: Tensor, B, rpb, x_ptr, x_ld, x_bs):
+    """dense tokens (bf16): focusing feature map + per-head (q' KV) / (q' . ksum) on tcgen05"""
+    _lib.call("sam6d_linattn_tc", ctypes.c_void_p(q_ptr), _ll(q_ld), _ll(q_bs), _p(blob), _p(KS), _p(sp_scale), int(B), int(rpb),
+              ctypes.c_void_p(x_ptr), _ll(x_ld), _ll(x_bs), _s())
+
+
 def coarse_assign(A: Tensor) -> Tuple[Tensor, Tensor]:
     _check(A, torch.float32, "atten", 3)
     B, S, _ = A.shape

@@ -567,7 +567,36 @@ class SparseToDenseTransformer(nn.Module):
 
     def _sample_feats(self, dense_feats, idx_ext):
         # quirk Q1 (transformer.py:651-658): the gather runs on the bg-prefixed sequence with the raw FPS index
+        if dense_feats.dtype == torch.bfloat16:
+            return ops.gather_rows_bf16_f32(dense_feats, idx_ext)
         return ops.gather_rows(dense_feats, idx_ext)
+
+    def _dense_layer_bf16(self, dense, sparse, w):
+        """_dense_layer for the bf16 token stream: dense (B,N+1,C) bf16, sparse (B,J+1,C) fp32.  Every GEMM is the persistent
+        TMA kernel over all B*(N+1) rows (the bg row rides along and is overwritten at the end), the feature map and the
+        per-head (q' KV) / (q' . ksum) run in one tcgen05 kernel, LayerNorms read and write bf16."""
+        B, N1, C = dense.shape
+        N, J = N1 - 1, sparse.shape[1] - 1
+        dev = dense.device
+        bf = torch.bfloat16
+        x2d = dense.view(B * N1, C)
+        q = ops.gemm_tma(x2d, w["wq"].bf16, w["bq"], out_dtype=bf)
+        kv = torch.empty(B * J, 2 * C, dtype=torch.float32, device=dev)
+        _gemm_raw("bf16", sparse.data_ptr() + C * 4, w["wkv"], w["bkv"], 0, kv.data_ptr(), J, 2 * C, C, C, 2 * C, 0, batch=B,
+                  sA=(J + 1) * C, sC=J * 2 * C)
+        ops.focus_rows_raw(kv.data_ptr(), (B * J, 0, 2 * C), kv.data_ptr(), (B * J, 0, 2 * C), w["sp_scale"], B * J, C)
+        blob, KS = ops.linattn_kv_pack_raw(kv.data_ptr(), 2 * C, J * 2 * C, kv.data_ptr() + C * 4, 2 * C, J * 2 * C, B, J, dev)
+        x_att = torch.empty(B * N1, C, dtype=bf, device=dev)
+        ops.linattn_tc_raw(q.data_ptr() + C * 2, C, N1 * C, blob, KS, w["sp_scale"], B, N, x_att.data_ptr() + C * 2, C, N1 * C)
+        x_att.view(B, N1, C)[:, 0, :] = 0                                   # bg rows: defined input for the GEMMs below
+        t = w["tail"]
+        y = ops.gemm_tma(x_att, t["wo"].bf16, t["bo"], residual=x2d, out_dtype=bf)
+        y = ops.layernorm_bf16io(y, t["g1"], t["b1"])
+        h = ops.gemm_tma(y, t["we"].bf16, t["be"], act=1, out_dtype=bf)
+        z = ops.gemm_tma(h, t["ws"].bf16, t["bs"], residual=y, out_dtype=bf)
+        out = ops.layernorm_bf16io(z, t["g2"], t["b2"]).view(B, N1, C)
+        out[:, 0, :] = sparse[:, 0, :].to(bf)                               # replaced bg token (transformer.py:660-668)
+        return out
 
     def _dense_layer(self, dense, sparse, w):
         """LinearTransformerLayer on dense[:,1:,:] with memory sparse[:,1:,:]; returns the new (B,N+1,C) sequence."""
@@ -612,13 +641,15 @@ class SparseToDenseTransformer(nn.Module):
             B = dense_feats0.shape[0]
             feats = self._sample_feats(dense, torch.cat([ext0, ext1], dim=0))
             feats0, feats1 = self.sparse_layer(feats[:B], embeddings0, feats[B:], embeddings1, masks0, masks1)
-            out = self._dense_layer(dense, torch.cat([feats0, feats1], dim=0), w)
+            layer = self._dense_layer_bf16 if dense.dtype == torch.bfloat16 else self._dense_layer
+            out = layer(dense, torch.cat([feats0, feats1], dim=0), w)
             return out[:B], out[B:]
         feats0 = self._sample_feats(dense_feats0.contiguous(), ext0)
         feats1 = self._sample_feats(dense_feats1.contiguous(), ext1)
         feats0, feats1 = self.sparse_layer(feats0, embeddings0, feats1, embeddings1, masks0, masks1)
-        dense_feats0 = self._dense_layer(dense_feats0.contiguous(), feats0, w)
-        dense_feats1 = self._dense_layer(dense_feats1.contiguous(), feats1, w)
+        layer = self._dense_layer_bf16 if dense_feats0.dtype == torch.bfloat16 else self._dense_layer
+        dense_feats0 = layer(dense_feats0.contiguous(), feats0, w)
+        dense_feats1 = layer(dense_feats1.contiguous(), feats1, w)
         return dense_feats0, dense_feats1
 
 
@@ -656,6 +687,13 @@ class FinePointMatching(nn.Module):
         w, pw = self._weights(), self.PE._weights()
         local = self.PE.local_features(pts)                                         # (B,N,256)
         tmp = _gemm(self.precision, f.reshape(B * N, C), w["w_in"], w["b_in"])
+        if self.precision == "bf16":
+            # the dense token stream of the fine stage is bf16 from here on (fp32 accumulation inside every kernel)
+            out = torch.empty(B, N + 1, H, dtype=torch.bfloat16, device=f.device)
+            out[:, 0, :] = self.bg_token.detach().reshape(1, -1).to(torch.bfloat16)
+            ops.gemm_tc_raw(local.data_ptr(), 0, pw["w3"].bf16.data_ptr(), 1, pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 2, 1,
+                            N, H, 256, 256, 256, H, H, batch=B, sA=N * 256, sW=0, sC=(N + 1) * H, sR=N * H)
+            return out
         out = torch.empty(B, N + 1, H, dtype=torch.float32, device=f.device)
         out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
         _gemm_raw(self.precision, local.data_ptr(), pw["w3"], pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 4, N, H, 256, 256, H, H,

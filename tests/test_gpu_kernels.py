@@ -220,6 +220,56 @@ def test_linear_attention(ops):
     torch.testing.assert_close(x.cpu(), ref, atol=1e-4, rtol=1e-3)
 
 
+@pytest.mark.parametrize("B,N,J", [(2, 300, 50), (3, 2048, 196), (1, 129, 7)])
+def test_linear_attention_tensor_core(ops, B, N, J):
+    """bf16 dense tokens: feature map + per-head (q' KV)/(q' . ksum) in one tcgen05 kernel, against fp64 math on the same
+    bf16-rounded query projection.  The token rows sit behind a bg row (the (B,N+1,C) layout of the fine stage)."""
+    C = 256
+    sp = (torch.rand(C, generator=G(5)) + 0.5)
+    q = torch.randn(B, N + 1, C, generator=G(1)).bfloat16()
+    k = torch.randn(B, J, C, generator=G(2))
+    v = torch.randn(B, J, C, generator=G(3))
+
+    def focus(x):
+        x = (torch.relu(x) + 1e-6) / sp.double()
+        n = x.norm(dim=-1, keepdim=True)
+        x = x ** 3
+        return x / x.norm(dim=-1, keepdim=True) * n
+
+    qf, kf = focus(q[:, 1:].double()), focus(k.double())
+    qh = qf.view(B, N, 4, 64).permute(0, 2, 1, 3)
+    kh = kf.view(B, J, 4, 64).permute(0, 2, 1, 3)
+    vh = v.double().view(B, J, 4, 64).permute(0, 2, 1, 3)
+    z = 1.0 / (qh @ kh.sum(dim=2).unsqueeze(-1) + 1e-6)
+    ref = ((qh @ (kh.transpose(-1, -2) @ vh)) * z).permute(0, 2, 1, 3).reshape(B, N, C)
+
+    kd, vd, spd = k.cuda().contiguous(), v.cuda().contiguous(), sp.cuda()
+    ops.focus_rows_raw(kd.data_ptr(), (B * J, 0, C), kd.data_ptr(), (B * J, 0, C), spd, B * J, C)
+    blob, KS = ops.linattn_kv_pack_raw(kd.data_ptr(), C, J * C, vd.data_ptr(), C, J * C, B, J, kd.device)
+    torch.testing.assert_close(KS.cpu().double(), kh.sum(dim=2), atol=1e-4, rtol=1e-4)
+    qd = q.cuda()
+    x = torch.full((B, N + 1, C), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.linattn_tc_raw(qd.data_ptr() + C * 2, C, (N + 1) * C, blob, KS, spd, B, N, x.data_ptr() + C * 2, C, (N + 1) * C)
+    x = x.cpu()
+    assert (x[:, 0] == 7.0).all()                                     # rows outside the view are untouched
+    torch.testing.assert_close(x[:, 1:].double(), ref, atol=2e-2 * ref.abs().max().item(), rtol=3e-2)
+
+
+def test_bf16_row_ops(ops):
+    x = torch.randn(5, 77, 256, generator=G(1)).bfloat16()
+    g, b = torch.randn(256, generator=G(2)), torch.randn(256, generator=G(3))
+    ref = torch.nn.functional.layer_norm(x.float(), (256,), g, b)
+    got = ops.layernorm_bf16io(x.cuda(), g.cuda(), b.cuda()).cpu()
+    assert got.dtype == torch.bfloat16
+    torch.testing.assert_close(got.float(), ref, atol=3e-2, rtol=1e-2)
+    idx = torch.randint(0, 77, (5, 40), generator=G(4), dtype=torch.int32)
+    idx[0, 3] = -1
+    out = ops.gather_rows_bf16_f32(x.cuda(), idx.cuda()).cpu()
+    ref = torch.gather(x.float(), 1, idx.clamp(min=0).long().unsqueeze(-1).expand(-1, -1, 256))
+    ref[0, 3] = 0
+    assert torch.equal(out, ref)
+
+
 # ------------------------------------------------------------------------------------------------- coarse pose pieces
 def _score_matrix(B, S, seed, peak=6.0):
     """cosine/temp-like matrix in [-10,10] with a planted permutation so that labels are decisive"""
@@ -457,6 +507,7 @@ def test_gemm_tma(ops, M, N, K, odt):
     W = torch.randn(N, K, generator=G(2)) / math.sqrt(K)
     bias = torch.randn(N, generator=G(3))
     R = torch.randn(M, N, generator=G(4))
+    R = R.to(odt)                           # the residual stream has the element type of the output
     ref = torch.nn.functional.gelu(A.bfloat16().double() @ W.bfloat16().double().t() * 0.5 + bias.double()) + R.double()
     got = ops.gemm_tma(A.cuda().bfloat16(), W.cuda().bfloat16(), bias.cuda(), residual=R.cuda(), act=2, alpha=0.5, out_dtype=odt).cpu()
     assert got.dtype == odt

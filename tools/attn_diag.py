@@ -24,7 +24,8 @@ nW, L, H2, D2 = 800, 196, 16, 80
 qkv2 = torch.randn(nW * L, 3 * H2 * D2, device="cuda").bfloat16()
 vt2 = ops.transpose_tokens(qkv2, 2 * H2 * D2, H2 * D2, nW, L)
 rh = torch.randn(27, 80, device="cuda") * 0.1; rw = torch.randn(27, 80, device="cuda") * 0.1
+blob = ops.pack_rel_pos(rh, rw)
 print("sam win no bias %8.1f us" % timeit(lambda: ops.attn_tc(qkv2, 0, qkv2, H2 * D2, vt2, nW, H2, L, L, D2, 0.11, out_dtype=torch.bfloat16), n=3))
-print("sam win rel-pos %8.1f us" % timeit(lambda: ops.attn_tc(qkv2, 0, qkv2, H2 * D2, vt2, nW, H2, L, L, D2, 0.11, rel=(ops.pack_rel_pos(rh, rw), 14, 14), out_dtype=torch.bfloat16), n=3))
+print("sam win rel-pos %8.1f us" % timeit(lambda: ops.attn_tc(qkv2, 0, qkv2, H2 * D2, vt2, nW, H2, L, L, D2, 0.11, rel=(blob, 14, 14), out_dtype=torch.bfloat16), n=3))
 qf = qkv2.float()
 print("sam win simt    %8.1f us" % timeit(lambda: ops.attn_relpos(qf, nW, 14, 14, H2, rh, rw, 0.11, out_dtype=torch.bfloat16), n=3))
