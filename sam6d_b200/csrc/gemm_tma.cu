@@ -6,7 +6,7 @@
 //                           columns are zero-filled by the TMA unit
 //   warp 1   MMA issuer   : 4 x tcgen05.mma M128 N256 K16 per stage into one of two 256-column TMEM accumulators,
 //                           tcgen05.commit releases the stage / publishes the accumulator
-//   warps 2-5 epilogue    : tcgen05.ld -> alpha, bias, activation, residual -> fp32 or bf16, transposed through shared memory
+//   warps 2..  epilogue   : tcgen05.ld -> alpha, bias, activation, residual -> fp32 or bf16, transposed through shared memory
 //                           into full-line global stores (epilogue.cuh); overlaps the next tile's loads and MMAs through
 //                           the second accumulator
 // No register staging and no LSU traffic for the operands: the CUDA-core staged kernel (gemm_tc.cu) tops out near 8 GB/s per
@@ -18,11 +18,18 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
+// Two shapes of the same kernel (227 KB of shared memory decide the split):
+//   deep K  (K >= 1024, the ViT-H Linears): 4-stage ring, 4 epilogue warps -- the MMAs of a tile outlast its epilogue
+//   short K (the 256/512-wide PEM Linears): a tile is 4-8 k-blocks, the epilogue sets the pace -> 8 epilogue warps (two per
+//           TMEM lane quadrant, 4 column chunks each), 3-stage ring
+template <int STAGES, int EW>
+struct Cfg {
+  static constexpr int kThreads = 64 + EW * 32;
+  static constexpr int kEpiBytes = EW * epi::WARP_STAGE_FLOATS * 4;
+  static constexpr int kSmem = STAGES * STAGE_BYTES + kEpiBytes + 1024;
+};
 
 struct Args {
   const float* bias; const void* R; void* C;   // R has the element type of C
@@ -32,9 +39,9 @@ struct Args {
   int act;
 };
 
-template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES>
-__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                  const __grid_constant__ CUtensorMap tmW, Args g) {
+template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, int STAGES, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmW, Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -47,7 +54,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_c
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 128); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], EW * 32); }
     tc::mbar_fence_init();
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
@@ -100,7 +107,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_c
   } else {
     // ------------------------------------------------------------------ epilogue: warp w -> TMEM lanes 32*(w%4) ..
     const int quad = warp & 3;
-    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + quad * epi::WARP_STAGE_FLOATS;
+    const int c_lo = (EW == 8) ? ((warp - 2) >> 2) * (BN / 64) : 0, c_hi = (EW == 8) ? c_lo + BN / 64 : BN / 32;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES) + (warp - 2) * epi::WARP_STAGE_FLOATS;
     long long it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tma_kernel(const __grid_c
       tc::tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= g.N) break;
         float v[32];
@@ -178,20 +186,24 @@ S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act};
   cudaStream_t st = s6_stream(stream);
+  const bool deep_k = K >= 1024;
+#define LAUNCH_ONE(OT, ACT, HB, HR, ST, EWN)                                                                           \
+  do {                                                                                                                 \
+    auto k = gemm_tma_kernel<OT, ACT, HB, HR, ST, EWN>;                                                                \
+    S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<ST, EWN>::kSmem));               \
+    k<<<grid, Cfg<ST, EWN>::kThreads, Cfg<ST, EWN>::kSmem, st>>>(tmA, tmW, g);                                         \
+  } while (0)
 #define LAUNCH_TMA(ACT, HB, HR)                                                                                        \
   do {                                                                                                                 \
     if (c_dtype) {                                                                                                     \
-      auto k = gemm_tma_kernel<__nv_bfloat16, ACT, HB, HR>;                                                            \
-      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                      \
-      k<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmW, g);                                                           \
+      if (deep_k) LAUNCH_ONE(__nv_bfloat16, ACT, HB, HR, 4, 4); else LAUNCH_ONE(__nv_bfloat16, ACT, HB, HR, 3, 8);    \
     } else {                                                                                                           \
-      auto k = gemm_tma_kernel<float, ACT, HB, HR>;                                                                    \
-      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                      \
-      k<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmW, g);                                                           \
+      if (deep_k) LAUNCH_ONE(float, ACT, HB, HR, 4, 4); else LAUNCH_ONE(float, ACT, HB, HR, 3, 8);                    \
     }                                                                                                                  \
   } while (0)
   EPI_DISPATCH(act, bias, R, LAUNCH_TMA);
 #undef LAUNCH_TMA
+#undef LAUNCH_ONE
   S6_LAUNCH_CHECK();
   return 0;
 }

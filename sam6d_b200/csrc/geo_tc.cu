@@ -20,14 +20,19 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 256, BK = 64, KBLOCKS = 4, ASTAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, KBLOCKS = 4;
 constexpr int A_SLAB = BM * BK * 2;          // 16 KB
 constexpr int W_SLAB = BN * BK * 2;          // 32 KB
 constexpr int NUM_PRODUCERS = 256;                  // warps 4-11
 constexpr int MMA_WARP = 12;
-constexpr int NUM_THREADS = 128 + NUM_PRODUCERS + 32;
-constexpr int EPI_BYTES = 4 * epi::WARP_STAGE_FLOATS * 4;
-constexpr int SMEM_BYTES = KBLOCKS * W_SLAB + ASTAGES * A_SLAB + EPI_BYTES + 1024;
+constexpr int NUM_THREADS = 128 + NUM_PRODUCERS + 32 + 128;   // epilogue warps 0-3 and 13-16 (two per TMEM lane quadrant)
+// the distance pass stages its full-line stores through shared memory (8 warps x 4.5 KB) and runs a 3-deep A ring to fit
+template <int MODE>
+struct Cfg {
+  static constexpr int kStages = (MODE == 0) ? 4 : 3;
+  static constexpr int kEpiBytes = (MODE == 0) ? 0 : 8 * epi::WARP_STAGE_FLOATS * 4;
+  static constexpr int kSmem = KBLOCKS * W_SLAB + kStages * A_SLAB + kEpiBytes + 1024;
+};
 
 template <typename ET>
 __device__ __forceinline__ void store8(ET* p, const float v[8]);
@@ -62,6 +67,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
                                                                       const float* __restrict__ div_term,
                                                                       const __nv_bfloat16* __restrict__ Wb,   // (256 out, 256 in) bf16
                                                                       const float* __restrict__ bias, ET* __restrict__ E) {
+  constexpr int ASTAGES = Cfg<MODE>::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_smem = smem;                              // 4 slabs [256][64] bf16
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
 
   if (tid == 0) {
     for (int s = 0; s < ASTAGES; ++s) { tc::mbar_init(&full_bar[s], NUM_PRODUCERS / 32); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 128); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 256); }
     tc::mbar_fence_init();
   }
   if (tid < 128) omega[tid] = div_term[tid];
@@ -175,29 +181,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
     long long it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
-      const int r = warp * 32 + lane;
+      const int quad = warp & 3, c0 = (warp < 4) ? 0 : 4;      // this warp's TMEM lane quadrant and its 4 column chunks
+      const int r = quad * 32 + lane;
       // angle pass: E already holds proj_d(...) + biases from the distance pass; fetch this lane's 8 x 8 columns of it before
       // waiting for the accumulator so the read-modify-write latency hides behind the MMAs of the tile
-      constexpr int RAW = (MODE == 0) ? 8 : 1;
+      constexpr int RAW = (MODE == 0) ? 4 : 1;
       uint4 raw[RAW][sizeof(ET) == 4 ? 2 : 1];
       if (MODE == 0) {
         const long long pair = tile * 32 + (r >> 2);
         if (pair < npairs) {
           const uint4* src = reinterpret_cast<const uint4*>(E + pair * 256 + (r & 3) * 8);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-            for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[c * (sizeof(ET) == 4 ? 8 : 4) + u];
+            for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[(c0 + c) * (sizeof(ET) == 4 ? 8 : 4) + u];
         }
       }
       tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       if (MODE == 0) {
         const long long pair = tile * 32 + (r >> 2);
         const int q = r & 3;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = c0 + cc;
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
           if (q == 3) {
@@ -221,18 +229,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
           }
           if (pair < npairs) {
             float e[8];
-            load8<ET>(reinterpret_cast<const ET*>(&raw[c][0]), e);
+            load8<ET>(reinterpret_cast<const ET*>(&raw[cc][0]), e);
 #pragma unroll
             for (int i = 0; i < 8; ++i) e[i] += o[i];
             store8<ET>(E + pair * 256 + c * 32 + q * 8, e);
           }
         }
       } else {
-        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * A_SLAB) + warp * epi::WARP_STAGE_FLOATS;
-        const long long row0 = tile * 128 + warp * 32;
+        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * A_SLAB) +
+                       (quad + c0) * epi::WARP_STAGE_FLOATS;
+        const long long row0 = tile * 128 + quad * 32;
         (void)raw;
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {
+        for (int c = c0; c < c0 + 4; ++c) {
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
           // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch)
@@ -252,12 +261,12 @@ template <int MODE, typename ET>
 int launch_pass(const float* T, long long npairs, const float* div_term, const __nv_bfloat16* W, const float* bias, ET* E, int sms,
                 cudaStream_t st) {
   auto kern = geo_embed_tc_kernel<MODE, ET>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<MODE>::kSmem);
   if (e != cudaSuccess) return (int)e;
   const long long per = (MODE == 0) ? 32 : 128;
   const long long ntiles = (npairs + per - 1) / per;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(T, npairs, div_term, W, bias, E);
+  kern<<<grid, NUM_THREADS, Cfg<MODE>::kSmem, st>>>(T, npairs, div_term, W, bias, E);
   return (int)cudaGetLastError();
 }
 

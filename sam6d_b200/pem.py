@@ -228,12 +228,60 @@ class GeometricTransformer(nn.Module):
                     B, NUM_HEADS, S, Sm, 1.0 / math.sqrt(C // NUM_HEADS), hid.data_ptr(), C, S * C)
         return _attn_tail(self.precision, x2d, hid, w["tail_cross"]).view(B, S, C)
 
+    # ---- bf16 token stream (precision="bf16", both clouds in one allocation): every Linear is the persistent TMA GEMM, the
+    # residual stream, LayerNorm inputs/outputs and the attention output are bf16, accumulation and statistics fp32.
+    def _tail_bf16(self, x2d, hid, lw, out=None):
+        bf = torch.bfloat16
+        y = ops.gemm_tma(hid, lw["wo"].bf16, lw["bo"], residual=x2d, out_dtype=bf)
+        y = ops.layernorm_bf16io(y, lw["g1"], lw["b1"])
+        h = ops.gemm_tma(y, lw["we"].bf16, lw["be"], act=1, out_dtype=bf)
+        z = ops.gemm_tma(h, lw["ws"].bf16, lw["bs"], residual=y, out_dtype=bf)
+        return ops.layernorm_bf16io(z, lw["g2"], lw["b2"], out=out)
+
+    def _self_bf16(self, x, emb, w):
+        B, S, C = x.shape
+        d = C // NUM_HEADS
+        x2d = x.view(B * S, C)
+        qkv = ops.gemm_tma(x2d, w["w_qkv"].bf16, w["b_qkv"], out_dtype=torch.bfloat16)             # (B*S, q|k|v)
+        u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                              # (B*S, 4*C) fp32
+        sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
+        vt = ops.transpose_tokens(qkv, 2 * C, C, B, S)
+        hid = ops.attn_tc(qkv, 0, qkv, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
+        return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
+
+    def _cross_bf16(self, x, mem, w, out):
+        B, S, C = x.shape
+        Sm = mem.shape[1]
+        d = C // NUM_HEADS
+        x2d = x.view(B * S, C)
+        q = ops.gemm_tma(x2d, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
+        kv = ops.gemm_tma(mem.view(B * Sm, C), w["wkv_c"].bf16, w["bkv_c"], out_dtype=torch.bfloat16)
+        vt = ops.transpose_tokens(kv, C, C, B, Sm)
+        hid = ops.attn_tc(q, 0, kv, 0, vt, B, NUM_HEADS, S, Sm, d, 1.0 / math.sqrt(d), out_dtype=torch.bfloat16)
+        self._tail_bf16(x2d, hid, w["tail_cross"], out=out.view(B * S, C))
+
+    def _forward_bf16(self, f, emb, w):
+        """f (2B,S,C) bf16 = [cloud 0 ; cloud 1], emb (2B,S,S,256) -> same layout"""
+        B = f.shape[0] // 2
+        f = self._self_bf16(f, emb, w)
+        out = torch.empty_like(f)
+        self._cross_bf16(f[:B], f[B:], w, out[:B])
+        self._cross_bf16(f[B:], out[:B], w, out[B:])        # sequential: sees the updated cloud 0 (transformer.py:505-507)
+        return out
+
     @torch.no_grad()
     def forward(self, feats0, embeddings0, feats1, embeddings1, masks0=None, masks1=None):
         if masks0 is not None or masks1 is not None:
             raise NotImplementedError("key masks are never used on the SAM-6D inference path")
         w = self._weights()
         emb = _stack2(embeddings0, embeddings1) if feats0.shape == feats1.shape else None
+        if emb is not None and self.precision == "bf16" and feats0.shape[1] <= 256:
+            B = feats0.shape[0]
+            f = _stack2(feats0, feats1)
+            if f is None:
+                f = torch.cat([feats0, feats1], dim=0)
+            f = self._forward_bf16(f.to(torch.bfloat16).contiguous(), emb, w)
+            return f[:B], f[B:]
         if emb is not None:
             # both clouds share the self-attention weights: one batch of 2B through every kernel of the layer
             B = feats0.shape[0]
@@ -387,9 +435,15 @@ class CoarsePointMatching(nn.Module):
     def _embed(self, f):
         B, n, C = f.shape
         w = self._weights()
-        out = torch.empty(B, n + 1, self.cfg.hidden_dim, dtype=torch.float32, device=f.device)
-        out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
         H = self.cfg.hidden_dim
+        if self.precision == "bf16":                          # the sparse token stream is bf16 in this mode
+            out = torch.empty(B, n + 1, H, dtype=torch.bfloat16, device=f.device)
+            out[:, 0, :] = self.bg_token.detach().reshape(1, -1).to(torch.bfloat16)
+            ops.gemm_tc_raw(f.data_ptr(), 0, w["w_in"].bf16.data_ptr(), 1, w["b_in"], 0, out.data_ptr() + H * 2, 1, n, H, C, C, C, H, 0,
+                            batch=B, sA=n * C, sW=0, sC=(n + 1) * H)
+            return out
+        out = torch.empty(B, n + 1, H, dtype=torch.float32, device=f.device)
+        out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
         _gemm_raw(self.precision, f.data_ptr(), w["w_in"], w["b_in"], 0, out.data_ptr() + H * 4, n, H, C, C, H, 0, batch=B,
                   sA=n * C, sC=(n + 1) * H)
         return out
@@ -568,7 +622,7 @@ class SparseToDenseTransformer(nn.Module):
     def _sample_feats(self, dense_feats, idx_ext):
         # quirk Q1 (transformer.py:651-658): the gather runs on the bg-prefixed sequence with the raw FPS index
         if dense_feats.dtype == torch.bfloat16:
-            return ops.gather_rows_bf16_f32(dense_feats, idx_ext)
+            return ops.gather_rows_bf16(dense_feats, idx_ext)
         return ops.gather_rows(dense_feats, idx_ext)
 
     def _dense_layer_bf16(self, dense, sparse, w):
@@ -582,8 +636,9 @@ class SparseToDenseTransformer(nn.Module):
         x2d = dense.view(B * N1, C)
         q = ops.gemm_tma(x2d, w["wq"].bf16, w["bq"], out_dtype=bf)
         kv = torch.empty(B * J, 2 * C, dtype=torch.float32, device=dev)
-        _gemm_raw("bf16", sparse.data_ptr() + C * 4, w["wkv"], w["bkv"], 0, kv.data_ptr(), J, 2 * C, C, C, 2 * C, 0, batch=B,
-                  sA=(J + 1) * C, sC=J * 2 * C)
+        s_bf = sparse.dtype == torch.bfloat16
+        ops.gemm_tc_raw(sparse.data_ptr() + C * (2 if s_bf else 4), int(s_bf), w["wkv"].bf16.data_ptr(), 1, w["bkv"], 0, kv.data_ptr(), 0,
+                        J, 2 * C, C, C, C, 2 * C, 0, batch=B, sA=(J + 1) * C, sW=0, sC=J * 2 * C)
         ops.focus_rows_raw(kv.data_ptr(), (B * J, 0, 2 * C), kv.data_ptr(), (B * J, 0, 2 * C), w["sp_scale"], B * J, C)
         blob, KS = ops.linattn_kv_pack_raw(kv.data_ptr(), 2 * C, J * 2 * C, kv.data_ptr() + C * 4, 2 * C, J * 2 * C, B, J, dev)
         x_att = torch.empty(B * N1, C, dtype=bf, device=dev)
