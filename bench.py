@@ -229,12 +229,36 @@ def main():
 
     host_out = torch.empty(world * B, sdist.POSE_FLOATS).pin_memory()
 
+    # end to end through the public API (Net.forward on a dict of device tensors): every step copies its inputs from pinned
+    # host memory and reads its poses back.  The copies run on a second stream into the other half of a double buffer, so
+    # step i+1's inputs arrive while step i computes (K host->device copies and K read-backs inside the timed region).
+    copy_stream = torch.cuda.Stream(dev)
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in h.items()} for h in host]
+    copied, computed, pipe = [None, None], [None, None], {"next": 0}
+
+    def issue_copy(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            if computed[s] is not None:
+                copy_stream.wait_event(computed[s])          # the step that last read this buffer has finished
+            for k, v in host[s].items():
+                dev_in[s][k].copy_(v, non_blocking=True)
+            copied[s] = torch.cuda.Event()
+            copied[s].record(copy_stream)
+        pipe["next"] = i + 1
+
     def step_e2e(i):
-        ep = {k: v.to(dev, non_blocking=True) for k, v in host[i % 2].items()}
+        if pipe["next"] <= i:
+            issue_copy(i)
+        torch.cuda.current_stream().wait_event(copied[i % 2])
+        if i + 1 < args.steps:
+            issue_copy(i + 1)
         rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev, generator=gen)
-        out = net(ep, rand=rand)
+        out = net(dict(dev_in[i % 2]), rand=rand)
         poses = sdist.all_gather_poses(sdist.pack_poses(out))
         host_out.copy_(poses, non_blocking=True)
+        computed[i % 2] = torch.cuda.Event()
+        computed[i % 2].record()
         return poses
 
     def barrier():
@@ -284,6 +308,8 @@ def main():
     _, _, kms = timed(step_resident, args.steps, profile_kernel="sam6d_rpe_scores")
     for i in range(2):
         step_e2e(i)
+    torch.cuda.synchronize()
+    pipe["next"], computed[0], computed[1] = 0, None, None     # the timed run issues all of its own copies
     ms_e2e, _, _ = timed(step_e2e, args.steps)
     if sampler:
         sampler.stop_flag = True

@@ -43,6 +43,10 @@ int sam6d_gather_rows_bf16_f32(const void* src, const int* idx, int b, int n, in
  * all zero when empty.  cnt (b,m), optional: number of distinct hits kept. */
 int sam6d_ball_query(const float* new_xyz, const float* xyz, int b, int n, int m, float radius, int nsample, int* idx,
                      int* cnt, void* stream);
+/* two concentric queries (radius_a <= radius_b) of the same clouds in one sweep; outputs as from two sam6d_ball_query calls
+ * (PositionalEncoding groups at r1/ns1 and r2/ns2, PEM/model/fine_point_matching.py:104-109) */
+int sam6d_ball_query_pair(const float* new_xyz, const float* xyz, int b, int n, int m, float radius_a, int nsample_a,
+                          float radius_b, int nsample_b, int* idx_a, int* idx_b, int* cnt_a, int* cnt_b, void* stream);
 
 /* _ext.group_points (PN2/_ext_src/src/group_points.cpp:13-38, group_points_gpu.cu:13-33): points (b,c,n), idx (b,np,ns) -> (b,c,np,ns) */
 int sam6d_group_points(const float* points, const int* idx, int b, int c, int n, int np, int ns, float* out, void* stream);
@@ -159,7 +163,8 @@ int sam6d_pe_mlp_max(const float* pts, const int* idx, const int* cnt, int B, in
 int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, const float* W1, const float* B1,
                         const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
                         int out_off, void* stream);
-/* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls */
+/* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls.  fine_assign: A (B,S,S) fp32 scores with row stride ld,
+ * ld % 4 == 0, 16-byte aligned rows, S >= 97; scratch rsum/csum (B,ld), cpart/cpi (B,ceil(S/32),ld). */
 int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
                       int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream);
 int sam6d_weighted_procrustes(const float* src, const float* ref, const float* wts, int B, int N, float weight_thresh,

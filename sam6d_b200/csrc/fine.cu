@@ -13,114 +13,159 @@ namespace {
 
 constexpr int RT = 32;  // rows per tile in the column-reducing passes
 
-// pass 1: rsum (B,S); column partial sums cpart (B,tiles,S)
-__global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict__ A, int S, int ld, float shift, float* __restrict__ rsum,
+// All three passes stream A with 16-byte loads (row stride ld % 4 == 0, the padded layout compute_feature_similarity writes):
+// a thread owns 4 adjacent columns, keeps its partial sums / maxima in registers and has up to 32 independent loads in
+// flight; reciprocals of the row and column sums are stored once (rinv, cinv) so the later passes multiply.
+__device__ __forceinline__ float4 exp4(const float4 v, float shift, int j, int S) {
+  float4 e;
+  e.x = (j + 0 < S) ? __expf(v.x - shift) : 0.f;   // padding columns hold arbitrary bits: select, never multiply
+  e.y = (j + 1 < S) ? __expf(v.y - shift) : 0.f;
+  e.z = (j + 2 < S) ? __expf(v.z - shift) : 0.f;
+  e.w = (j + 3 < S) ? __expf(v.w - shift) : 0.f;
+  return e;
+}
+
+// pass 1: rinv (B,ld) = 1 / row sums; column partial sums cpart (B,tiles,ld)
+__global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict__ A, int S, int ld, float shift, float* __restrict__ rinv,
                                                         float* __restrict__ cpart) {
-  __shared__ float racc[RT];
-  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const int i0 = tile * RT;
-  if (tid < RT) racc[tid] = 0.f;
-  __syncthreads();
-  const float* Ab = A + (size_t)b * S * ld;
-  for (int j0 = 0; j0 < S; j0 += 256) {
-    const int j = j0 + tid;
-    float cacc = 0.f;
+  __shared__ float red[8][RT];
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i0 = tile * RT, rmax = min(RT, S - i0);
+  const float* Ab = A + (size_t)b * S * ld + (size_t)i0 * ld;
+  float racc[RT];
+#pragma unroll
+  for (int r = 0; r < RT; ++r) racc[r] = 0.f;
+  for (int j = tid * 4; j < S; j += 1024) {
+    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
     for (int r = 0; r < RT; ++r) {
-      const int i = i0 + r;
-      if (i >= S) break;
-      float e = (j < S) ? __expf(Ab[(size_t)i * ld + j] - shift) : 0.f;
-      cacc += e;
-      float rs = warp_sum(e);
-      if (lane == 0) atomicAdd(&racc[r], rs);
-    }
-    if (j < S) cpart[((size_t)b * gridDim.x + tile) * S + j] = cacc;
-  }
-  __syncthreads();
-  if (tid < RT && i0 + tid < S) rsum[(size_t)b * S + i0 + tid] = racc[tid];
-}
-
-__global__ void colsum_reduce_kernel(const float* __restrict__ cpart, int tiles, int S, float* __restrict__ csum) {
-  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= S) return;
-  float s = 0.f;
-  for (int t = 0; t < tiles; ++t) s += cpart[((size_t)b * tiles + t) * S + j];
-  csum[(size_t)b * S + j] = s;
-}
-
-// pass 2: column labels lab2[b,j] = argmax_i P_ij (first max) as per-tile partials.  Along a column the factor
-// e_ij / csum_j ... is shared, so P_ij is ordered like e_ij * (e_ij / rsum_i); we evaluate the full product like the reference.
-__global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rsum,
-                                                             const float* __restrict__ csum, float* __restrict__ cpv,
-                                                             int* __restrict__ cpi) {
-  __shared__ float rinv[RT];
-  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  const int i0 = tile * RT;
-  if (tid < RT) rinv[tid] = (i0 + tid < S) ? 1.f / rsum[(size_t)b * S + i0 + tid] : 0.f;
-  __syncthreads();
-  const float* Ab = A + (size_t)b * S * ld;
-  for (int j0 = 0; j0 < S; j0 += 256) {
-    const int j = j0 + tid;
-    if (j >= S) break;
-    const float cinv = 1.f / csum[(size_t)b * S + j];
-    float cbv = -INFINITY;
-    int cbi = 0;
-#pragma unroll 8
-    for (int r = 0; r < RT; ++r) {
-      const int i = i0 + r;
-      if (i < S) {
-        float e = __expf(Ab[(size_t)i * ld + j] - shift);
-        float p = (e * rinv[r]) * (e * cinv);
-        if (p > cbv) { cbv = p; cbi = i; }                     // ascending i: first max wins
+      if (r < rmax) {
+        const float4 e = exp4(__ldcs(reinterpret_cast<const float4*>(Ab + (size_t)r * ld + j)), shift, j, S);
+        c.x += e.x; c.y += e.y; c.z += e.z; c.w += e.w;
+        racc[r] += (e.x + e.y) + (e.z + e.w);
       }
     }
-    cpv[((size_t)b * gridDim.x + tile) * S + j] = cbv;
-    cpi[((size_t)b * gridDim.x + tile) * S + j] = cbi;
+    *reinterpret_cast<float4*>(cpart + ((size_t)b * gridDim.x + tile) * ld + j) = c;
+  }
+#pragma unroll
+  for (int r = 0; r < RT; ++r) {
+    const float v = warp_sum(racc[r]);
+    if (lane == 0) red[warp][r] = v;
+  }
+  __syncthreads();
+  if (tid < rmax) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    rinv[(size_t)b * ld + i0 + tid] = 1.f / s;
   }
 }
 
-__global__ void collab_reduce_kernel(const float* __restrict__ cpv, const int* __restrict__ cpi, int tiles, int S,
+__global__ void colsum_reduce_kernel(const float* __restrict__ cpart, int tiles, int S, int ld, float* __restrict__ cinv) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld) return;
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += cpart[((size_t)b * tiles + t) * ld + j];
+  cinv[(size_t)b * ld + j] = (j < S) ? 1.f / s : 0.f;
+}
+
+// pass 2: column labels lab2[b,j] = argmax_i P_ij (first max) as per-tile partials; the full product is evaluated like the
+// reference does.
+__global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rinv,
+                                                             const float* __restrict__ cinv, float* __restrict__ cpv,
+                                                             int* __restrict__ cpi) {
+  __shared__ float ri[RT];
+  const int tile = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const int i0 = tile * RT, rmax = min(RT, S - i0);
+  if (tid < RT) ri[tid] = (tid < rmax) ? rinv[(size_t)b * ld + i0 + tid] : 0.f;
+  __syncthreads();
+  const float* Ab = A + (size_t)b * S * ld + (size_t)i0 * ld;
+  for (int j = tid * 4; j < S; j += 1024) {
+    const float4 ci = *reinterpret_cast<const float4*>(cinv + (size_t)b * ld + j);
+    float4 bv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    int4 bi = make_int4(0, 0, 0, 0);
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+      if (r < rmax) {
+        const float4 e = exp4(__ldcs(reinterpret_cast<const float4*>(Ab + (size_t)r * ld + j)), shift, j, S);
+        const float rr = ri[r];
+        const float p0 = (e.x * rr) * (e.x * ci.x), p1 = (e.y * rr) * (e.y * ci.y), p2 = (e.z * rr) * (e.z * ci.z), p3 = (e.w * rr) * (e.w * ci.w);
+        if (p0 > bv.x) { bv.x = p0; bi.x = i0 + r; }              // ascending i: first max wins
+        if (p1 > bv.y) { bv.y = p1; bi.y = i0 + r; }
+        if (p2 > bv.z) { bv.z = p2; bi.z = i0 + r; }
+        if (p3 > bv.w) { bv.w = p3; bi.w = i0 + r; }
+      }
+    }
+    *reinterpret_cast<float4*>(cpv + ((size_t)b * gridDim.x + tile) * ld + j) = bv;
+    *reinterpret_cast<int4*>(cpi + ((size_t)b * gridDim.x + tile) * ld + j) = bi;
+  }
+}
+
+__global__ void collab_reduce_kernel(const float* __restrict__ cpv, const int* __restrict__ cpi, int tiles, int S, int ld,
                                      int* __restrict__ lab2) {
   const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S) return;
   float bv = -INFINITY; int bi = 0;
   for (int t = 0; t < tiles; ++t) {
-    float v = cpv[((size_t)b * tiles + t) * S + j];
-    if (v > bv) { bv = v; bi = cpi[((size_t)b * tiles + t) * S + j]; }
+    float v = cpv[((size_t)b * tiles + t) * ld + j];
+    if (v > bv) { bv = v; bi = cpi[((size_t)b * tiles + t) * ld + j]; }
   }
   lab2[(size_t)b * S + j] = bi;
 }
 
+// the masked template points of pass 3: q4[b,j] = (pts2[b,j-1], 1) if column j >= 1 is matched to a non-background row
+// (lab2 > 0), else 0.  Written over the (now consumed) partials.
+__global__ void masked_points_kernel(const int* __restrict__ lab2, const float* __restrict__ pts2, int S, int ld,
+                                     float4* __restrict__ q4) {
+  const int b = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ld) return;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j >= 1 && j < S && lab2[(size_t)b * S + j] > 0) {
+    const float* p = pts2 + ((size_t)b * (S - 1) + (j - 1)) * 3;
+    q = make_float4(p[0], p[1], p[2], 1.f);
+  }
+  q4[(size_t)b * ld + j] = q;
+}
+
 // pass 3, one warp per row i >= 1: lab1_i = argmax_j P_ij (first max); if it is not the background column,
 //   w_i = sum_{j>=1, lab2_j>0} P_ij,  pred_i = sum_j P_ij pts2_j / (w_i + 1e-6)      (second sweep hits L1/L2)
-__global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rsum,
-                                                            const float* __restrict__ csum, int* __restrict__ lab1,
-                                                            const int* __restrict__ lab2, const float* __restrict__ pts2,
-                                                            float* __restrict__ wts, float* __restrict__ pred) {
+__global__ void __launch_bounds__(256) fine_weighted_kernel(const float* __restrict__ A, int S, int ld, float shift, const float* __restrict__ rinv,
+                                                            const float* __restrict__ cinv, int* __restrict__ lab1,
+                                                            const float4* __restrict__ q4, float* __restrict__ wts, float* __restrict__ pred) {
   const int b = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * 8 + (threadIdx.x >> 5);   // dense index 0..N-1
   const int N = S - 1;
   if (i >= N) return;
   const float* row = A + ((size_t)b * S + i + 1) * ld;
-  const float rinv = 1.f / rsum[(size_t)b * S + i + 1];
-  const float* cs = csum + (size_t)b * S;
+  const float ri = rinv[(size_t)b * ld + i + 1];
+  const float* ci = cinv + (size_t)b * ld;
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  for (int j = lane; j < S; j += 32) {
-    float e = __expf(row[j] - shift);
-    float p = (e * rinv) * (e / cs[j]);
-    if (p > bv) { bv = p; bi = j; }
+#pragma unroll 4
+  for (int j = lane * 4; j < S; j += 128) {
+    const float4 e = exp4(*reinterpret_cast<const float4*>(row + j), shift, j, S);
+    const float4 c = *reinterpret_cast<const float4*>(ci + j);
+    const float p0 = (e.x * ri) * (e.x * c.x), p1 = (e.y * ri) * (e.y * c.y), p2 = (e.z * ri) * (e.z * c.z), p3 = (e.w * ri) * (e.w * c.w);
+    if (p0 > bv) { bv = p0; bi = j; }                       // padding columns give p = 0 (cinv = 0, e = 0): never a strict max
+    if (p1 > bv) { bv = p1; bi = j + 1; }
+    if (p2 > bv) { bv = p2; bi = j + 2; }
+    if (p3 > bv) { bv = p3; bi = j + 3; }
   }
   warp_argmax_first(bv, bi);
   if (lane == 0) lab1[(size_t)b * S + i + 1] = bi;
   float w = 0.f, px = 0.f, py = 0.f, pz = 0.f;
   if (bi > 0) {
-    const int* l2 = lab2 + (size_t)b * S;
-    for (int j = 1 + lane; j < S; j += 32) {
-      if (l2[j] > 0) {
-        float e = __expf(row[j] - shift);
-        float p = (e * rinv) * (e / cs[j]);
-        const float* q = pts2 + ((size_t)b * N + (j - 1)) * 3;
-        w += p; px = fmaf(p, q[0], px); py = fmaf(p, q[1], py); pz = fmaf(p, q[2], pz);
+    const float4* qb = q4 + (size_t)b * ld;
+#pragma unroll 2
+    for (int j = lane * 4; j < S; j += 128) {
+      const float4 e = exp4(*reinterpret_cast<const float4*>(row + j), shift, j, S);
+      const float4 c = *reinterpret_cast<const float4*>(ci + j);
+      const float pk[4] = {(e.x * ri) * (e.x * c.x), (e.y * ri) * (e.y * c.y), (e.z * ri) * (e.z * c.z), (e.w * ri) * (e.w * c.w)};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 q = qb[j + k];
+        const float p = pk[k] * q.w;
+        w += p; px = fmaf(p, q.x, px); py = fmaf(p, q.y, py); pz = fmaf(p, q.z, pz);
       }
     }
     w = warp_sum(w); px = warp_sum(px); py = warp_sum(py); pz = warp_sum(pz);
@@ -235,26 +280,32 @@ __global__ void __launch_bounds__(1024) pose_score_kernel(const float* __restric
 
 }  // namespace
 
-// A (B,S,S) f32 score matrix with row stride ld >= S (row/col 0 = background), pts2 (B,S-1,3).
+// A (B,S,S) f32 score matrix with row stride ld >= S, ld % 4 == 0, 16-byte aligned (row/col 0 = background), pts2 (B,S-1,3).
 // Outputs: lab1 (B,S) i32 (row argmax of P; entry 0 unused), lab2 (B,S) i32, wts (B,S-1), pred (B,S-1,3).
-// Scratch: rsum (B,S), csum (B,S), cpart (B,tiles,S) f32, cpi (B,tiles,S) i32, tiles = ceil(S/32).
+// Scratch: rsum (B,ld), csum (B,ld) [hold the reciprocal sums], cpart (B,tiles,ld) f32, cpi (B,tiles,ld) i32, tiles = ceil(S/32).
 S6_API int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum,
                              float* cpart, int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream) {
   S6_REQUIRE(A && pts2 && rsum && csum && cpart && cpi && lab1 && lab2 && wts && pred && B >= 0 && S >= 2 && ld >= S);
+  S6_REQUIRE((ld % 4) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(rsum) | reinterpret_cast<uintptr_t>(csum) |
+                               reinterpret_cast<uintptr_t>(cpart) | reinterpret_cast<uintptr_t>(cpi)) & 15) == 0);
   if (B == 0) return 0;
   cudaStream_t st = s6_stream(stream);
   const int tiles = s6_cdiv(S, RT);
-  dim3 gt(tiles, B), gc(s6_cdiv(S, 256), B);
+  S6_REQUIRE(tiles >= 4);                                  // the masked points (B,ld) float4 live in cpart after pass 2
+  dim3 gt(tiles, B), gc(s6_cdiv(ld, 256), B);
   fine_sums_kernel<<<gt, 256, 0, st>>>(A, S, ld, shift, rsum, cpart);
   S6_LAUNCH_CHECK();
-  colsum_reduce_kernel<<<gc, 256, 0, st>>>(cpart, tiles, S, csum);
+  colsum_reduce_kernel<<<gc, 256, 0, st>>>(cpart, tiles, S, ld, csum);
   S6_LAUNCH_CHECK();
   fine_collabels_kernel<<<gt, 256, 0, st>>>(A, S, ld, shift, rsum, csum, cpart, cpi);
   S6_LAUNCH_CHECK();
-  collab_reduce_kernel<<<gc, 256, 0, st>>>(cpart, cpi, tiles, S, lab2);
+  collab_reduce_kernel<<<gc, 256, 0, st>>>(cpart, cpi, tiles, S, ld, lab2);
+  S6_LAUNCH_CHECK();
+  float4* q4 = reinterpret_cast<float4*>(cpart);
+  masked_points_kernel<<<gc, 256, 0, st>>>(lab2, pts2, S, ld, q4);
   S6_LAUNCH_CHECK();
   dim3 gw(s6_cdiv(S - 1, 8), B);
-  fine_weighted_kernel<<<gw, 256, 0, st>>>(A, S, ld, shift, rsum, csum, lab1, lab2, pts2, wts, pred);
+  fine_weighted_kernel<<<gw, 256, 0, st>>>(A, S, ld, shift, rsum, csum, lab1, q4, wts, pred);
   S6_LAUNCH_CHECK();
   return 0;
 }

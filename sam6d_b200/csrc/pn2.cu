@@ -336,6 +336,84 @@ S6_API int sam6d_ball_query(const float* new_xyz, const float* xyz, int b, int n
   return 0;
 }
 
+// Two concentric ball queries over the same clouds in one sweep (PositionalEncoding groups every point at r1/ns1 and r2/ns2,
+// fine_point_matching.py:104-109): the distance is computed once, each list keeps its own counter and first hit.
+__global__ void __launch_bounds__(256) ball_query_pair_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n,
+                                                              int m, float ra2, int nsa, float rb2, int nsb, int* __restrict__ idxa,
+                                                              int* __restrict__ idxb, int* __restrict__ cnta_out,
+                                                              int* __restrict__ cntb_out) {
+  extern __shared__ float sp[];
+  const int TILE = 1024;
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;
+  const float* p = xyz + (size_t)b * n * 3;
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if (j < m) {
+    const float* q = new_xyz + ((size_t)b * m + j) * 3;
+    nx = q[0]; ny = q[1]; nz = q[2];
+  }
+  int* oa = (j < m) ? idxa + ((size_t)b * m + j) * nsa : nullptr;
+  int* ob = (j < m) ? idxb + ((size_t)b * m + j) * nsb : nullptr;
+  int ca = 0, cb = 0, fa = 0, fb = 0;
+  const unsigned below = (1u << lane) - 1u;
+  for (int base = 0; base < n; base += TILE) {
+    int tn = min(TILE, n - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) sp[i] = p[(size_t)base * 3 + i];
+    __syncthreads();
+    if (j < m && (ca < nsa || cb < nsb)) {
+      for (int k0 = 0; k0 < tn && (ca < nsa || cb < nsb); k0 += 32) {
+        int k = k0 + lane;
+        float d2 = INFINITY;
+        if (k < tn) {
+          float dx = nx - sp[k * 3 + 0], dy = ny - sp[k * 3 + 1], dz = nz - sp[k * 3 + 2];
+          d2 = __fmul_rn(dx, dx);
+          d2 = __fmaf_rn(dy, dy, d2);
+          d2 = __fmaf_rn(dz, dz, d2);
+        }
+        const bool ha = d2 < ra2, hb = d2 < rb2;
+        const unsigned mb = __ballot_sync(0xffffffffu, hb);
+        if (mb) {
+          if (cb < nsb) {
+            if (cb == 0) fb = base + k0 + __ffs(mb) - 1;
+            int pos = cb + __popc(mb & below);
+            if (hb && pos < nsb) ob[pos] = base + k;
+            cb += __popc(mb);
+          }
+          const unsigned ma = __ballot_sync(0xffffffffu, ha);
+          if (ma && ca < nsa) {
+            if (ca == 0) fa = base + k0 + __ffs(ma) - 1;
+            int pos = ca + __popc(ma & below);
+            if (ha && pos < nsa) oa[pos] = base + k;
+            ca += __popc(ma);
+          }
+        }
+      }
+    }
+  }
+  if (j < m) {
+    int c = min(ca, nsa);
+    for (int l = c + lane; l < nsa; l += 32) oa[l] = (ca > 0) ? fa : 0;
+    if (cnta_out && lane == 0) cnta_out[(size_t)b * m + j] = c;
+    c = min(cb, nsb);
+    for (int l = c + lane; l < nsb; l += 32) ob[l] = (cb > 0) ? fb : 0;
+    if (cntb_out && lane == 0) cntb_out[(size_t)b * m + j] = c;
+  }
+}
+
+// radius_a <= radius_b.  Same outputs as two sam6d_ball_query calls.
+S6_API int sam6d_ball_query_pair(const float* new_xyz, const float* xyz, int b, int n, int m, float radius_a, int nsample_a,
+                                 float radius_b, int nsample_b, int* idx_a, int* idx_b, int* cnt_a, int* cnt_b, void* stream) {
+  S6_REQUIRE(new_xyz && xyz && idx_a && idx_b && b >= 0 && n > 0 && m >= 0 && nsample_a > 0 && nsample_b > 0 &&
+             radius_a <= radius_b);
+  if (b == 0 || m == 0) return 0;
+  dim3 grid(s6_cdiv(m, 8), b);
+  ball_query_pair_kernel<<<grid, 256, 1024 * 3 * sizeof(float), s6_stream(stream)>>>(
+      new_xyz, xyz, n, m, radius_a * radius_a, nsample_a, radius_b * radius_b, nsample_b, idx_a, idx_b, cnt_a, cnt_b);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------
 // group points, the reference ABI: points (b,c,n), idx (b,np,ns) -> out (b,c,np,ns)  (group_points_gpu.cu:13-33)
 // ------------------------------------------------------------------------------------------

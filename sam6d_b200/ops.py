@@ -90,6 +90,22 @@ def ball_query(new_xyz: Tensor, xyz: Tensor, radius: float, nsample: int, return
     return (idx, cnt) if return_count else idx
 
 
+def ball_query_pair(new_xyz: Tensor, xyz: Tensor, ra: float, nsa: int, rb: float, nsb: int):
+    """two concentric ball queries (ra <= rb) in one sweep -> (idx_a, cnt_a, idx_b, cnt_b)"""
+    _check(new_xyz, torch.float32, "new_xyz", 3)
+    _check(xyz, torch.float32, "xyz", 3)
+    b, m, _ = new_xyz.shape
+    n = xyz.shape[1]
+    dev = xyz.device
+    ia = torch.empty(b, m, nsa, dtype=torch.int32, device=dev)
+    ib = torch.empty(b, m, nsb, dtype=torch.int32, device=dev)
+    ca = torch.empty(b, m, dtype=torch.int32, device=dev)
+    cb = torch.empty(b, m, dtype=torch.int32, device=dev)
+    _lib.call("sam6d_ball_query_pair", _p(new_xyz), _p(xyz), b, n, m, _f(ra), int(nsa), _f(rb), int(nsb), _p(ia), _p(ib), _p(ca),
+              _p(cb), _s())
+    return ia, ca, ib, cb
+
+
 def group_points(points: Tensor, idx: Tensor) -> Tensor:
     """_ext.group_points: (B,C,N) f32, (B,np,ns) i32 -> (B,C,np,ns)."""
     _check(points, torch.float32, "points", 3)
@@ -479,18 +495,26 @@ def pe_mlp_max_tc(pts: Tensor, idx: Tensor, weights, out: Tensor, out_off: int):
 
 
 def fine_assign(A: Tensor, pts2: Tensor, shift: float):
-    """A: (B,S,S) fp32, contiguous or a [:, :, :S] view of a (B,S,ld) allocation (padded rows for aligned stores)"""
-    if A.dim() != 3 or A.dtype != torch.float32 or not A.is_cuda or A.stride(2) != 1 or A.stride(0) != A.shape[1] * A.stride(1):
-        raise RuntimeError("atten must be a CUDA fp32 (B,S,S) tensor with dense rows")
+    """A: (B,S,S) fp32 as a [:, :, :S] view of a (B,S,ld) allocation with ld % 4 == 0 (the layout compute_feature_similarity
+    writes: every row starts on a 16-byte boundary); a contiguous (B,S,S) tensor is re-laid out once."""
+    if A.dim() != 3 or A.dtype != torch.float32 or not A.is_cuda:
+        raise RuntimeError("atten must be a CUDA fp32 (B,S,S) tensor")
     _check(pts2, torch.float32, "pts2", 3)
     B, S, _ = A.shape
+    if A.stride(2) != 1 or A.stride(0) != S * A.stride(1) or A.stride(1) % 4 or A.data_ptr() % 16:
+        ld = (S + 3) // 4 * 4
+        store = torch.empty(B, S, ld, dtype=torch.float32, device=A.device)
+        store[:, :, :S] = A
+        A = store[:, :, :S]
     ld = A.stride(1)
     dev = A.device
     tiles = (S + 31) // 32
-    rsum = torch.empty(B, S, dtype=torch.float32, device=dev)
-    csum = torch.empty(B, S, dtype=torch.float32, device=dev)
-    cpart = torch.empty(B, tiles, S, dtype=torch.float32, device=dev)
-    cpi = torch.empty(B, tiles, S, dtype=torch.int32, device=dev)
+    if tiles < 4:
+        raise RuntimeError("fine_assign: S >= 97 required")
+    rsum = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    csum = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    cpart = torch.empty(B, tiles, ld, dtype=torch.float32, device=dev)
+    cpi = torch.empty(B, tiles, ld, dtype=torch.int32, device=dev)
     lab1 = torch.zeros(B, S, dtype=torch.int32, device=dev)
     lab2 = torch.zeros(B, S, dtype=torch.int32, device=dev)
     wts = torch.empty(B, S - 1, dtype=torch.float32, device=dev)

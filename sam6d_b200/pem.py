@@ -544,8 +544,12 @@ class PositionalEncoding(nn.Module):
         pts = pts.contiguous()
         B, N, _ = pts.shape
         feat = torch.empty(B, N, 256, dtype=torch.float32, device=pts.device)
+        pair = ops.ball_query_pair(pts, pts, self.r1, self.ns1, self.r2, self.ns2) if self.r1 <= self.r2 else None
         for r, ns, name, off in ((self.r1, self.ns1, "m1", 0), (self.r2, self.ns2, "m2", 128)):
-            idx, cnt = ops.ball_query(pts, pts, r, ns, return_count=True)
+            if pair is not None:
+                idx, cnt = pair[:2] if off == 0 else pair[2:]
+            else:
+                idx, cnt = ops.ball_query(pts, pts, r, ns, return_count=True)
             if self.precision == "bf16":
                 ops.pe_mlp_max_tc(pts, idx, w[name + "_tc"], feat, off)
             else:

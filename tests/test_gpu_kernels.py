@@ -79,6 +79,14 @@ def test_ball_query_exact(ops, n, r, ns):
     assert ops.ball_query(far.cuda(), x.cuda(), r, ns).abs().sum().item() == 0
 
 
+def test_ball_query_pair_matches_two_queries(ops):
+    xyz = (torch.rand(3, 2048, 3, generator=G(5)) - 0.5).cuda()
+    ia, ca, ib, cb = ops.ball_query_pair(xyz, xyz, 0.1, 32, 0.2, 64)
+    ra, rca = ops.ball_query(xyz, xyz, 0.1, 32, return_count=True)
+    rb, rcb = ops.ball_query(xyz, xyz, 0.2, 64, return_count=True)
+    assert torch.equal(ia, ra) and torch.equal(ca, rca) and torch.equal(ib, rb) and torch.equal(cb, rcb)
+
+
 def test_native_layer_argument_errors(ops):
     x = torch.randn(1, 64, 3)
     with pytest.raises(RuntimeError):
