@@ -178,6 +178,13 @@ int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const flo
 int sam6d_attn_relpos(const float* qkv, long long tok_ld, int nW, int Hs, int Ws, int nH, int head_dim, const float* rel_h,
                       const float* rel_w, float scale, void* out, int out_is_bf16, long long out_ld, void* stream);
 
+/* Global-attention blocks (64 x 64 token grid, 4096 keys, head_dim 80) on tcgen05 with an online softmax: qkv bf16
+ * (B*4096, ld) rows [q|k|v]; Vt = V^T per (image, head) from sam6d_transpose_tokens_bf16 (B*H*80 rows, vt_ld >= 4096);
+ * rel_blob = rel_pos_h, rel_pos_w ((127,80) each) packed as bf16 UMMA slabs of 128 rows (ops.pack_rel_pos(.., slab_rows=128));
+ * out (B*4096, H*80) fp32 / bf16.  image_encoder.py:224-240 (attention), 325-361 (add_decomposed_rel_pos). */
+int sam6d_attn_global_tc(const void* qkv, long long ld, const void* Vt, long long vt_ld, const void* rel_blob, int B, int H, int grid,
+                         float scale, void* out, int out_is_bf16, long long out_ld, void* stream);
+
 /* ---- ISM template scoring (ISM/model/loss.py:21-44, ISM/model/detector.py:198-207,260-296) ------------------------ */
 int sam6d_template_score(const float* Qn, const float* Rn, int P, int O, int T, int C, float* sim_out, float* obj_score,
                          int* best_obj, float* best_score, int* best_tmpl, void* stream);

@@ -29,13 +29,30 @@ struct ident { using type = T; };   // keeps RT out of template argument deducti
 __device__ __forceinline__ float ld_res(const float* p) { return *p; }
 __device__ __forceinline__ float ld_res(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
-// RT: residual element type (fp32, or bf16 for the all-bf16 activation flow).
+template <typename OT, typename RT, bool HAS_RES>
+__device__ __forceinline__ bool chunk_vec_ok(int col0, int N, long long ldc, long long ldr) {
+  return (col0 + 32 <= N) && ((ldc & (sizeof(OT) == 4 ? 3 : 7)) == 0) && (!HAS_RES || (ldr & (sizeof(RT) == 4 ? 3 : 7)) == 0);
+}
+
+// bf16 residual tile of one 32 x 32 chunk in its coalesced register layout: lane l holds 16 B of row (i*8 + l/4), piece l%4.
+// Issued before the accumulator is ready, the loads overlap the tile's TMA and MMA time instead of stalling every chunk.
+__device__ __forceinline__ void prefetch_res_bf16(const __nv_bfloat16* __restrict__ R, long long ldr, int row0, int M, int col0, int lane,
+                                                  uint4 pre[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2), q = lane & 3;
+    pre[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (row0 + r < M) pre[i] = *reinterpret_cast<const uint4*>(R + (size_t)(row0 + r) * ldr + col0 + q * 8);
+  }
+}
+
+// RT: residual element type (fp32, or bf16 for the all-bf16 activation flow).  pre: the chunk's residual from
+// prefetch_res_bf16 (bf16 residual, vector path only) or nullptr.
 template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, typename RT = float>
 __device__ __forceinline__ void process_chunk(float v[32], float* stage, int lane, int row0, int M, int col0, int N, float alpha,
                                               const float* __restrict__ bias, const typename ident<RT>::type* __restrict__ R, long long ldr,
-                                              OT* __restrict__ C, long long ldc) {
-  const bool full = (col0 + 32 <= N);
-  const bool vec_ok = full && ((ldc & (sizeof(OT) == 4 ? 3 : 7)) == 0) && (!HAS_RES || (ldr & (sizeof(RT) == 4 ? 3 : 7)) == 0);
+                                              OT* __restrict__ C, long long ldc, const uint4* pre = nullptr) {
+  const bool vec_ok = chunk_vec_ok<OT, RT, HAS_RES>(col0, N, ldc, ldr);
   if (vec_ok) {
     if constexpr (HAS_RES && sizeof(RT) == 2) {
       // bf16 residual tile: a row of the chunk is 64 bytes; lane l reads 16 B of row (i*8 + l/4), piece l%4
@@ -43,7 +60,8 @@ __device__ __forceinline__ void process_chunk(float v[32], float* stage, int lan
       for (int i = 0; i < 4; ++i) {
         const int r = i * 8 + (lane >> 2), q = lane & 3;
         uint4 t = make_uint4(0u, 0u, 0u, 0u);
-        if (row0 + r < M) t = *reinterpret_cast<const uint4*>(R + (size_t)(row0 + r) * ldr + col0 + q * 8);
+        if (pre) t = pre[i];
+        else if (row0 + r < M) t = *reinterpret_cast<const uint4*>(R + (size_t)(row0 + r) * ldr + col0 + q * 8);
         *reinterpret_cast<uint4*>(stage + r * TILE_LD + q * 4) = t;
       }
       __syncwarp();

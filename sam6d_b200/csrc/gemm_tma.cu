@@ -113,17 +113,46 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
       const int m0 = (int)(tile % m_tiles) * BM, n0 = (int)(tile / m_tiles) * BN;
+      constexpr bool PRE = HAS_RES && (sizeof(OT) == 2) && (EW == 8);   // short-K tiles with a bf16 residual stream
+      uint4 pre[PRE ? 4 : 1][4];
+      if constexpr (PRE) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int col0 = n0 + (c_lo + cc) * 32;
+          if (epi::chunk_vec_ok<OT, OT, true>(col0, g.N, g.ldc, g.ldr))
+            epi::prefetch_res_bf16(reinterpret_cast<const __nv_bfloat16*>(g.R), g.ldr, m0 + quad * 32, g.M, col0, lane, pre[cc]);
+        }
+      }
       tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      if constexpr (PRE) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = c_lo + cc, col0 = n0 + c * 32;
+          if (col0 < g.N) {
+            float v[32];
+            tc::tmem_ld32(t_addr + c * 32, v);
+            if (epi::chunk_vec_ok<OT, OT, true>(col0, g.N, g.ldc, g.ldr))   // two call sites: `pre` stays in registers
+              epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
+                                                                 reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C),
+                                                                 g.ldc, pre[cc]);
+            else
+              epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
+                                                                 reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C),
+                                                                 g.ldc);
+          }
+        }
+      } else {
 #pragma unroll 1
-      for (int c = c_lo; c < c_hi; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= g.N) break;
-        float v[32];
-        tc::tmem_ld32(t_addr + c * 32, v);
-        epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
-                                                           reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C), g.ldc);
+        for (int c = c_lo; c < c_hi; ++c) {
+          const int col0 = n0 + c * 32;
+          if (col0 >= g.N) break;
+          float v[32];
+          tc::tmem_ld32(t_addr + c * 32, v);
+          epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
+                                                             reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C), g.ldc);
+        }
       }
       tc::tc_fence_before_sync();
       tc::mbar_arrive(&tmem_empty_bar[acc]);

@@ -341,20 +341,36 @@ def mha_raw(q_ptr, q_ld, q_bs, k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, bias: Optio
               ctypes.c_void_p(o_ptr), _ll(o_ld), _ll(o_bs), _s())
 
 
-def pack_rel_pos(rel_h: Tensor, rel_w: Tensor) -> Tensor:
-    """rel_pos_h / rel_pos_w ((2S-1, D) fp32, S <= 16) -> the bf16 image attn_tc bulk-copies into shared memory: for each table
-    ceil(D/64) slabs of [32 rows][64 channels], K-major with the 128-byte swizzle (16-byte chunk index XOR (row % 8))."""
+def pack_rel_pos(rel_h: Tensor, rel_w: Tensor, slab_rows: int = 32) -> Tensor:
+    """rel_pos_h / rel_pos_w ((2S-1, D) fp32) -> the bf16 image the attention kernels bulk-copy into shared memory: for each
+    table ceil(D/64) slabs of [slab_rows rows][64 channels], K-major with the 128-byte swizzle (16-byte chunk index XOR
+    (row % 8)).  slab_rows = 32 for the 14 x 14 windows, 128 for the 64 x 64 global grid."""
     D = rel_h.shape[1]
     DS = (D + 63) // 64
-    blob = torch.zeros(2 * DS * 32 * 64, dtype=torch.bfloat16, device=rel_h.device)
-    j = torch.arange(32, device=rel_h.device).view(32, 1)
+    if rel_h.shape[0] > slab_rows or rel_w.shape[0] > slab_rows:
+        raise RuntimeError("pack_rel_pos: table has more rows than the slab")
+    blob = torch.zeros(2 * DS * slab_rows * 64, dtype=torch.bfloat16, device=rel_h.device)
+    j = torch.arange(slab_rows, device=rel_h.device).view(slab_rows, 1)
     c = torch.arange(D, device=rel_h.device).view(1, D)
     off = j * 64 + ((((c % 64) // 8) ^ (j % 8)) * 8) + (c % 8)                     # element offset inside a slab
     for t, tab in enumerate((rel_h, rel_w)):
         n = tab.shape[0]
-        idx = ((t * DS + c // 64) * 32 * 64 + off)[:n]
+        idx = ((t * DS + c // 64) * slab_rows * 64 + off)[:n]
         blob[idx.reshape(-1)] = tab.to(torch.bfloat16).reshape(-1)
     return blob
+
+
+def attn_global_tc(qkv: Tensor, vt: Tensor, rel_blob: Tensor, B: int, H: int, grid: int, scale: float, out_dtype=torch.bfloat16) -> Tensor:
+    """SAM global attention (grid x grid = 4096 tokens, head_dim 80) on tcgen05: qkv (B*L, 3*H*80) bf16, vt from
+    transpose_tokens, rel_blob from pack_rel_pos(rel_h, rel_w, slab_rows=128) -> (B*L, H*80)"""
+    _check(qkv, torch.bfloat16, "qkv", 2)
+    _check(vt, torch.bfloat16, "vt", 2)
+    _check(rel_blob, torch.bfloat16, "rel_blob", 1)
+    L = grid * grid
+    out = torch.empty(B * L, H * 80, dtype=out_dtype, device=qkv.device)
+    _lib.call("sam6d_attn_global_tc", _p(qkv), _ll(qkv.shape[1]), _p(vt), _ll(vt.shape[1]), _p(rel_blob), int(B), int(H), int(grid),
+              _f(scale), _p(out), int(out_dtype == torch.bfloat16), _ll(H * 80), _s())
+    return out
 
 
 def attn_tc(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, Vt: Tensor, B: int, H: int, Sq: int, Sk: int, D: int, scale: float,

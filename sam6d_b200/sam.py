@@ -119,8 +119,9 @@ class ImageEncoderViT(nn.Module):
                     n1w=_f32(blk.norm1.weight), n1b=_f32(blk.norm1.bias), eps1=blk.norm1.eps,
                     qkv=_W(blk.attn.qkv.weight), qkv_b=_f32(blk.attn.qkv.bias), proj=_W(blk.attn.proj.weight),
                     proj_b=_f32(blk.attn.proj.bias), rh=_f32(blk.attn.rel_pos_h), rw=_f32(blk.attn.rel_pos_w),
-                    rel_blob=(ops.pack_rel_pos(_f32(blk.attn.rel_pos_h), _f32(blk.attn.rel_pos_w))
-                              if blk.attn.rel_pos_h.shape[0] <= 31 and blk.attn.rel_pos_h.is_cuda else None),
+                    rel_blob=(ops.pack_rel_pos(_f32(blk.attn.rel_pos_h), _f32(blk.attn.rel_pos_w),
+                                               slab_rows=32 if blk.attn.rel_pos_h.shape[0] <= 32 else 128)
+                              if blk.attn.rel_pos_h.shape[0] <= 128 and blk.attn.rel_pos_h.is_cuda else None),
                     n2w=_f32(blk.norm2.weight), n2b=_f32(blk.norm2.bias), eps2=blk.norm2.eps,
                     l1=_W(blk.mlp.lin1.weight), l1b=_f32(blk.mlp.lin1.bias), l2=_W(blk.mlp.lin2.weight), l2b=_f32(blk.mlp.lin2.bias)))
             oc = self.neck[0].out_channels
@@ -228,8 +229,13 @@ def _block_bf16(self, blk, bw, tok, B, L, C, G, maps):
         vt = ops.transpose_tokens(qkv, 2 * C, C, nW, Hs * Hs)
         att = ops.attn_tc(qkv, 0, qkv, C, vt, nW, self.num_heads, Hs * Hs, Hs * Hs, C // self.num_heads, blk.attn.scale,
                           rel=(bw["rel_blob"], Hs, Hs), out_dtype=torch.bfloat16)
+    elif Hs == 64 and C // self.num_heads == 80 and bw["rel_blob"] is not None:
+        # global blocks of the 64 x 64 grid (4096 keys): tcgen05 attention with an online softmax, scores never leave TMEM
+        qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"], out_dtype=torch.bfloat16)
+        vt = ops.transpose_tokens(qkv, 2 * C, C, nW, Hs * Hs)
+        att = ops.attn_global_tc(qkv, vt, bw["rel_blob"], nW, self.num_heads, Hs, blk.attn.scale)
     else:
-        # global blocks (4096 keys): flash-style CUDA-core kernel with online softmax
+        # other grids: flash-style CUDA-core kernel with online softmax
         qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"])
         att = ops.attn_relpos(qkv, nW, Hs, Hs, self.num_heads, bw["rh"], bw["rw"], blk.attn.scale, out_dtype=torch.bfloat16)
     if blk.window_size > 0:

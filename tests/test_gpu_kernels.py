@@ -586,3 +586,32 @@ def test_attn_tc_sam_window(ops):
                       rel=(ops.pack_rel_pos(rel_h.cuda(), rel_w.cuda()), S, S)).cpu()
     torch.testing.assert_close(got, ref, atol=2e-2, rtol=2e-2)
     assert (got - ref).abs().mean().item() < 3e-3
+
+
+def test_attn_global_tensor_core(ops):
+    """SAM global attention (64 x 64 tokens, online softmax on tcgen05) against the reference formula
+    (image_encoder.py:224-240, 325-361) evaluated in fp32 on the same bf16-rounded q, k, v."""
+    from oracle import sam_oracle as so
+    B, S, H, D = 2, 64, 2, 80
+    L = S * S
+    g = G(78)
+    qkv = (torch.randn(B * L, 3 * H * D, generator=g) * 1.5).bfloat16()
+    rel_h = torch.randn(2 * S - 1, D, generator=g) * 0.2
+    rel_w = torch.randn(2 * S - 1, D, generator=g) * 0.2
+    x = qkv.float().cuda().view(B, L, 3, H, D).permute(2, 0, 3, 1, 4).reshape(3, B * H, L, D)
+    q, k, v = x.unbind(0)
+    attn = (q * D ** -0.5) @ k.transpose(-2, -1)
+    Rh, Rw = so.rel_pos_table(S, rel_h).cuda(), so.rel_pos_table(S, rel_w).cuda()
+    rq = q.reshape(B * H, S, S, D)
+    attn = (attn.view(-1, S, S, S, S) + torch.einsum("bhwc,hkc->bhwk", rq, Rh)[:, :, :, :, None] +
+            torch.einsum("bhwc,wkc->bhwk", rq, Rw)[:, :, :, None, :]).view(-1, L, L).softmax(dim=-1)
+    ref = (attn @ v).view(B, H, L, D).permute(0, 2, 1, 3).reshape(B * L, H * D).cpu()
+    qd = qkv.cuda()
+    vt = ops.transpose_tokens(qd, 2 * H * D, H * D, B, L)
+    blob = ops.pack_rel_pos(rel_h.cuda(), rel_w.cuda(), slab_rows=128)
+    # bf16 P and bf16 rel-pos tables (|q . rel| ~ 3 here): worst-case logit error ~1e-2 -> output error of a few 1e-2 on a
+    # handful of peaked rows, mean error an order of magnitude lower
+    for odt in (torch.float32, torch.bfloat16):
+        got = ops.attn_global_tc(qd, vt, blob, B, H, S, D ** -0.5, out_dtype=odt).cpu().float()
+        torch.testing.assert_close(got, ref, atol=6e-2, rtol=2e-2)
+        assert (got - ref).abs().mean().item() < 3e-3

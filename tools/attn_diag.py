@@ -29,3 +29,11 @@ print("sam win no bias %8.1f us" % timeit(lambda: ops.attn_tc(qkv2, 0, qkv2, H2 
 print("sam win rel-pos %8.1f us" % timeit(lambda: ops.attn_tc(qkv2, 0, qkv2, H2 * D2, vt2, nW, H2, L, L, D2, 0.11, rel=(blob, 14, 14), out_dtype=torch.bfloat16), n=3))
 qf = qkv2.float()
 print("sam win simt    %8.1f us" % timeit(lambda: ops.attn_relpos(qf, nW, 14, 14, H2, rh, rw, 0.11, out_dtype=torch.bfloat16), n=3))
+# SAM global attention shape: 16 images x 16 heads x 4096 tokens
+Bg, Hg, Sg, Dg = 16, 16, 64, 80
+qkvg = torch.randn(Bg * Sg * Sg, 3 * Hg * Dg, device="cuda").bfloat16()
+vtg = ops.transpose_tokens(qkvg, 2 * Hg * Dg, Hg * Dg, Bg, Sg * Sg)
+rhg = torch.randn(127, 80, device="cuda") * 0.1; rwg = torch.randn(127, 80, device="cuda") * 0.1
+blobg = ops.pack_rel_pos(rhg, rwg, slab_rows=128)
+t = timeit(lambda: ops.attn_global_tc(qkvg, vtg, blobg, Bg, Hg, Sg, 0.11), n=3)
+print("sam global tc   %8.1f us  (%.1f TFLOP/s)" % (t, 4.0 * Bg * Hg * 4096 * 4096 * 80 / t / 1e6))
