@@ -212,51 +212,71 @@ __global__ void __launch_bounds__(1024) topk_smallest_kernel(const float* __rest
 }
 
 // ---- 5. pose selection ----------------------------------------------------------------------------------------
-// grid = (n2, B); 256 threads cover the n points of pts1 (n <= 256*PS_PPT); model points staged in smem.
-__global__ void __launch_bounds__(256) coarse_select_kernel(const float* __restrict__ Rt, const int* __restrict__ top, int n1, int n2,
-                                                            const float* __restrict__ pts1, const float* __restrict__ w1, int n,
-                                                            const float* __restrict__ model, int nm, float* __restrict__ scores) {
-  extern __shared__ float sm[];   // model: nm*3 + nm (x,y,z,|m|^2 as SoA)
-  float* mx = sm; float* my = mx + nm; float* mz = my + nm; float* m2 = mz + nm;
-  __shared__ float red[2][8];
-  const int pose = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < nm; i += 256) {
+// grid = (ceil(n2 / SEL_PP), B); a thread owns one point of pts1 under SEL_PP hypotheses; the CAD samples sit in shared memory as
+// (x, y, z, |m|^2) quadruples, so the inner loop is one 16-byte broadcast load and 4 instructions per (hypothesis, point, sample):
+// min_m (|x|^2 - 2 x.m + |m|^2) = |x|^2 + min_m (|m|^2 - 2 x.m), the clamp at 0 commutes with the minimum
+// (pairwise_distance, model_utils.py:98-111).
+constexpr int SEL_PP = 4, SEL_THREADS = 224;
+__global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const float* __restrict__ Rt, const int* __restrict__ top, int n1,
+                                                                    int n2, const float* __restrict__ pts1, const float* __restrict__ w1,
+                                                                    int n, const float* __restrict__ model, int nm,
+                                                                    float* __restrict__ scores) {
+  extern __shared__ float4 smq[];   // nm quadruples
+  __shared__ float red[2 * SEL_PP][SEL_THREADS / 32];
+  __shared__ float rts[SEL_PP][12];
+  const int pose0 = blockIdx.x * SEL_PP, b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < nm; i += SEL_THREADS) {
     const float* q = model + ((size_t)b * nm + i) * 3;
-    float x = q[0], y = q[1], z = q[2];
-    mx[i] = x; my[i] = y; mz[i] = z; m2[i] = x * x + y * y + z * z;
+    const float x = q[0], y = q[1], z = q[2];
+    smq[i] = make_float4(x, y, z, x * x + y * y + z * z);
   }
-  const float* rt = Rt + ((size_t)b * n1 + top[(size_t)b * n2 + pose]) * 12;
-  float R[9], t[3];
+  if (tid < SEL_PP * 12) {
+    const int pp = tid / 12, e = tid - pp * 12;
+    const int pose = min(pose0 + pp, n2 - 1);
+    rts[pp][e] = Rt[((size_t)b * n1 + top[(size_t)b * n2 + pose]) * 12 + e];
+  }
+  __syncthreads();
+  float num = 0.f, den[SEL_PP];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = rt[i];
-  t[0] = rt[9]; t[1] = rt[10]; t[2] = rt[11];
-  __syncthreads();
-  float num = 0.f, den = 0.f;
-  for (int i = tid; i < n; i += 256) {
+  for (int pp = 0; pp < SEL_PP; ++pp) den[pp] = 0.f;
+  for (int i = tid; i < n; i += SEL_THREADS) {
     const float* p = pts1 + ((size_t)b * n + i) * 3;
-    float x = p[0] - t[0], y = p[1] - t[1], z = p[2] - t[2];
-    float tx = x * R[0] + y * R[3] + z * R[6];
-    float ty = x * R[1] + y * R[4] + z * R[7];
-    float tz = x * R[2] + y * R[5] + z * R[8];
-    float x2 = tx * tx + ty * ty + tz * tz;
-    float best = INFINITY;
-    for (int m = 0; m < nm; ++m) {
-      // pairwise_distance: x2 - 2 xy + y2, clamp at 0 (model_utils.py:98-111)
-      float xy = tx * mx[m] + ty * my[m] + tz * mz[m];
-      float d = fmaxf(x2 - 2.f * xy + m2[m], 0.f);
-      best = fminf(best, d);
+    const float px = p[0], py = p[1], pz = p[2];
+    float ax[SEL_PP], ay[SEL_PP], az[SEL_PP], x2[SEL_PP], best[SEL_PP];
+#pragma unroll
+    for (int pp = 0; pp < SEL_PP; ++pp) {
+      const float* R = rts[pp];
+      const float x = px - R[9], y = py - R[10], z = pz - R[11];
+      const float tx = x * R[0] + y * R[3] + z * R[6];
+      const float ty = x * R[1] + y * R[4] + z * R[7];
+      const float tz = x * R[2] + y * R[5] + z * R[8];
+      x2[pp] = tx * tx + ty * ty + tz * tz;
+      ax[pp] = -2.f * tx; ay[pp] = -2.f * ty; az[pp] = -2.f * tz;
+      best[pp] = INFINITY;
     }
-    float wi = w1[(size_t)b * n + i];
+#pragma unroll 4
+    for (int m = 0; m < nm; ++m) {
+      const float4 q = smq[m];
+#pragma unroll
+      for (int pp = 0; pp < SEL_PP; ++pp) best[pp] = fminf(best[pp], fmaf(ax[pp], q.x, fmaf(ay[pp], q.y, fmaf(az[pp], q.z, q.w))));
+    }
+    const float wi = w1[(size_t)b * n + i];
     num += wi;
-    den += sqrtf(best) * wi;
+#pragma unroll
+    for (int pp = 0; pp < SEL_PP; ++pp) den[pp] += sqrtf(fmaxf(x2[pp] + best[pp], 0.f)) * wi;
   }
-  num = warp_sum(num); den = warp_sum(den);
-  if ((tid & 31) == 0) { red[0][tid >> 5] = num; red[1][tid >> 5] = den; }
+  num = warp_sum(num);
+#pragma unroll
+  for (int pp = 0; pp < SEL_PP; ++pp) den[pp] = warp_sum(den[pp]);
+  if ((tid & 31) == 0) {
+#pragma unroll
+    for (int pp = 0; pp < SEL_PP; ++pp) { red[pp][tid >> 5] = num; red[SEL_PP + pp][tid >> 5] = den[pp]; }
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < SEL_PP && pose0 + tid < n2) {
     float a = 0.f, c = 0.f;
-    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
-    scores[(size_t)b * n2 + pose] = a / (c + 1e-8f);
+    for (int w = 0; w < SEL_THREADS / 32; ++w) { a += red[tid][w]; c += red[SEL_PP + tid][w]; }
+    scores[(size_t)b * n2 + pose0 + tid] = a / (c + 1e-8f);
   }
 }
 
@@ -332,8 +352,8 @@ S6_API int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, i
   size_t smem = (size_t)nm * 4 * sizeof(float);
   S6_REQUIRE(smem <= 200 * 1024);
   S6_CHECK(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(n2, B);
-  coarse_select_kernel<<<grid, 256, smem, s6_stream(stream)>>>(Rt, top, n1, n2, pts1, w1, n, model, nm, scores);
+  dim3 grid(s6_cdiv(n2, SEL_PP), B);
+  coarse_select_kernel<<<grid, SEL_THREADS, smem, s6_stream(stream)>>>(Rt, top, n1, n2, pts1, w1, n, model, nm, scores);
   S6_LAUNCH_CHECK();
   coarse_pick_kernel<<<B, 32, 0, s6_stream(stream)>>>(scores, top, Rt, n1, n2, R, t);
   S6_LAUNCH_CHECK();

@@ -4,9 +4,10 @@
 // Per tile, in one CTA of 128 worker threads (thread <-> row) + 1 MMA warp:
 //   layer 1 (6 -> 32)   CUDA cores, fp32: x = [p_j - p_i, p_j]; h1 = relu(W1 x + b1) -> bf16 row of the A1 slab
 //   layer 2 (32 -> 64)  tcgen05.mma M128 N64 (2 x K16) into TMEM; workers read it back, + b2, ReLU, bf16 -> A2 slab
-//   layer 3 (64 -> 128) tcgen05.mma M128 N128 (4 x K16) into the same TMEM columns
-//   max-pool            tcgen05.ld + 31-shuffle transpose-reduce per 32-column chunk: lane c ends with max over the point's
-//                       rows of column c; + b3, ReLU (monotone, commutes with max); coalesced 128-byte stores
+//   layer 3 (64 -> 128) tcgen05.mma M128 N128 (4 x K16) with the operands swapped: D^T = W3 A2^T, so a TMEM lane is an output
+//                       channel and the columns are the tile's rows (both slabs are K-major, either can be the A operand)
+//   max-pool            thread = channel: the samples of a point are 32 / 64 adjacent columns of its lane -> tcgen05.ld + a
+//                       register max, no shuffles; + b3, ReLU (monotone, commutes with max); a warp stores 32 adjacent channels
 // BatchNorm is folded into the 1x1 convs on the host.  The (B,6,N,ns) grouped tensor and the (B,128,N,ns) activations of the
 // reference are never materialised; padded duplicate samples are simply recomputed (they cannot change a max).
 // Four CTAs share an SM (56 KB smem, 128 TMEM columns each), so one tile's serial chain hides behind the others'.
@@ -38,7 +39,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
   uint8_t* w3s = w2s + W2_SLAB;
   __shared__ __align__(16) float w1s[32 * 8];
   __shared__ float b1s[32], b2s[64], b3s[128];
-  __shared__ float red[2][32];
   __shared__ __align__(8) uint64_t a1_full, d2_full, a2_full, d3_full;
   __shared__ uint32_t tmem_slot;
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
         tc::tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          tc::umma_bf16(tmem_base, tc::umma_desc_sw128(a2_addr + k * 32), tc::umma_desc_sw128(w3_addr + k * 32), idesc3, k ? 1u : 0u);
+          tc::umma_bf16(tmem_base, tc::umma_desc_sw128(w3_addr + k * 32), tc::umma_desc_sw128(a2_addr + k * 32), idesc3, k ? 1u : 0u);
         tc::umma_commit(&d3_full);
       }
     }
@@ -159,40 +159,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a2_full);
       }
-      // ---- layer 3 epilogue: max over the rows of each point
+      // ---- layer 3 epilogue: this thread is output channel `tid`; columns [32 c, 32 c + 32) are rows of the tile
       tc::mbar_wait(&d3_full, ph);
       tc::tc_fence_after_sync();
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tc::tmem_ld32(t_addr + c * 32, v);
-        if (!valid) {
+      {
+        const float bias = b3s[tid];
+        float m = -INFINITY;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
-        }
-        // transpose-reduce: after the 5 steps lane l holds max over the warp's 32 rows of column l
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tc::tmem_ld32(t_addr + c * 32, v);
 #pragma unroll
-        for (int step = 0; step < 5; ++step) {
-          const int o = 16 >> step, half = 16 >> step;
-          const bool up = (lane & o) != 0;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (i < half) {
-              float keep = up ? v[i + half] : v[i], send = up ? v[i] : v[i + half];
-              v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
-            }
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
+          if (NS == 32 || (c & 1)) {                                // a point's samples are complete
+            const long long p_out = tile * PPT + (NS == 32 ? c : (c >> 1));
+            if (p_out < total_points) out[p_out * out_ld + out_off + tid] = fmaxf(m + bias, 0.f);
+            m = -INFINITY;
           }
         }
-        float m = v[0];
-        if (NS == 64) {
-          if (warp & 1) red[warp >> 1][lane] = m;
-          worker_bar();
-          if (!(warp & 1)) m = fmaxf(m, red[warp >> 1][lane]);
-          worker_bar();
-        }
-        const long long p_out = tile * PPT + (NS == 64 ? (warp >> 1) : warp);
-        if ((NS == 32 || !(warp & 1)) && p_out < total_points)
-          out[p_out * out_ld + out_off + c * 32 + lane] = fmaxf(m + b3s[c * 32 + lane], 0.f);
       }
       tc::tc_fence_before_sync();
     }
