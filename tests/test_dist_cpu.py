@@ -61,3 +61,40 @@ def test_all_gather_poses_world2_even_and_ragged():
         for p in procs:
             p.join(timeout=60)
         assert res == [(0, True), (1, True)]
+
+
+def _oracle_local_best(desc, refs):
+    """the CPU oracle as the per-shard scorer (the product path uses the CUDA kernel)"""
+    from oracle import ism_oracle as io
+    _, _, _, _, scores, per_obj = io.compute_semantic_score(desc, refs, confidence_thresh=-1.0)
+    score, obj = per_obj.max(dim=1)
+    tmpl = scores.argmax(dim=-1).gather(1, obj[:, None])[:, 0]
+    return obj, score, tmpl
+
+
+def _score_worker(rank, world, port, O, q):
+    from oracle import ism_oracle as io
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    desc, refs = io.make_descriptors(P=24, O=O, T=42, C=64, seed=5)[:2]
+    lo, hi = sdist.shard_range(O, rank, world)
+    got = sdist.sharded_semantic_score(desc, refs[lo:hi], lo, confidence_thresh=0.2, local_best=_oracle_local_best)
+    ref = io.compute_semantic_score(desc, refs, confidence_thresh=0.2)[:4]
+    q.put((rank, all(bool(torch.equal(a, b)) for a, b in zip(got, ref))))
+    dist.destroy_process_group()
+
+
+def test_object_sharded_template_scoring_world2():
+    """reference descriptors sharded by object, 12 bytes per proposal exchanged, identical
+    (idx_selected, object, score, best_template) on every rank -- including a rank that owns no object."""
+    ctx = mp.get_context("spawn")
+    for O in (7, 1):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_score_worker, args=(r, 2, port, O, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=120) for _ in range(2))
+        for p in procs:
+            p.join(timeout=60)
+        assert res == [(0, True), (1, True)]

@@ -71,3 +71,14 @@ def test_image_encoder_batch_and_independence():
     one = enc(img[1:2].contiguous())
     torch.testing.assert_close(both[1:2], one, atol=1e-5, rtol=1e-5)
     assert torch.isfinite(both).all()
+
+
+def test_sharded_semantic_score_single_rank_matches_oracle():
+    """dist.sharded_semantic_score with the CUDA scorer (world 1 = one shard holding every object)"""
+    from oracle import ism_oracle as io
+    from sam6d_b200 import dist as sdist
+    desc, refs = io.make_descriptors(P=40, O=6, T=42, C=256, seed=9)[:2]
+    got = sdist.sharded_semantic_score(desc.cuda(), refs.cuda(), 0, confidence_thresh=0.2)
+    ref = io.compute_semantic_score(desc, refs, confidence_thresh=0.2)[:4]
+    assert torch.equal(got[0].cpu(), ref[0]) and torch.equal(got[1].cpu(), ref[1]) and torch.equal(got[3].cpu(), ref[3])
+    torch.testing.assert_close(got[2].cpu(), ref[2], atol=1e-5, rtol=1e-5)
