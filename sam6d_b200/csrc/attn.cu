@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(256) rpe_scores_kernel(const ET* __restrict__ 
   const int row = blockIdx.x;  // b*S + n
   const int b = row / S, n = row - b * S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s6_pdl_trigger();
+  s6_pdl_wait();                 // U comes from the GEMM before us
   float u[4][8];
   const float* up = U + (size_t)row * u_ld + lane * 8;
 #pragma unroll
@@ -286,9 +288,10 @@ S6_API int sam6d_rpe_scores(const void* E, int e_is_bf16, const float* U, long l
   S6_REQUIRE(E && U && SP && B >= 0 && S > 0 && u_ld >= 1024 && (u_ld % 4) == 0);
   if (B == 0) return 0;
   if (e_is_bf16)
-    rpe_scores_kernel<__nv_bfloat16><<<B * S, 256, 0, s6_stream(stream)>>>((const __nv_bfloat16*)E, U, u_ld, S, SP);
+    S6_CHECK(s6_launch_pdl(rpe_scores_kernel<__nv_bfloat16>, dim3(B * S), dim3(256), 0, s6_stream(stream), (const __nv_bfloat16*)E, U,
+                           u_ld, S, SP));
   else
-    rpe_scores_kernel<float><<<B * S, 256, 0, s6_stream(stream)>>>((const float*)E, U, u_ld, S, SP);
+    S6_CHECK(s6_launch_pdl(rpe_scores_kernel<float>, dim3(B * S), dim3(256), 0, s6_stream(stream), (const float*)E, U, u_ld, S, SP));
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -72,11 +72,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     tc::mbar_init(&rel_ready, 128);
     tc::mbar_fence_init();
   }
+  s6_pdl_trigger();
   if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  s6_pdl_wait();                                   // Q / K / V^T / bias come from the kernels before us
 
   if (warp == 4) {
     if (lane == 0) {
@@ -303,7 +305,8 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   dim3 grid(s6_cdiv(a.Sq, QT), a.H, B);
-  kern<<<grid, NUM_THREADS, smem, st>>>(tq, tk, tv, a);
+  cudaError_t le = s6_launch_pdl(kern, grid, dim3(NUM_THREADS), smem, st, tq, tk, tv, a);
+  if (le != cudaSuccess) return (int)le;
   return (int)cudaGetLastError();
 }
 
@@ -313,6 +316,8 @@ __global__ void __launch_bounds__(256) transpose_tokens_kernel(const __nv_bfloat
   __shared__ __nv_bfloat16 tile[64][66];
   const int w = blockIdx.z, c0 = blockIdx.y * 64, l0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  s6_pdl_trigger();
+  s6_pdl_wait();
   for (int i = ty; i < 64; i += 4) {
     const int l = l0 + i, c = c0 + tx;
     tile[i][tx] = (l < L && c < C) ? src[((size_t)w * L + l) * ld + col0 + c] : __float2bfloat16(0.f);
@@ -331,8 +336,8 @@ S6_API int sam6d_transpose_tokens_bf16(const void* src, long long ld, int col0, 
   if (nB == 0) return 0;
   S6_REQUIRE(nB <= 65535);
   dim3 grid(s6_cdiv(N1, 64), s6_cdiv(C, 64), nB);
-  transpose_tokens_kernel<<<grid, 256, 0, s6_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), ld, col0, C, L, N1,
-                                                              reinterpret_cast<__nv_bfloat16*>(out));
+  S6_CHECK(s6_launch_pdl(transpose_tokens_kernel, grid, dim3(256), 0, s6_stream(stream), reinterpret_cast<const __nv_bfloat16*>(src), ld,
+                         col0, C, L, N1, reinterpret_cast<__nv_bfloat16*>(out)));
   S6_LAUNCH_CHECK();
   return 0;
 }

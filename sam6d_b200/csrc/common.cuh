@@ -28,6 +28,24 @@
 
 static inline cudaStream_t s6_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL).  A step is ~280 launches, many of them 10-us kernels on 12608 token rows: with the
+// launch attribute below the next grid is scheduled as soon as every CTA of the current one has started (s6_pdl_trigger at
+// the top of the kernel), runs its prologue (barrier init, TMEM allocation, descriptor prefetch) on free SMs and blocks in
+// s6_pdl_wait until the predecessor has completed and flushed.  Every kernel launched this way calls s6_pdl_wait before its
+// first global access that may depend on an earlier kernel; kernels launched the ordinary way are unaffected on either side.
+__device__ __forceinline__ void s6_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void s6_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t s6_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

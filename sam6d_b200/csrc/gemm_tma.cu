@@ -59,11 +59,13 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmW);
   }
+  s6_pdl_trigger();
   if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
   const uint32_t tmem_base = tmem_slot;
+  s6_pdl_wait();                                   // operands / residual may come from the kernel before us
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -220,7 +222,7 @@ S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const
   do {                                                                                                                 \
     auto k = gemm_tma_kernel<OT, ACT, HB, HR, ST, EWN>;                                                                \
     S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<ST, EWN>::kSmem));               \
-    k<<<grid, Cfg<ST, EWN>::kThreads, Cfg<ST, EWN>::kSmem, st>>>(tmA, tmW, g);                                         \
+    S6_CHECK(s6_launch_pdl(k, dim3(grid), dim3(Cfg<ST, EWN>::kThreads), Cfg<ST, EWN>::kSmem, st, tmA, tmW, g));        \
   } while (0)
 #define LAUNCH_TMA(ACT, HB, HR)                                                                                        \
   do {                                                                                                                 \

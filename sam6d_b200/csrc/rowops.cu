@@ -30,6 +30,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const IT* __restrict__ x
                                                         long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  s6_pdl_trigger();
+  s6_pdl_wait();
   if (r >= rows) return;
   const IT* xp = x + xv.off(r);
   OT* yp = y + yv.off(r);
@@ -148,6 +150,13 @@ __global__ void scale_by_radius_kernel(const float* __restrict__ src, const floa
     else if ((C) <= 1024) KERNEL<32 ROW_EXTRA> __VA_ARGS__;            \
     else KERNEL<64 ROW_EXTRA> __VA_ARGS__;                             \
   } while (0)
+// LayerNorm goes through the PDL launch (see common.cuh)
+#define LN_DISPATCH(C, IT, OT, ...)                                                                                          \
+  do {                                                                                                                       \
+    if ((C) <= 256) S6_CHECK(s6_launch_pdl(layernorm_kernel<8, OT, IT>, __VA_ARGS__));                                       \
+    else if ((C) <= 1024) S6_CHECK(s6_launch_pdl(layernorm_kernel<32, OT, IT>, __VA_ARGS__));                                \
+    else S6_CHECK(s6_launch_pdl(layernorm_kernel<64, OT, IT>, __VA_ARGS__));                                                 \
+  } while (0)
 
 #define ROW_EXTRA , float
 S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
@@ -155,8 +164,8 @@ S6_API int sam6d_layernorm(const float* x, long long x_rpb, long long x_bstride,
                            float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld}, y,
-               RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps));
+  LN_DISPATCH(C, float, float, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, RowView{x_rpb, x_bstride, x_ld}, y,
+              RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
   S6_LAUNCH_CHECK();
   return 0;
 }
@@ -169,8 +178,8 @@ S6_API int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bst
                                 float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld},
-               reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps));
+  LN_DISPATCH(C, float, __nv_bfloat16, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, RowView{x_rpb, x_bstride, x_ld},
+              reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
   S6_LAUNCH_CHECK();
   return 0;
 }
@@ -182,9 +191,9 @@ S6_API int sam6d_layernorm_bf16io(const void* x, long long x_rpb, long long x_bs
                                   float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
-  ROW_DISPATCH(C, layernorm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x),
-               RowView{x_rpb, x_bstride, x_ld}, reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta,
-               rows, C, eps));
+  LN_DISPATCH(C, __nv_bfloat16, __nv_bfloat16, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream),
+              reinterpret_cast<const __nv_bfloat16*>(x), RowView{x_rpb, x_bstride, x_ld}, reinterpret_cast<__nv_bfloat16*>(y),
+              RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
   S6_LAUNCH_CHECK();
   return 0;
 }
