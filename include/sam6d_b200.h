@@ -71,6 +71,11 @@ int sam6d_gemm_bf16(const void* A, int a_dtype, const void* W, int w_dtype, cons
  * 4-stage ring, two TMEM accumulators overlap epilogue and MMA.  A (M,K) bf16, W (N,K) bf16, C fp32 (0) / bf16 (1). */
 int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                    long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream);
+/* `batch` independent problems stacked along the rows of A and W (problem z: rows [z*a_rpb, +M) of A, [z*w_rpb, +N) of W,
+ * output at C + z*c_bs elements): the per-proposal cosine score matrices (PEM/utils/model_utils.py:114-136). */
+int sam6d_gemm_tma_batched(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
+                           long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb, long long w_rpb,
+                           long long c_bs, long long r_bs, float alpha, int act, void* stream);
 
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
 
@@ -89,6 +94,8 @@ int sam6d_layernorm_bf16io(const void* x, long long x_rpb, long long x_bstride, 
 /* F.normalize(x, p=2, dim=-1) (PEM/utils/model_utils.py:124-126; ISM/model/loss.py:32-33) */
 int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                       long long y_bstride, long long y_ld, long long rows, int C, void* stream);
+int sam6d_l2norm_rows_bf16(const float* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                           long long y_bstride, long long y_ld, long long rows, int C, void* stream);
 /* focused-linear-attention feature map (PEM/model/transformer.py:541-550); softplus_scale (C) = softplus(scale) */
 int sam6d_focus_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                      long long y_bstride, long long y_ld, const float* softplus_scale, long long rows, int C, void* stream);

@@ -35,7 +35,10 @@ __global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict_
   float racc[RT];
 #pragma unroll
   for (int r = 0; r < RT; ++r) racc[r] = 0.f;
-  for (int j = tid * 4; j < S; j += 1024) {
+  // S = 2049: the last 16-byte column group would be a third sweep with one active thread whose 32 serial loads the whole
+  // block then waits for.  Such a short tail (<= 4 columns past a multiple of 1024) is handled row-parallel instead.
+  const int tail = S & 1023, S_main = (tail != 0 && tail <= 4) ? S - tail : S;
+  for (int j = tid * 4; j < S_main; j += 1024) {
     float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < RT; ++r) {
@@ -47,6 +50,14 @@ __global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict_
     }
     *reinterpret_cast<float4*>(cpart + ((size_t)b * gridDim.x + tile) * ld + j) = c;
   }
+  float tail_row = 0.f;                                   // thread r < 32: row r of the tail columns
+  if (S_main < S && warp == 0) {
+    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane < rmax) e = exp4(__ldcs(reinterpret_cast<const float4*>(Ab + (size_t)lane * ld + S_main)), shift, S_main, S);
+    tail_row = (e.x + e.y) + (e.z + e.w);
+    const float4 c = make_float4(warp_sum(e.x), warp_sum(e.y), warp_sum(e.z), warp_sum(e.w));
+    if (lane == 0) *reinterpret_cast<float4*>(cpart + ((size_t)b * gridDim.x + tile) * ld + S_main) = c;
+  }
 #pragma unroll
   for (int r = 0; r < RT; ++r) {
     const float v = warp_sum(racc[r]);
@@ -54,7 +65,7 @@ __global__ void __launch_bounds__(256) fine_sums_kernel(const float* __restrict_
   }
   __syncthreads();
   if (tid < rmax) {
-    float s = 0.f;
+    float s = tail_row;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][tid];
     rinv[(size_t)b * ld + i0 + tid] = 1.f / s;
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __rest
   if (tid < RT) ri[tid] = (tid < rmax) ? rinv[(size_t)b * ld + i0 + tid] : 0.f;
   __syncthreads();
   const float* Ab = A + (size_t)b * S * ld + (size_t)i0 * ld;
-  for (int j = tid * 4; j < S; j += 1024) {
+  const int tail = S & 1023, S_main = (tail != 0 && tail <= 4) ? S - tail : S;    // see fine_sums_kernel
+  for (int j = tid * 4; j < S_main; j += 1024) {
     const float4 ci = *reinterpret_cast<const float4*>(cinv + (size_t)b * ld + j);
     float4 bv = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     int4 bi = make_int4(0, 0, 0, 0);
@@ -98,6 +110,27 @@ __global__ void __launch_bounds__(256) fine_collabels_kernel(const float* __rest
     }
     *reinterpret_cast<float4*>(cpv + ((size_t)b * gridDim.x + tile) * ld + j) = bv;
     *reinterpret_cast<int4*>(cpi + ((size_t)b * gridDim.x + tile) * ld + j) = bi;
+  }
+  if (S_main < S && tid < 32) {                            // tail columns: lane = row, warp argmax (smallest row on ties)
+    const int lane = tid;
+    const float4 ci = *reinterpret_cast<const float4*>(cinv + (size_t)b * ld + S_main);
+    float pv[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (lane < rmax) {
+      const float4 e = exp4(__ldcs(reinterpret_cast<const float4*>(Ab + (size_t)lane * ld + S_main)), shift, S_main, S);
+      const float rr = ri[lane];
+      pv[0] = (e.x * rr) * (e.x * ci.x); pv[1] = (e.y * rr) * (e.y * ci.y); pv[2] = (e.z * rr) * (e.z * ci.z); pv[3] = (e.w * rr) * (e.w * ci.w);
+    }
+    float ov[4]; int oi[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v = pv[k]; int i = (lane < rmax) ? i0 + lane : 0x7fffffff;
+      warp_argmax_first(v, i);
+      ov[k] = v; oi[k] = (i == 0x7fffffff) ? 0 : i;
+    }
+    if (lane == 0) {
+      *reinterpret_cast<float4*>(cpv + ((size_t)b * gridDim.x + tile) * ld + S_main) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+      *reinterpret_cast<int4*>(cpi + ((size_t)b * gridDim.x + tile) * ld + S_main) = make_int4(oi[0], oi[1], oi[2], oi[3]);
+    }
   }
 }
 

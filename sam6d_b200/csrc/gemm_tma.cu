@@ -37,6 +37,9 @@ struct Args {
   long long ldc, ldr;
   float alpha;
   int act;
+  int batch;                 // independent problems stacked along the rows of A and W (score matrices: one per proposal)
+  long long a_rpb, w_rpb;    // rows of A / W per problem (a tile may run into the next problem's rows: masked on store)
+  long long c_bs, r_bs;      // element strides of C / R between problems
 };
 
 template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, int STAGES, int EW>
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = (g.N + BN - 1) / BN;
-  const long long ntiles = (long long)m_tiles * n_tiles;
+  const long long tpb = (long long)m_tiles * n_tiles, ntiles = tpb * g.batch;
   const int nkb = (g.K + BK - 1) / BK;
 
   if (tid == 0) {
@@ -72,14 +75,16 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
     if (lane == 0) {
       long long gk = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (int)(tile % m_tiles) * BM, n0 = (int)(tile / m_tiles) * BN;
+        const long long bz = tile / tpb, t = tile - bz * tpb;
+        const int m0 = (int)(t % m_tiles) * BM, n0 = (int)(t / m_tiles) * BN;
+        const int a_row = (int)(bz * g.a_rpb) + m0, w_row = (int)(bz * g.w_rpb) + n0;
         for (int kb = 0; kb < nkb; ++kb, ++gk) {
           const int s = (int)(gk % STAGES);
           tc::mbar_wait(&empty_bar[s], (uint32_t)(((gk / STAGES) & 1) ^ 1));
           tc::mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
           uint8_t* a_slab = smem + s * STAGE_BYTES;
-          tc::tma_load_2d(&tmA, &full_bar[s], a_slab, kb * BK, m0);
-          tc::tma_load_2d(&tmW, &full_bar[s], a_slab + A_BYTES, kb * BK, n0);
+          tc::tma_load_2d(&tmA, &full_bar[s], a_slab, kb * BK, a_row);
+          tc::tma_load_2d(&tmW, &full_bar[s], a_slab + A_BYTES, kb * BK, w_row);
         }
       }
     }
@@ -114,7 +119,10 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
     long long it = 0;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = (int)(it & 1);
-      const int m0 = (int)(tile % m_tiles) * BM, n0 = (int)(tile / m_tiles) * BN;
+      const long long bz = tile / tpb, t = tile - bz * tpb;
+      const int m0 = (int)(t % m_tiles) * BM, n0 = (int)(t / m_tiles) * BN;
+      OT* Cb = reinterpret_cast<OT*>(g.C) + bz * g.c_bs;
+      const OT* Rb = reinterpret_cast<const OT*>(g.R) + bz * g.r_bs;
       constexpr bool PRE = HAS_RES && (sizeof(OT) == 2) && (EW == 8);   // short-K tiles with a bf16 residual stream
       uint4 pre[PRE ? 4 : 1][4];
       if constexpr (PRE) {
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
         for (int cc = 0; cc < 4; ++cc) {
           const int col0 = n0 + (c_lo + cc) * 32;
           if (epi::chunk_vec_ok<OT, OT, true>(col0, g.N, g.ldc, g.ldr))
-            epi::prefetch_res_bf16(reinterpret_cast<const __nv_bfloat16*>(g.R), g.ldr, m0 + quad * 32, g.M, col0, lane, pre[cc]);
+            epi::prefetch_res_bf16(reinterpret_cast<const __nv_bfloat16*>(Rb), g.ldr, m0 + quad * 32, g.M, col0, lane, pre[cc]);
         }
       }
       tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
@@ -137,11 +145,11 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
             tc::tmem_ld32(t_addr + c * 32, v);
             if (epi::chunk_vec_ok<OT, OT, true>(col0, g.N, g.ldc, g.ldr))   // two call sites: `pre` stays in registers
               epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
-                                                                 reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C),
+                                                                 Rb, g.ldr, Cb,
                                                                  g.ldc, pre[cc]);
             else
               epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
-                                                                 reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C),
+                                                                 Rb, g.ldr, Cb,
                                                                  g.ldc);
           }
         }
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
           epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
-                                                             reinterpret_cast<const OT*>(g.R), g.ldr, reinterpret_cast<OT*>(g.C), g.ldc);
+                                                             Rb, g.ldr, Cb, g.ldc);
         }
       }
       tc::tc_fence_before_sync();
@@ -197,25 +205,27 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, long long K, lon
 
 }  // namespace
 
-// A (M,K) bf16 lda, W (N,K) bf16 ldw, C (M,N) fp32 (c_dtype 0) or bf16 (1), bias (N) fp32 or NULL, R (M,N) or NULL: the
-// residual has the element type of C (fp32 stream with fp32 output, bf16 stream with bf16 output).
-// K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, 16-byte aligned bases.  act: 0 none, 1 ReLU, 2 GELU(erf).
-S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
-                          long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream) {
+namespace {
+
+int launch_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
+                    long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb, long long w_rpb,
+                    long long c_bs, long long r_bs, float alpha, int act, void* stream) {
   S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && act >= 0 && act <= 2);
-  S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
-  if (M == 0) return 0;
+  S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && batch >= 0);
+  S6_REQUIRE(a_rpb * (long long)batch < 2000000000LL && w_rpb * (long long)batch < 2000000000LL);
+  if (M == 0 || batch == 0) return 0;
   CUtensorMap tmA, tmW;
-  int rc = make_map(&tmA, A, M, K, lda, BM);
+  const long long a_rows = batch > 1 ? a_rpb * (batch - 1) + M : M, w_rows = batch > 1 ? w_rpb * (batch - 1) + N : N;
+  int rc = make_map(&tmA, A, a_rows, K, lda, BM);
   if (rc) return rc;
-  rc = make_map(&tmW, W, N, K, ldw, BN);
+  rc = make_map(&tmW, W, w_rows, K, ldw, BN);
   if (rc) return rc;
   int dev = 0, sms = 0;
   S6_CHECK(cudaGetDevice(&dev));
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const long long ntiles = (long long)s6_cdiv(M, BM) * s6_cdiv(N, BN);
+  const long long ntiles = (long long)s6_cdiv(M, BM) * s6_cdiv(N, BN) * batch;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act};
+  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act, batch, a_rpb, w_rpb, c_bs, r_bs};
   cudaStream_t st = s6_stream(stream);
   const bool deep_k = K >= 1024;
 #define LAUNCH_ONE(OT, ACT, HB, HR, ST, EWN)                                                                           \
@@ -237,4 +247,24 @@ S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const
 #undef LAUNCH_ONE
   S6_LAUNCH_CHECK();
   return 0;
+}
+
+}  // namespace
+
+// A (M,K) bf16 lda, W (N,K) bf16 ldw, C (M,N) fp32 (c_dtype 0) or bf16 (1), bias (N) fp32 or NULL, R (M,N) or NULL: the
+// residual has the element type of C (fp32 stream with fp32 output, bf16 stream with bf16 output).
+// K % 8 == 0, lda % 8 == 0, ldw % 8 == 0, 16-byte aligned bases.  act: 0 none, 1 ReLU, 2 GELU(erf).
+S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
+                          long long lda, long long ldw, long long ldc, long long ldr, float alpha, int act, void* stream) {
+  return launch_gemm_tma(A, W, bias, R, C, c_dtype, M, N, K, lda, ldw, ldc, ldr, 1, 0, 0, 0, 0, alpha, act, stream);
+}
+
+// `batch` independent problems C_z = act(alpha A_z W_z^T + bias) (+ R_z): problem z reads rows [z*a_rpb, z*a_rpb + M) of A and
+// [z*w_rpb, z*w_rpb + N) of W (both matrices are the problems stacked along the rows) and writes C + z*c_bs (elements).
+// The cosine score matrices of the matching stages: A = normalised scene tokens, W = normalised template tokens per proposal.
+S6_API int sam6d_gemm_tma_batched(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N,
+                                  int K, long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb,
+                                  long long w_rpb, long long c_bs, long long r_bs, float alpha, int act, void* stream) {
+  S6_REQUIRE(a_rpb >= M && w_rpb >= N);
+  return launch_gemm_tma(A, W, bias, R, C, c_dtype, M, N, K, lda, ldw, ldc, ldr, batch, a_rpb, w_rpb, c_bs, r_bs, alpha, act, stream);
 }

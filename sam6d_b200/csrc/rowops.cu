@@ -53,14 +53,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const IT* __restrict__ x
 }
 
 // F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
-template <int MAXV>
-__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, float* __restrict__ y, RowView yv,
+template <int MAXV, typename OT = float>
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
                                                      long long rows, int C) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const float* xp = x + xv.off(r);
-  float* yp = y + yv.off(r);
+  OT* yp = y + yv.off(r);
   const int nv = C >> 5;
   float v[MAXV];
   float s = 0.f;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x
   const float n = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
-    if (i < nv) yp[lane + 32 * i] = v[i] / n;
+    if (i < nv) st_out(yp + lane + 32 * i, v[i] / n);
 }
 
 // Focused linear attention feature map (PEM/model/transformer.py:541-550):
@@ -209,6 +209,21 @@ S6_API int sam6d_l2norm_rows(const float* x, long long x_rpb, long long x_bstrid
   S6_LAUNCH_CHECK();
   return 0;
 }
+
+#undef ROW_EXTRA
+#define ROW_EXTRA , __nv_bfloat16
+// same, bf16 result: the operands of the tensor-core score GEMM
+S6_API int sam6d_l2norm_rows_bf16(const float* x, long long x_rpb, long long x_bstride, long long x_ld, void* y, long long y_rpb,
+                                  long long y_bstride, long long y_ld, long long rows, int C, void* stream) {
+  S6_REQUIRE(x && y && rows >= 0 && ROW_ARGS_OK(C));
+  if (rows == 0) return 0;
+  ROW_DISPATCH(C, l2norm_kernel, <<<s6_cdiv(rows, 8), 256, 0, s6_stream(stream)>>>(x, RowView{x_rpb, x_bstride, x_ld},
+               reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, rows, C));
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+#undef ROW_EXTRA
+#define ROW_EXTRA
 
 S6_API int sam6d_focus_rows(const float* x, long long x_rpb, long long x_bstride, long long x_ld, float* y, long long y_rpb,
                             long long y_bstride, long long y_ld, const float* softplus_scale, long long rows, int C,

@@ -260,6 +260,30 @@ def l2norm_rows(x: Tensor) -> Tensor:
     return out
 
 
+def l2norm_rows_bf16(x: Tensor) -> Tensor:
+    """F.normalize(x, dim=-1) with a bf16 result (operand of the tensor-core score GEMM)"""
+    _check(x, torch.float32, "x")
+    C = x.shape[-1]
+    rows = x.numel() // C
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.call("sam6d_l2norm_rows_bf16", _p(x), _ll(max(rows, 1)), _ll(0), _ll(C), _p(out), _ll(max(rows, 1)), _ll(0), _ll(C), _ll(rows), C,
+              _s())
+    return out
+
+
+def gemm_tma_batched(A: Tensor, W: Tensor, out: Tensor, M: int, N: int, ldc: int, c_bs: int, alpha: float = 1.0) -> Tensor:
+    """A (batch, a_rows, K) bf16, W (batch, w_rows, K) bf16 -> out[z, :M, :N] = alpha * A[z,:M] @ W[z,:N]^T for every z, written
+    with row stride ldc and problem stride c_bs (elements) into `out` (fp32 or bf16)"""
+    _check(A, torch.bfloat16, "A", 3)
+    _check(W, torch.bfloat16, "W", 3)
+    batch, a_rows, K = A.shape
+    if W.shape[0] != batch or W.shape[2] != K or a_rows < M or W.shape[1] < N:
+        raise RuntimeError("gemm_tma_batched: shape mismatch")
+    _lib.call("sam6d_gemm_tma_batched", _p(A), _p(W), None, None, _p(out), _DT[out.dtype], int(M), int(N), int(K), _ll(K), _ll(K),
+              _ll(ldc), _ll(0), int(batch), _ll(a_rows), _ll(W.shape[1]), _ll(c_bs), _ll(0), _f(alpha), 0, _s())
+    return out
+
+
 def focus_rows_raw(x_ptr, x_view, y_ptr, y_view, sp_scale: Tensor, rows: int, C: int):
     _lib.call("sam6d_focus_rows", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
               ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(sp_scale), _ll(rows), int(C), _s())

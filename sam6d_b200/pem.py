@@ -362,14 +362,16 @@ def compute_feature_similarity(feat1, feat2, type='cosine', temp=1.0, normalize_
         raise NotImplementedError("SAM-6D uses sim_type='cosine'")
     B, N, C = feat1.shape
     M = feat2.shape[1]
-    f1 = ops.l2norm_rows(feat1.contiguous()) if normalize_feat else feat1.contiguous()
-    f2 = ops.l2norm_rows(feat2.contiguous()) if normalize_feat else feat2.contiguous()
     ld = (M + 3) // 4 * 4                      # rows padded to 16 bytes so the epilogue can use full-line vector stores
     store = torch.empty(B, N, ld, dtype=torch.float32, device=feat1.device)
     if precision == "bf16":
-        ops.gemm_tc_raw(f1.data_ptr(), 0, f2.data_ptr(), 0, None, 0, store.data_ptr(), 0, N, M, C, C, C, ld, 0, batch=B, sA=N * C,
-                        sW=M * C, sC=N * ld, alpha=1.0 / temp)
+        # normalised bf16 tokens -> persistent TMA GEMM over all proposals (tiles that run past a proposal's rows are masked)
+        f1 = ops.l2norm_rows_bf16(feat1.contiguous()) if normalize_feat else feat1.contiguous().to(torch.bfloat16)
+        f2 = ops.l2norm_rows_bf16(feat2.contiguous()) if normalize_feat else feat2.contiguous().to(torch.bfloat16)
+        ops.gemm_tma_batched(f1, f2, store, N, M, ld, N * ld, alpha=1.0 / temp)
     else:
+        f1 = ops.l2norm_rows(feat1.contiguous()) if normalize_feat else feat1.contiguous()
+        f2 = ops.l2norm_rows(feat2.contiguous()) if normalize_feat else feat2.contiguous()
         ops.gemm_raw(f1.data_ptr(), f2.data_ptr(), None, 0, store.data_ptr(), N, M, C, C, C, ld, 0, batch=B, sA=N * C, sW=M * C,
                      sC=N * ld, alpha=1.0 / temp)
     return store[:, :, :M]                     # (B,N,M) like the reference; dense rows, row stride ld

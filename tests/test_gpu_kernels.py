@@ -615,3 +615,19 @@ def test_attn_global_tensor_core(ops):
         got = ops.attn_global_tc(qd, vt, blob, B, H, S, D ** -0.5, out_dtype=odt).cpu().float()
         torch.testing.assert_close(got, ref, atol=6e-2, rtol=2e-2)
         assert (got - ref).abs().mean().item() < 3e-3
+
+
+@pytest.mark.parametrize("B,S,T", [(3, 197, 197), (2, 2049, 2049), (4, 130, 77)])
+def test_gemm_tma_batched_scores(ops, B, S, T):
+    """stacked per-proposal score matrices: tiles that run into the next proposal's rows must not leak into the output"""
+    C = 256
+    a = torch.randn(B, S, C, generator=G(1))
+    w = torch.randn(B, T, C, generator=G(2))
+    ld = (T + 3) // 4 * 4
+    out = torch.full((B, S, ld), 7.0, device="cuda")
+    an, wn = ops.l2norm_rows_bf16(a.cuda()), ops.l2norm_rows_bf16(w.cuda())
+    ops.gemm_tma_batched(an, wn, out, S, T, ld, S * ld, alpha=10.0)
+    ref = 10.0 * an.float().cpu().double() @ wn.float().cpu().double().transpose(1, 2)
+    torch.testing.assert_close(out.cpu()[:, :, :T].double(), ref, atol=2e-4, rtol=1e-5)
+    assert (out.cpu()[:, :, T:] == 7.0).all()
+    torch.testing.assert_close(an.float().cpu(), torch.nn.functional.normalize(a, dim=-1), atol=4e-3, rtol=4e-3)
