@@ -76,6 +76,11 @@ int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const void* 
 int sam6d_gemm_tma_batched(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                            long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb, long long w_rpb,
                            long long c_bs, long long r_bs, float alpha, int act, void* stream);
+/* fused QKV / KV projection (bf16 out, bias): output columns [vt_col0, N) are written transposed per cloud of vt_S token rows
+ * into Vt[(cloud * (N - vt_col0) + c) * vt_N1 + token] (the V^T operand of sam6d_attn_tc) instead of C; the key-padding columns
+ * [vt_S, vt_N1) of Vt are left untouched and must be finite. */
+int sam6d_gemm_tma_vt(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long lda, long long ldw,
+                      long long ldc, void* Vt, int vt_col0, int vt_S, int vt_N1, void* stream);
 
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
 
@@ -168,8 +173,8 @@ int sam6d_pe_mlp_max(const float* pts, const int* idx, const int* cnt, int B, in
                      int out_ld, int out_off, void* stream);
 /* tensor-core version: layers 2 and 3 on tcgen05 (W2 (64,32), W3 (128,64) bf16), max-pool in the TMEM epilogue */
 int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, const float* W1, const float* B1,
-                        const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
-                        int out_off, void* stream);
+                        const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, void* out, int out_is_bf16,
+                        int out_ld, int out_off, void* stream);
 /* compute_fine_Rt (PEM/utils/model_utils.py:250-283) in three calls.  fine_assign: A (B,S,S) fp32 scores with row stride ld,
  * ld % 4 == 0, 16-byte aligned rows, S >= 97; scratch rsum/csum (B,ld), cpart/cpi (B,ceil(S/32),ld). */
 int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum, float* cpart,

@@ -289,13 +289,13 @@ int g_make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols
 
 }  // namespace
 
-// qkv: bf16 (B*4096 rows, ld >= 3*H*80) rows [q | k | v], head h at columns h*80 of each third; Vt: bf16 (B*H*80 rows, vt_ld >= 4096)
+// qkv: bf16 (B*4096 rows, ld >= 2*H*80) rows [q | k (| v)], head h at columns h*80 of q and H*80 + h*80 of k; Vt: bf16 (B*H*80 rows, vt_ld >= 4096)
 // = V^T per (image, head) (sam6d_transpose_tokens_bf16); rel_blob: rel_pos_h / rel_pos_w ((127, 80) each) packed as bf16 UMMA
 // slabs with 128-row slabs (ops.pack_rel_pos(..., slab_rows=128)); out (B*4096, H*80) fp32 or bf16.  64 x 64 token grid only.
 S6_API int sam6d_attn_global_tc(const void* qkv, long long ld, const void* Vt, long long vt_ld, const void* rel_blob, int B, int H,
                                 int grid, float scale, void* out, int out_is_bf16, long long out_ld, void* stream) {
   S6_REQUIRE(qkv && Vt && rel_blob && out && B >= 0 && H > 0 && grid == GRID);
-  S6_REQUIRE((ld % 8) == 0 && ld >= 3LL * H * D && (vt_ld % 8) == 0 && vt_ld >= GRID * GRID && (out_ld % (out_is_bf16 ? 8 : 4)) == 0);
+  S6_REQUIRE((ld % 8) == 0 && ld >= 2LL * H * D && (vt_ld % 8) == 0 && vt_ld >= GRID * GRID && (out_ld % (out_is_bf16 ? 8 : 4)) == 0);
   S6_REQUIRE((reinterpret_cast<uintptr_t>(rel_blob) & 15) == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
              (reinterpret_cast<uintptr_t>(Vt) & 15) == 0);
   if (B == 0) return 0;

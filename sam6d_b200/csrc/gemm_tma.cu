@@ -40,9 +40,12 @@ struct Args {
   int batch;                 // independent problems stacked along the rows of A and W (score matrices: one per proposal)
   long long a_rpb, w_rpb;    // rows of A / W per problem (a tile may run into the next problem's rows: masked on store)
   long long c_bs, r_bs;      // element strides of C / R between problems
+  // VT kernels: output columns >= vt_col0 are V of an attention layer and are written transposed, as the K-major B operand of
+  // the P V MMA: vt[(cloud * vt_C + c) * vt_N1 + token], cloud = row / vt_S (saves the transpose pass over V)
+  void* vt; int vt_col0, vt_S, vt_N1, vt_C;
 };
 
-template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, int STAGES, int EW>
+template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, int STAGES, int EW, bool VT = false>
 __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW, Args g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -154,12 +157,27 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
           }
         }
       } else {
+        [[maybe_unused]] const int vrow = m0 + quad * 32 + lane, vcloud = VT ? vrow / g.vt_S : 0, vtok = VT ? vrow - vcloud * g.vt_S : 0;
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           const int col0 = n0 + c * 32;
           if (col0 >= g.N) break;
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
+          if (VT && col0 >= g.vt_col0) {
+            // lane = token: 32 lanes write 32 adjacent tokens of one channel row (64 bytes) per store
+            if (vrow < g.M) {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.vt) + ((size_t)vcloud * g.vt_C + (col0 - g.vt_col0)) * g.vt_N1 + vtok;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < g.N) {
+                  float x = v[i] * g.alpha;
+                  if constexpr (HAS_BIAS) x += __ldg(g.bias + col0 + i);
+                  dst[(size_t)i * g.vt_N1] = __float2bfloat16(epi::act_fn<ACT>(x));
+                }
+            }
+            continue;
+          }
           epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias,
                                                              Rb, g.ldr, Cb, g.ldc);
         }
@@ -209,7 +227,8 @@ namespace {
 
 int launch_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                     long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb, long long w_rpb,
-                    long long c_bs, long long r_bs, float alpha, int act, void* stream) {
+                    long long c_bs, long long r_bs, float alpha, int act, void* stream, void* vt = nullptr, int vt_col0 = 0, int vt_S = 1,
+                    int vt_N1 = 0) {
   S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && act >= 0 && act <= 2);
   S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && batch >= 0);
   S6_REQUIRE(a_rpb * (long long)batch < 2000000000LL && w_rpb * (long long)batch < 2000000000LL);
@@ -225,7 +244,7 @@ int launch_gemm_tma(const void* A, const void* W, const float* bias, const void*
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long ntiles = (long long)s6_cdiv(M, BM) * s6_cdiv(N, BN) * batch;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act, batch, a_rpb, w_rpb, c_bs, r_bs};
+  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act, batch, a_rpb, w_rpb, c_bs, r_bs, vt, vt_col0, vt_S, vt_N1, N - vt_col0};
   cudaStream_t st = s6_stream(stream);
   const bool deep_k = K >= 1024;
 #define LAUNCH_ONE(OT, ACT, HB, HR, ST, EWN)                                                                           \
@@ -242,6 +261,22 @@ int launch_gemm_tma(const void* A, const void* W, const float* bias, const void*
       if (deep_k) LAUNCH_ONE(float, ACT, HB, HR, 4, 4); else LAUNCH_ONE(float, ACT, HB, HR, 3, 8);                    \
     }                                                                                                                  \
   } while (0)
+  if (vt) {
+    // V^T epilogue: bf16 output, bias, no activation / residual (the QKV and KV projections)
+    S6_REQUIRE(c_dtype == 1 && bias && !R && act == 0 && batch == 1 && vt_col0 > 0 && vt_col0 < N && (vt_col0 % 32) == 0 && vt_S > 0 &&
+               vt_N1 >= vt_S);
+    if (deep_k) {
+      auto k = gemm_tma_kernel<__nv_bfloat16, 0, true, false, 4, 4, true>;
+      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<4, 4>::kSmem));
+      S6_CHECK(s6_launch_pdl(k, dim3(grid), dim3(Cfg<4, 4>::kThreads), Cfg<4, 4>::kSmem, st, tmA, tmW, g));
+    } else {
+      auto k = gemm_tma_kernel<__nv_bfloat16, 0, true, false, 3, 8, true>;
+      S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3, 8>::kSmem));
+      S6_CHECK(s6_launch_pdl(k, dim3(grid), dim3(Cfg<3, 8>::kThreads), Cfg<3, 8>::kSmem, st, tmA, tmW, g));
+    }
+    S6_LAUNCH_CHECK();
+    return 0;
+  }
   EPI_DISPATCH(act, bias, R, LAUNCH_TMA);
 #undef LAUNCH_TMA
 #undef LAUNCH_ONE
@@ -260,11 +295,21 @@ S6_API int sam6d_gemm_tma(const void* A, const void* W, const float* bias, const
 }
 
 // `batch` independent problems C_z = act(alpha A_z W_z^T + bias) (+ R_z): problem z reads rows [z*a_rpb, z*a_rpb + M) of A and
-// [z*w_rpb, z*w_rpb + N) of W (both matrices are the problems stacked along the rows) and writes C + z*c_bs (elements).
+// [z*w_rpb, z*w_rpb + N) of W (w_rpb = 0: shared W) (both matrices are the problems stacked along the rows) and writes C + z*c_bs (elements).
 // The cosine score matrices of the matching stages: A = normalised scene tokens, W = normalised template tokens per proposal.
 S6_API int sam6d_gemm_tma_batched(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N,
                                   int K, long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb,
                                   long long w_rpb, long long c_bs, long long r_bs, float alpha, int act, void* stream) {
-  S6_REQUIRE(a_rpb >= M && w_rpb >= N);
+  S6_REQUIRE(a_rpb >= M && (w_rpb >= N || w_rpb == 0));       // w_rpb = 0: one weight matrix shared by every problem
   return launch_gemm_tma(A, W, bias, R, C, c_dtype, M, N, K, lda, ldw, ldc, ldr, batch, a_rpb, w_rpb, c_bs, r_bs, alpha, act, stream);
+}
+
+// sam6d_gemm_tma for a fused QKV / KV projection (bf16 output, bias): columns [vt_col0, N) are the values of an attention layer
+// and go to Vt instead of C, transposed per cloud of vt_S token rows: Vt[(cloud * (N - vt_col0) + c) * vt_N1 + token] -- the
+// layout sam6d_transpose_tokens_bf16 produces and sam6d_attn_tc / sam6d_attn_global_tc consume.  The key-padding columns
+// [vt_S, vt_N1) of Vt are not written (the caller keeps them finite, e.g. zeroed once).
+S6_API int sam6d_gemm_tma_vt(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long lda, long long ldw,
+                             long long ldc, void* Vt, int vt_col0, int vt_S, int vt_N1, void* stream) {
+  S6_REQUIRE(Vt != nullptr);
+  return launch_gemm_tma(A, W, bias, nullptr, C, 1, M, N, K, lda, ldw, ldc, 0, 1, 0, 0, 0, 0, 1.f, 0, stream, Vt, vt_col0, vt_S, vt_N1);
 }

@@ -24,13 +24,16 @@ constexpr int NUM_THREADS = 160;
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int NS>
+__device__ __forceinline__ void st_feat(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_feat(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+
+template <int NS, typename OT>
 __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __restrict__ pts, const int* __restrict__ idx, int N,
                                                                long long total_points,
                                                                const float* __restrict__ W1, const float* __restrict__ B1,
                                                                const __nv_bfloat16* __restrict__ W2, const float* __restrict__ B2,
                                                                const __nv_bfloat16* __restrict__ W3, const float* __restrict__ B3,
-                                                               float* __restrict__ out, int out_ld, int out_off) {
+                                                               OT* __restrict__ out, int out_ld, int out_off) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a1 = smem;
@@ -173,7 +176,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
           for (int i = 0; i < 32; ++i) m = fmaxf(m, v[i]);
           if (NS == 32 || (c & 1)) {                                // a point's samples are complete
             const long long p_out = tile * PPT + (NS == 32 ? c : (c >> 1));
-            if (p_out < total_points) out[p_out * out_ld + out_off + tid] = fmaxf(m + bias, 0.f);
+            if (p_out < total_points) st_feat(out + p_out * out_ld + out_off + tid, fmaxf(m + bias, 0.f));
             m = -INFINITY;
           }
         }
@@ -189,9 +192,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
 }  // namespace
 
 // Same contract as sam6d_pe_mlp_max, with W2 (64,32) and W3 (128,64) in bf16 (W1 / biases fp32); cnt is not needed.
+// out: fp32 (out_is_bf16 = 0) or bf16 rows of out_ld elements.
 S6_API int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, const float* W1, const float* B1,
-                               const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, float* out, int out_ld,
-                               int out_off, void* stream) {
+                               const void* W2_bf16, const float* B2, const void* W3_bf16, const float* B3, void* out, int out_is_bf16,
+                               int out_ld, int out_off, void* stream) {
   S6_REQUIRE(pts && idx && W1 && B1 && W2_bf16 && B2 && W3_bf16 && B3 && out && B >= 0 && N > 0);
   S6_REQUIRE(ns == 32 || ns == 64);
   if (B == 0) return 0;
@@ -204,13 +208,15 @@ S6_API int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, i
   cudaStream_t st = s6_stream(stream);
   const __nv_bfloat16* W2 = reinterpret_cast<const __nv_bfloat16*>(W2_bf16);
   const __nv_bfloat16* W3 = reinterpret_cast<const __nv_bfloat16*>(W3_bf16);
-  if (ns == 32) {
-    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    pe_tc_kernel<32><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3, out, out_ld, out_off);
-  } else {
-    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    pe_tc_kernel<64><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3, out, out_ld, out_off);
-  }
+#define PE_LAUNCH(NSV, OT)                                                                                                          \
+  do {                                                                                                                              \
+    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<NSV, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                 \
+    pe_tc_kernel<NSV, OT><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3,                         \
+                                                                 reinterpret_cast<OT*>(out), out_ld, out_off);                      \
+  } while (0)
+  if (ns == 32) { if (out_is_bf16) PE_LAUNCH(32, __nv_bfloat16); else PE_LAUNCH(32, float); }
+  else { if (out_is_bf16) PE_LAUNCH(64, __nv_bfloat16); else PE_LAUNCH(64, float); }
+#undef PE_LAUNCH
   S6_LAUNCH_CHECK();
   return 0;
 }

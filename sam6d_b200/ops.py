@@ -190,6 +190,40 @@ def gemm_tma(A: Tensor, W: Tensor, bias: Optional[Tensor] = None, residual: Opti
     return out
 
 
+_VT_CACHE = {}
+
+
+def _vt_buffer(rows: int, n1: int, device, slot: int) -> Tensor:
+    """V^T operand buffers are reused across layers (stream order keeps producer and consumer apart); they are zeroed once so
+    the key-padding columns, which the GEMM epilogue never writes, stay finite"""
+    key = (rows, n1, str(device), slot)
+    buf = _VT_CACHE.get(key)
+    if buf is None:
+        if len(_VT_CACHE) > 64:
+            _VT_CACHE.clear()
+        buf = torch.zeros(rows, n1, dtype=torch.bfloat16, device=device)
+        _VT_CACHE[key] = buf
+    return buf
+
+
+def gemm_tma_vt(A: Tensor, W: Tensor, bias: Tensor, vt_col0: int, S: int, slot: int = 0) -> Tuple[Tensor, Tensor]:
+    """fused QKV / KV projection: A (M,K) bf16, W (N,K) bf16 -> (QK (M, vt_col0) bf16, Vt) where the value columns
+    [vt_col0, N) are written transposed per cloud of S token rows: Vt (M/S * (N - vt_col0), ceil16(S)) = the operand
+    transpose_tokens would produce"""
+    _check(A, torch.bfloat16, "A", 2)
+    _check(W, torch.bfloat16, "W", 2)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K or M % S or not (0 < vt_col0 < N):
+        raise RuntimeError("gemm_tma_vt: shape mismatch")
+    n1 = (S + 15) // 16 * 16
+    out = torch.empty(M, vt_col0, dtype=torch.bfloat16, device=A.device)
+    vt = _vt_buffer((M // S) * (N - vt_col0), n1, A.device, slot)
+    _lib.call("sam6d_gemm_tma_vt", _p(A), _p(W), _p(bias), _p(out), M, N, K, _ll(K), _ll(K), _ll(vt_col0), _p(vt), int(vt_col0), int(S),
+              int(n1), _s())
+    return out, vt
+
+
 def layernorm_raw(x_ptr, x_view, y_ptr, y_view, gamma: Tensor, beta: Tensor, rows: int, C: int, eps: float = 1e-5):
     _lib.call("sam6d_layernorm", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
               ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(gamma), _p(beta), _ll(rows), int(C),
@@ -271,16 +305,22 @@ def l2norm_rows_bf16(x: Tensor) -> Tensor:
     return out
 
 
-def gemm_tma_batched(A: Tensor, W: Tensor, out: Tensor, M: int, N: int, ldc: int, c_bs: int, alpha: float = 1.0) -> Tensor:
-    """A (batch, a_rows, K) bf16, W (batch, w_rows, K) bf16 -> out[z, :M, :N] = alpha * A[z,:M] @ W[z,:N]^T for every z, written
-    with row stride ldc and problem stride c_bs (elements) into `out` (fp32 or bf16)"""
+def gemm_tma_batched(A: Tensor, W: Tensor, out: Tensor, M: int, N: int, ldc: int, c_bs: int, alpha: float = 1.0,
+                     bias: Optional[Tensor] = None, residual: Optional[Tensor] = None, ldr: int = 0, r_bs: int = 0) -> Tensor:
+    """A (batch, a_rows, K) bf16; W (batch, w_rows, K) bf16 or one shared (N, K) matrix ->
+    out[z, :M, :N] = alpha * A[z,:M] @ W[z,:N]^T (+ bias) (+ residual[z]) for every z, written with row stride ldc and problem
+    stride c_bs (elements) into `out` (fp32 or bf16; the residual has out's element type, row stride ldr, problem stride r_bs)"""
     _check(A, torch.bfloat16, "A", 3)
-    _check(W, torch.bfloat16, "W", 3)
+    _check(W, torch.bfloat16, "W")
     batch, a_rows, K = A.shape
-    if W.shape[0] != batch or W.shape[2] != K or a_rows < M or W.shape[1] < N:
+    shared = W.dim() == 2
+    if W.shape[-1] != K or a_rows < M or (not shared and (W.shape[0] != batch or W.shape[1] < N)) or (shared and W.shape[0] != N):
         raise RuntimeError("gemm_tma_batched: shape mismatch")
-    _lib.call("sam6d_gemm_tma_batched", _p(A), _p(W), None, None, _p(out), _DT[out.dtype], int(M), int(N), int(K), _ll(K), _ll(K),
-              _ll(ldc), _ll(0), int(batch), _ll(a_rows), _ll(W.shape[1]), _ll(c_bs), _ll(0), _f(alpha), 0, _s())
+    if residual is not None and residual.dtype != out.dtype:
+        raise RuntimeError("gemm_tma_batched: the residual must have the output's element type")
+    _lib.call("sam6d_gemm_tma_batched", _p(A), _p(W), _p(bias), _p(residual), _p(out), _DT[out.dtype], int(M), int(N), int(K), _ll(K),
+              _ll(K), _ll(ldc), _ll(ldr), int(batch), _ll(a_rows), _ll(0 if shared else W.shape[1]), _ll(c_bs), _ll(r_bs), _f(alpha), 0,
+              _s())
     return out
 
 
@@ -530,8 +570,10 @@ def pe_mlp_max_tc(pts: Tensor, idx: Tensor, weights, out: Tensor, out_off: int):
     W1, B1, W2, B2, W3, B3 = weights
     _check(W2, torch.bfloat16, "W2", 2)
     _check(W3, torch.bfloat16, "W3", 2)
+    if out.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("pe_mlp_max_tc: out must be float32 or bfloat16")
     _lib.call("sam6d_pe_mlp_max_tc", _p(pts), _p(idx), B, N, ns, _p(W1), _p(B1), _p(W2), _p(B2), _p(W3), _p(B3), _p(out),
-              out.shape[-1], int(out_off), _s())
+              int(out.dtype == torch.bfloat16), out.shape[-1], int(out_off), _s())
 
 
 def fine_assign(A: Tensor, pts2: Tensor, shift: float):

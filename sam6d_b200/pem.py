@@ -242,11 +242,10 @@ class GeometricTransformer(nn.Module):
         B, S, C = x.shape
         d = C // NUM_HEADS
         x2d = x.view(B * S, C)
-        qkv = ops.gemm_tma(x2d, w["w_qkv"].bf16, w["b_qkv"], out_dtype=torch.bfloat16)             # (B*S, q|k|v)
+        qk, vt = ops.gemm_tma_vt(x2d, w["w_qkv"].bf16, w["b_qkv"], 2 * C, S)                        # (B*S, q|k) and V^T
         u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                              # (B*S, 4*C) fp32
         sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
-        vt = ops.transpose_tokens(qkv, 2 * C, C, B, S)
-        hid = ops.attn_tc(qkv, 0, qkv, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
+        hid = ops.attn_tc(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
         return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
 
     def _cross_bf16(self, x, mem, w, out):
@@ -255,9 +254,8 @@ class GeometricTransformer(nn.Module):
         d = C // NUM_HEADS
         x2d = x.view(B * S, C)
         q = ops.gemm_tma(x2d, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
-        kv = ops.gemm_tma(mem.view(B * Sm, C), w["wkv_c"].bf16, w["bkv_c"], out_dtype=torch.bfloat16)
-        vt = ops.transpose_tokens(kv, C, C, B, Sm)
-        hid = ops.attn_tc(q, 0, kv, 0, vt, B, NUM_HEADS, S, Sm, d, 1.0 / math.sqrt(d), out_dtype=torch.bfloat16)
+        k, vt = ops.gemm_tma_vt(mem.view(B * Sm, C), w["wkv_c"].bf16, w["bkv_c"], C, Sm, slot=1)   # keys and V^T
+        hid = ops.attn_tc(q, 0, k, 0, vt, B, NUM_HEADS, S, Sm, d, 1.0 / math.sqrt(d), out_dtype=torch.bfloat16)
         self._tail_bf16(x2d, hid, w["tail_cross"], out=out.view(B * S, C))
 
     def _forward_bf16(self, f, emb, w):
@@ -545,7 +543,7 @@ class PositionalEncoding(nn.Module):
         w = self._weights()
         pts = pts.contiguous()
         B, N, _ = pts.shape
-        feat = torch.empty(B, N, 256, dtype=torch.float32, device=pts.device)
+        feat = torch.empty(B, N, 256, dtype=torch.bfloat16 if self.precision == "bf16" else torch.float32, device=pts.device)
         pair = ops.ball_query_pair(pts, pts, self.r1, self.ns1, self.r2, self.ns2) if self.r1 <= self.r2 else None
         for r, ns, name, off in ((self.r1, self.ns1, "m1", 0), (self.r2, self.ns2, "m2", 128)):
             if pair is not None:
@@ -565,6 +563,8 @@ class PositionalEncoding(nn.Module):
         w = self._weights()
         feat = self.local_features(pts1)
         B, N, _ = feat.shape
+        if self.precision == "bf16":
+            return ops.gemm_tma(feat.view(B * N, 256), w["w3"].bf16, w["b3"]).view(B, N, -1)
         return _gemm(self.precision, feat.view(B * N, 256), w["w3"], w["b3"]).view(B, N, -1)
 
 
@@ -747,14 +747,16 @@ class FinePointMatching(nn.Module):
         H = self.cfg.hidden_dim
         w, pw = self._weights(), self.PE._weights()
         local = self.PE.local_features(pts)                                         # (B,N,256)
-        tmp = _gemm(self.precision, f.reshape(B * N, C), w["w_in"], w["b_in"])
         if self.precision == "bf16":
-            # the dense token stream of the fine stage is bf16 from here on (fp32 accumulation inside every kernel)
+            # the dense token stream of the fine stage is bf16 from here on (fp32 accumulation inside every kernel):
+            # in_proj(f) in bf16 is the residual of the mlp3 GEMM over the bf16 local features, written behind the bg row
+            tmp = ops.gemm_tc(f.reshape(B * N, C), w["w_in"].bf16, w["b_in"], out_dtype=torch.bfloat16)
             out = torch.empty(B, N + 1, H, dtype=torch.bfloat16, device=f.device)
             out[:, 0, :] = self.bg_token.detach().reshape(1, -1).to(torch.bfloat16)
-            ops.gemm_tc_raw(local.data_ptr(), 0, pw["w3"].bf16.data_ptr(), 1, pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 2, 1,
-                            N, H, 256, 256, 256, H, H, batch=B, sA=N * 256, sW=0, sC=(N + 1) * H, sR=N * H)
+            ops.gemm_tma_batched(local, pw["w3"].bf16, out[:, 1:, :], N, H, H, (N + 1) * H, bias=pw["b3"],
+                                 residual=tmp.view(B, N, H), ldr=H, r_bs=N * H)
             return out
+        tmp = _gemm(self.precision, f.reshape(B * N, C), w["w_in"], w["b_in"])
         out = torch.empty(B, N + 1, H, dtype=torch.float32, device=f.device)
         out[:, 0, :] = self.bg_token.detach().reshape(1, -1)
         _gemm_raw(self.precision, local.data_ptr(), pw["w3"], pw["b3"], tmp.data_ptr(), out.data_ptr() + H * 4, N, H, 256, 256, H, H,

@@ -225,15 +225,13 @@ def _block_bf16(self, blk, bw, tok, B, L, C, G, maps):
         xw, nW, Hs = xn, B, G
     if Hs * Hs <= 256:
         # windowed blocks: tensor-core attention (QK^T and PV on tcgen05, decomposed rel-pos bias in the softmax warps)
-        qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"], out_dtype=torch.bfloat16)
-        vt = ops.transpose_tokens(qkv, 2 * C, C, nW, Hs * Hs)
-        att = ops.attn_tc(qkv, 0, qkv, C, vt, nW, self.num_heads, Hs * Hs, Hs * Hs, C // self.num_heads, blk.attn.scale,
+        qk, vt = ops.gemm_tma_vt(xw, bw["qkv"].bf16, bw["qkv_b"], 2 * C, Hs * Hs)                   # [q|k] rows and V^T per window
+        att = ops.attn_tc(qk, 0, qk, C, vt, nW, self.num_heads, Hs * Hs, Hs * Hs, C // self.num_heads, blk.attn.scale,
                           rel=(bw["rel_blob"], Hs, Hs), out_dtype=torch.bfloat16)
     elif Hs == 64 and C // self.num_heads == 80 and bw["rel_blob"] is not None:
         # global blocks of the 64 x 64 grid (4096 keys): tcgen05 attention with an online softmax, scores never leave TMEM
-        qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"], out_dtype=torch.bfloat16)
-        vt = ops.transpose_tokens(qkv, 2 * C, C, nW, Hs * Hs)
-        att = ops.attn_global_tc(qkv, vt, bw["rel_blob"], nW, self.num_heads, Hs, blk.attn.scale)
+        qk, vt = ops.gemm_tma_vt(xw, bw["qkv"].bf16, bw["qkv_b"], 2 * C, Hs * Hs, slot=2)
+        att = ops.attn_global_tc(qk, vt, bw["rel_blob"], nW, self.num_heads, Hs, blk.attn.scale)
     else:
         # other grids: flash-style CUDA-core kernel with online softmax
         qkv = ops.gemm_tma(xw, bw["qkv"].bf16, bw["qkv_b"])

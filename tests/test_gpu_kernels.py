@@ -493,7 +493,7 @@ def test_positional_encoding_tensor_core(ops):
     l32 = pe.local_features(pts.cuda()).cpu()
     torch.testing.assert_close(l32, ref_local, atol=2e-4, rtol=1e-4)
     pe.precision = "bf16"
-    l16 = pe.local_features(pts.cuda()).cpu()
+    l16 = pe.local_features(pts.cuda()).cpu().float()          # bf16 features in this mode
     err = (l16 - ref_local).abs()
     scale = ref_local.abs().mean().item()
     print("PE tc: mean |ref|", scale, "median err", err.median().item(), "max err", err.max().item())
@@ -504,7 +504,7 @@ def test_positional_encoding_tensor_core(ops):
     pe.precision = "fp32"
     a = pe.local_features(pts2.cuda()).cpu()
     pe.precision = "bf16"
-    b = pe.local_features(pts2.cuda()).cpu()
+    b = pe.local_features(pts2.cuda()).cpu().float()
     torch.testing.assert_close(b, a, atol=8e-2 * max(scale, 1.0), rtol=5e-2)
 
 
@@ -631,3 +631,17 @@ def test_gemm_tma_batched_scores(ops, B, S, T):
     torch.testing.assert_close(out.cpu()[:, :, :T].double(), ref, atol=2e-4, rtol=1e-5)
     assert (out.cpu()[:, :, T:] == 7.0).all()
     torch.testing.assert_close(an.float().cpu(), torch.nn.functional.normalize(a, dim=-1), atol=4e-3, rtol=4e-3)
+
+
+@pytest.mark.parametrize("nB,S,C,K", [(5, 197, 256, 256), (3, 196, 1280, 1280), (1, 4096, 160, 256)])
+def test_gemm_tma_vt_matches_gemm_plus_transpose(ops, nB, S, C, K):
+    """QKV projection with the value columns written as V^T by the epilogue == plain GEMM followed by transpose_tokens"""
+    M, N = nB * S, 3 * C
+    A = torch.randn(M, K, generator=G(1)).bfloat16().cuda()
+    W = (torch.randn(N, K, generator=G(2)) / math.sqrt(K)).bfloat16().cuda()
+    b = torch.randn(N, generator=G(3)).cuda()
+    full = ops.gemm_tma(A, W, b, out_dtype=torch.bfloat16)
+    vt_ref = ops.transpose_tokens(full, 2 * C, C, nB, S)
+    qk, vt = ops.gemm_tma_vt(A, W, b, 2 * C, S, slot=7)
+    assert torch.equal(qk, full[:, :2 * C])
+    assert torch.equal(vt, vt_ref)
