@@ -67,6 +67,31 @@ class ClockSampler(threading.Thread):
                     reasons=reasons, samples=len(self.samples))
 
 
+def host_threads() -> int:
+    """cores this process may really use: the smaller of the affinity mask and the cgroup CPU quota (os.cpu_count() reports the
+    machine, and oversubscribing torch's intra-op pool beyond the quota makes the CPU legs several times slower)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, quota // period))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 def cpu_oracle_throughput(reps: int, threads: int, nprop: int = 0):
     """the reference algorithm (oracle port, torch fp32 on the host) on a bounded sample of the workload"""
     from oracle import pem_oracle as po
@@ -88,17 +113,20 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    # one proposal per step keeps K steps + warm-up within a few minutes on the host cores (a 4-proposal pass is 25-85 s)
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_oracle_throughput(1, threads, REF_ARM_B)
+    threads = host_threads()
+    # The step's sample is sized from a 1-proposal warm-up so that K steps end within a few minutes: 4 proposals per step
+    # (better host throughput per pose) when that fits ~4 minutes, otherwise 1.
     t0 = time.perf_counter()
-    val, times = cpu_oracle_throughput(max(1, args.steps), threads, REF_ARM_B)
+    cpu_oracle_throughput(1, threads, 1)
+    t1 = time.perf_counter() - t0
+    nprop = 4 if t1 * 2.5 * max(1, args.steps) < 240.0 else 1
+    t0 = time.perf_counter()
+    val, times = cpu_oracle_throughput(max(1, args.steps), threads, nprop)
     ms = 1e3 * (time.perf_counter() - t0) / max(1, args.steps)
-    sample = f"{REF_ARM_B} proposal x {N_PTS} pts per step (of the {B_PER_GPU}-proposal batch), fp32, torch CPU"
+    sample = f"{nprop} proposal(s) x {N_PTS} pts per step (of the {B_PER_GPU}-proposal batch), fp32, torch CPU, {threads} threads"
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, proposals_per_step=REF_ARM_B, scene_points=N_PTS, template_points=N_PTS,
+                config=dict(workload=WORKLOAD, proposals_per_step=nprop, scene_points=N_PTS, template_points=N_PTS,
                             note="reference algorithm restated on the host (oracle port; the Python reference cannot travel)"),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -166,7 +194,7 @@ def run_ism(args):
                 roofline=dict(kernel="whole encoder (tcgen05 GEMMs + attention)", bound="tensor", achieved=ach, peak=pk["tensor"], unit="TFLOP/s",
                               frac=ach / pk["tensor"], traffic=None, peak_source=pk["source"] + " bf16_tflops_sustained"))
     if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         torch.set_num_threads(threads)
         sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
         t0 = time.perf_counter()
@@ -353,7 +381,7 @@ def main():
             clocks=sampler.summary() if sampler else None,
         )
         if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
+            threads = host_threads()
             cpu_oracle_throughput(1, threads, 1)
             val, times = cpu_oracle_throughput(1, threads)
             line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=threads, kind="port",
