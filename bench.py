@@ -26,7 +26,7 @@ WORKLOAD = "pem_matching_32x2048x2048"
 B_PER_GPU, N_PTS, N_MODEL, C_FEAT = 32, 2048, 1024, 256
 METRIC, UNIT = "poses/sec", "poses/s"
 REF_ARM_B = 1
-CPU_SAMPLE_B = 4
+CPU_SAMPLE_B = 8
 
 
 def peaks():
@@ -38,17 +38,41 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  NVML when it is importable (a query
+    takes ~1 ms, so a 100 ms timed region still gets tens of samples), else the nvidia-smi command line every 0.2 s."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            dev = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(dev.split(",")[index]) if dev and all(x.strip().isdigit() for x in dev.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_sample(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        bits = [0x8, 0x40, 0x20, 0x4]          # HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap
+        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._nvml_sample())
+                    time.sleep(0.005)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -61,10 +85,9 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unsampled"])
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                    reasons=reasons, samples=len(self.samples))
+                    reasons=reasons, samples=len(self.samples), source="nvml" if self.nvml is not None else "nvidia-smi")
 
 
 def host_threads() -> int:
@@ -383,9 +406,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             cpu_oracle_throughput(1, threads, 1)
-            val, times = cpu_oracle_throughput(1, threads)
+            val, times = cpu_oracle_throughput(2, threads)
             line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=threads, kind="port",
-                                        sample=f"{CPU_SAMPLE_B} of the {B} proposals, 1 timed pass after a 1-proposal warm-up, "
+                                        sample=f"{CPU_SAMPLE_B} of the {B} proposals, 2 timed passes after a 1-proposal warm-up, "
                                                f"{sum(times):.1f} s of CPU work, torch fp32 on {threads} threads")
         print(json.dumps(line))
     if world > 1:
