@@ -33,7 +33,11 @@ __device__ __forceinline__ bool fps_better(float d2, int k2, float d1, int k1, i
   return k2 < k1;
 }
 
-// One CTA per cloud, all points and running min-distances in registers (n <= THREADS*PPT).
+// One CTA per cloud, all points and running min-distances in registers (n <= THREADS*PPT <= 4096).
+// The order of fps_better is folded into one pair of unsigned keys per candidate -- hi = bits of the (non-negative) distance,
+// lo = 2^21 - ((bit-reversed thread slot << 12) | k), 0 for "no candidate" -- so the arg-max of a round is two redux.sync per
+// level (max of hi, then max of lo among the lanes that hold it) instead of a five-step shuffle tree of compares: the 195
+// serial rounds are pure latency.
 template <int THREADS, int PPT>
 __global__ void __launch_bounds__(THREADS) fps_reg_kernel(const float* __restrict__ xyz, int n, int m,
                                                            int bs_ref, int* __restrict__ idx) {
@@ -41,8 +45,8 @@ __global__ void __launch_bounds__(THREADS) fps_reg_kernel(const float* __restric
   float* sx = sm;
   float* sy = sm + n;
   float* sz = sm + 2 * n;
-  __shared__ float red_d[2][THREADS / 32];
-  __shared__ int red_k[2][THREADS / 32];
+  constexpr int NW = THREADS / 32;
+  __shared__ unsigned red_hi[2][NW], red_lo[2][NW];
 
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* p = xyz + (size_t)b * n * 3;
@@ -53,7 +57,9 @@ __global__ void __launch_bounds__(THREADS) fps_reg_kernel(const float* __restric
     (c == 0 ? sx : (c == 1 ? sy : sz))[k] = v;
   }
   __syncthreads();
+  const int bs_mask = bs_ref - 1, nb = 31 - __clz(bs_ref);      // bs_ref is a power of two
   float px[PPT], py[PPT], pz[PPT], tmp[PPT];
+  unsigned lo[PPT];
 #pragma unroll
   for (int i = 0; i < PPT; ++i) {
     int k = tid + i * THREADS;
@@ -62,43 +68,34 @@ __global__ void __launch_bounds__(THREADS) fps_reg_kernel(const float* __restric
     py[i] = ok ? sy[k] : 0.f;
     pz[i] = ok ? sz[k] : 0.f;
     tmp[i] = 1e10f;
+    const unsigned slot = nb ? (__brev((unsigned)(k & bs_mask)) >> (32 - nb)) : 0u;
+    lo[i] = ok ? (1u << 21) - ((slot << 12) | (unsigned)k) : 0u;
   }
-  const int bs_mask = bs_ref - 1;
   int old = 0;
   if (tid == 0) out[0] = 0;
   for (int j = 1; j < m; ++j) {
     float x1 = sx[old], y1 = sy[old], z1 = sz[old];
-    float best = -1.f;
-    int besti = 0;
+    unsigned bh = 0u, bl = 0u;
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
-      int k = tid + i * THREADS;
-      if (k < n) {
+      if (lo[i]) {
         float d = sqdist_ref(x1, y1, z1, px[i], py[i], pz[i]);
         float d2 = fminf(d, tmp[i]);
         tmp[i] = d2;
-        if (fps_better(d2, k, best, besti, bs_mask) || best < 0.f) { best = d2; besti = k; }
+        const unsigned h = __float_as_uint(d2);
+        if (h > bh || (h == bh && lo[i] > bl)) { bh = h; bl = lo[i]; }
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      float d2 = __shfl_xor_sync(0xffffffffu, best, o);
-      int k2 = __shfl_xor_sync(0xffffffffu, besti, o);
-      // a lane without points carries best = -1 and loses to any real candidate
-      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
-    }
+    unsigned wh = __reduce_max_sync(0xffffffffu, bh);
+    unsigned wl = __reduce_max_sync(0xffffffffu, bh == wh ? bl : 0u);
     const int buf = j & 1;
-    if (lane == 0) { red_d[buf][warp] = best; red_k[buf][warp] = besti; }
+    if (lane == 0) { red_hi[buf][warp] = wh; red_lo[buf][warp] = wl; }
     __syncthreads();
-    best = red_d[buf][0];
-    besti = red_k[buf][0];
-#pragma unroll
-    for (int w = 1; w < THREADS / 32; ++w) {
-      float d2 = red_d[buf][w];
-      int k2 = red_k[buf][w];
-      if (d2 >= 0.f && (best < 0.f || fps_better(d2, k2, best, besti, bs_mask))) { best = d2; besti = k2; }
-    }
-    old = besti;
+    bh = lane < NW ? red_hi[buf][lane] : 0u;
+    bl = lane < NW ? red_lo[buf][lane] : 0u;
+    wh = __reduce_max_sync(0xffffffffu, bh);
+    wl = __reduce_max_sync(0xffffffffu, bh == wh ? bl : 0u);
+    old = (int)(((1u << 21) - wl) & 0xfffu);
     if (tid == 0) out[j] = old;
   }
 }

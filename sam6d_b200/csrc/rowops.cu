@@ -52,6 +52,43 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const IT* __restrict__ x
     if (i < nv) { int c = lane + 32 * i; st_out(yp + c, (v[i] - mean) * rstd * gamma[c] + beta[c]); }
 }
 
+// C = 256 bf16 rows (every LayerNorm of the bf16 PEM path): a row is 32 lanes x 16 bytes, one load and one store per lane
+__global__ void __launch_bounds__(256) layernorm256_bf16_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, __nv_bfloat16* __restrict__ y,
+                                                                RowView yv, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                long long rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  s6_pdl_trigger();
+  const float4 g0 = *reinterpret_cast<const float4*>(gamma + lane * 8), g1 = *reinterpret_cast<const float4*>(gamma + lane * 8 + 4);
+  const float4 b0 = *reinterpret_cast<const float4*>(beta + lane * 8), b1 = *reinterpret_cast<const float4*>(beta + lane * 8 + 4);
+  s6_pdl_wait();
+  if (r >= rows) return;
+  const uint4 raw = *reinterpret_cast<const uint4*>(x + xv.off(r) + lane * 8);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    s += v[2 * i] + v[2 * i + 1];
+  }
+  const float mean = warp_sum(s) * (1.f / 256.f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+  const float rstd = rsqrtf(warp_sum(q) * (1.f / 256.f) + eps);
+  const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = (v[2 * i] - mean) * rstd * gg[2 * i] + bb[2 * i], c = (v[2 * i + 1] - mean) * rstd * gg[2 * i + 1] + bb[2 * i + 1];
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(y + yv.off(r) + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
 template <int MAXV, typename OT = float>
 __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
@@ -191,6 +228,14 @@ S6_API int sam6d_layernorm_bf16io(const void* x, long long x_rpb, long long x_bs
                                   float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
+  if (C == 256 && (x_ld % 8) == 0 && (y_ld % 8) == 0 && (x_bstride % 8) == 0 && (y_bstride % 8) == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    S6_CHECK(s6_launch_pdl(layernorm256_bf16_kernel, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream),
+                           reinterpret_cast<const __nv_bfloat16*>(x), RowView{x_rpb, x_bstride, x_ld}, reinterpret_cast<__nv_bfloat16*>(y),
+                           RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, eps));
+    S6_LAUNCH_CHECK();
+    return 0;
+  }
   LN_DISPATCH(C, __nv_bfloat16, __nv_bfloat16, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream),
               reinterpret_cast<const __nv_bfloat16*>(x), RowView{x_rpb, x_bstride, x_ld}, reinterpret_cast<__nv_bfloat16*>(y),
               RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
