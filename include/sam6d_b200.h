@@ -179,6 +179,14 @@ int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, int ns, 
  * ld % 4 == 0, 16-byte aligned rows, S >= 97; scratch rsum/csum (B,ld), cpart/cpi (B,ceil(S/32),ld). */
 int sam6d_fine_assign(const float* A, int B, int S, int ld, float shift, const float* pts2, float* rsum, float* csum, float* cpart,
                       int* cpi, int* lab1, int* lab2, float* wts, float* pred, void* stream);
+/* The same assignment without the (B,S,S) score matrix (bf16 path): every pass recomputes its score tiles on tcgen05 from the
+ * L2-normalised bf16 tokens Fa (rows) and Fb (columns), both (B*S, 256), and reduces them in TMEM.
+ * mode 0: out_inv (B,ld_f) = 1 / sum_j exp(alpha <a_i,b_j> - shift);  mode 1: lab (B,S) = argmax_j (e*row_f_i)*(e*col_f_j);
+ * mode 2: mode 1 plus wts (B,S-1), pred (B,S-1,3) for rows >= 1 from q4 (B,ld_f) float4 (sam6d_fine_masked_points).
+ * compute_fine_Rt = mode 0 on (F1,F2) and (F2,F1), mode 1 on (F2,F1) [column labels], masked points, mode 2 on (F1,F2). */
+int sam6d_fine_pass_tc(const void* Fa, const void* Fb, int B, int S, float alpha, float shift, int mode, const float* row_f,
+                       const float* col_f, int ld_f, const float* q4, float* out_inv, int* lab, float* wts, float* pred, void* stream);
+int sam6d_fine_masked_points(const int* lab2, const float* pts2, int B, int S, int ld, float* q4, void* stream);
 int sam6d_weighted_procrustes(const float* src, const float* ref, const float* wts, int B, int N, float weight_thresh,
                               float eps, float* R, float* t, void* stream);
 int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const float* R, const float* t, const float* model,

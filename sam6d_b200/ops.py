@@ -606,6 +606,35 @@ def fine_assign(A: Tensor, pts2: Tensor, shift: float):
     return lab1, lab2, wts, pred
 
 
+def fine_assign_tc(f1n: Tensor, f2n: Tensor, pts2: Tensor, alpha: float):
+    """the assignment of compute_fine_Rt from the normalised bf16 tokens f1n (B,S,256) [scene, rows] and f2n (B,S,256) [template,
+    columns] without forming the (B,S,S) score matrix: 4 tcgen05 passes (row sums, column sums, column labels, row labels +
+    weighted correspondences).  alpha = 1/temp (also the softmax shift: cosine <= 1).  -> lab1 (B,S), lab2 (B,S), wts, pred"""
+    _check(f1n, torch.bfloat16, "f1n", 3)
+    _check(f2n, torch.bfloat16, "f2n", 3)
+    _check(pts2, torch.float32, "pts2", 3)
+    B, S, C = f1n.shape
+    if C != 256 or f2n.shape != f1n.shape or pts2.shape[1] != S - 1:
+        raise RuntimeError("fine_assign_tc: (B,S,256) tokens and (B,S-1,3) points expected")
+    dev = f1n.device
+    ld = (S + 3) // 4 * 4
+    rinv = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    cinv = torch.empty(B, ld, dtype=torch.float32, device=dev)
+    q4 = torch.empty(B, ld, 4, dtype=torch.float32, device=dev)
+    lab1 = torch.zeros(B, S, dtype=torch.int32, device=dev)
+    lab2 = torch.zeros(B, S, dtype=torch.int32, device=dev)
+    wts = torch.empty(B, S - 1, dtype=torch.float32, device=dev)
+    pred = torch.empty(B, S - 1, 3, dtype=torch.float32, device=dev)
+    a, sh = _f(alpha), _f(alpha)
+    _lib.call("sam6d_fine_pass_tc", _p(f1n), _p(f2n), B, S, a, sh, 0, None, None, ld, None, _p(rinv), None, None, None, _s())
+    _lib.call("sam6d_fine_pass_tc", _p(f2n), _p(f1n), B, S, a, sh, 0, None, None, ld, None, _p(cinv), None, None, None, _s())
+    _lib.call("sam6d_fine_pass_tc", _p(f2n), _p(f1n), B, S, a, sh, 1, _p(cinv), _p(rinv), ld, None, None, _p(lab2), None, None, _s())
+    _lib.call("sam6d_fine_masked_points", _p(lab2), _p(pts2), B, S, ld, _p(q4), _s())
+    _lib.call("sam6d_fine_pass_tc", _p(f1n), _p(f2n), B, S, a, sh, 2, _p(rinv), _p(cinv), ld, _p(q4), None, _p(lab1), _p(wts), _p(pred),
+              _s())
+    return lab1, lab2, wts, pred
+
+
 def weighted_procrustes(src: Tensor, ref: Tensor, wts: Tensor, weight_thresh: float = 0.0, eps: float = 1e-5):
     _check(src, torch.float32, "src", 3)
     _check(ref, torch.float32, "ref", 3)

@@ -787,9 +787,17 @@ class FinePointMatching(nn.Module):
         else:
             o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
             o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
-        atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
-        pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
+        if (self.precision == "bf16" and self.cfg.sim_type == 'cosine' and self.cfg.normalize_feat and H == 256
+                and o1.shape[-1] == 256 and not self.return_feat):
+            # score tiles are recomputed on the tensor cores inside every assignment pass: no (B,2049,2049) matrix in HBM
+            f1n, f2n = ops.l2norm_rows_bf16(o1.contiguous()), ops.l2norm_rows_bf16(o2.contiguous())
+            lab1, _, wts, pred = ops.fine_assign_tc(f1n, f2n, p2, 1.0 / self.cfg.temp)
+            pred_R, pred_t = ops.weighted_procrustes(pred, p1, wts, 0.0, 1e-5)
+            score, t_scaled = ops.pose_score(p1, lab1, pred_R, pred_t, model.contiguous(), radius.contiguous(), 0.15)
+        else:
+            atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
+            pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
         end_points['pred_R'] = pred_R
         end_points['pred_t'] = t_scaled
         end_points['pred_pose_score'] = score

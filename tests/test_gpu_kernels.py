@@ -645,3 +645,30 @@ def test_gemm_tma_vt_matches_gemm_plus_transpose(ops, nB, S, C, K):
     qk, vt = ops.gemm_tma_vt(A, W, b, 2 * C, S, slot=7)
     assert torch.equal(qk, full[:, :2 * C])
     assert torch.equal(vt, vt_ref)
+
+
+@pytest.mark.parametrize("B,S", [(2, 513), (3, 2049), (1, 130)])
+def test_fine_assign_tensor_core_fused(ops, B, S):
+    """compute_fine_Rt's assignment recomputed tile by tile on tcgen05 (no (B,S,S) matrix) against fp64 math on the same
+    bf16-rounded normalised tokens: labels exact (planted matches make them decisive), weights / correspondences to 1e-3"""
+    g = G(31)
+    C, temp = 256, 0.1
+    f2 = torch.randn(B, S, C, generator=g)
+    perm = torch.stack([torch.randperm(S, generator=g) for _ in range(B)])
+    f1 = torch.gather(f2, 1, perm[:, :, None].expand(-1, -1, C)) + 0.35 * torch.randn(B, S, C, generator=g)
+    pts2 = torch.randn(B, S - 1, 3, generator=g) * 0.4
+    f1n, f2n = ops.l2norm_rows_bf16(f1.cuda()), ops.l2norm_rows_bf16(f2.cuda())
+    a, b = f1n.cpu().double(), f2n.cpu().double()
+    A = a @ b.transpose(1, 2) / temp
+    P = torch.softmax(A, dim=2) * torch.softmax(A, dim=1)
+    lab1_ref = P.argmax(dim=2)                                   # (B,S) incl. the bg row 0 (unused)
+    lab2_ref = P.argmax(dim=1)
+    mask = (lab2_ref[:, 1:] > 0).double()                        # columns j >= 1 matched to a non-background row
+    Pm = P[:, 1:, 1:] * mask[:, None, :]
+    w_ref = Pm.sum(dim=2) * (lab1_ref[:, 1:] > 0)
+    pred_ref = (Pm @ pts2.double()) * (lab1_ref[:, 1:] > 0)[:, :, None] / (w_ref[:, :, None] + 1e-6)
+    lab1, lab2, wts, pred = ops.fine_assign_tc(f1n, f2n, pts2.cuda(), 1.0 / temp)
+    assert torch.equal(lab1.cpu()[:, 1:].long(), lab1_ref[:, 1:])
+    assert torch.equal(lab2.cpu().long(), lab2_ref)
+    torch.testing.assert_close(wts.cpu().double(), w_ref, atol=1e-6, rtol=2e-3)
+    torch.testing.assert_close(pred.cpu().double(), pred_ref, atol=2e-5, rtol=2e-3)
