@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fine_pass_kernel(const __grid_
   __shared__ __align__(8) uint64_t a_full, a_empty, full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float comb[2][BM][6];             // upper-half partial state of each row, double-buffered over items
+  __shared__ float sc[2][BN];                  // column factors of the current / next column tile (modes 1, 2)
+  __shared__ __align__(16) float4 sq[2][BN];   // masked template points of the tile (mode 2)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m_tiles = (g.S + BM - 1) / BM, n_tiles = (g.S + BN - 1) / BN;
@@ -142,6 +144,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fine_pass_kernel(const __grid_
       int bi = 0x7fffffff;
       for (int nt = 0; nt < n_tiles; ++nt, ++tcount) {
         const int acc = (int)(tcount & 1);
+        if (MODE != 0) {
+          // stage the tile's 256 column factors (and masked points) once per CTA while the MMAs of the tile run; the
+          // element loop then reads them as shared-memory broadcasts instead of two dependent global loads per element
+          const int et = tid - 64, j = nt * BN + et;
+          sc[acc][et] = (j < g.S) ? cf[j] : 0.f;
+          if (MODE == 2) sq[acc][et] = (j < g.S) ? q4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          epi_bar();
+        }
         tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((tcount >> 1) & 1));
         tc::tc_fence_after_sync();
         const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
@@ -158,11 +168,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) fine_pass_kernel(const __grid_
             if (MODE == 0) {
               sum += e;
             } else {
-              const float cj = (j < g.S) ? __ldg(cf + j) : 0.f;       // warp-uniform address: one transaction
+              const float cj = sc[acc][half * 128 + c * 32 + k];      // 0 past the last column
               const float p = (e * rf) * (e * cj);
               if (p > bv) { bv = p; bi = j; }                         // ascending j inside this thread: first maximum
               if (MODE == 2) {
-                const float4 q = (j < g.S) ? __ldg(q4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 q = sq[acc][half * 128 + c * 32 + k];
                 const float pm = p * q.w;
                 w += pm; px = fmaf(pm, q.x, px); py = fmaf(pm, q.y, py); pz = fmaf(pm, q.z, pz);
               }
