@@ -137,6 +137,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     float* my_tab = nullptr;
     (void)my_tab;
     const int nchunk = (a.N1 + 31) / 32;
+    // dense bias: a chunk's tile is fetched one chunk ahead (32 independent 128-byte requests per warp: for each of the warp's
+    // 32 rows the lanes read 32 consecutive columns), so its latency hides behind the previous chunk's arithmetic
+    float bl[32];
+    auto fetch_bias = [&](int c) {
+      const int col = c * 32 + lane;
+      const size_t rowbase = ((size_t)b * a.H + h) * a.Sq;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) {
+        const int nn = min(n0 + warp * 32 + rr, a.Sq - 1);
+        bl[rr] = (col < Sk) ? __ldg(a.bias + (rowbase + nn) * Sk + col) : 0.f;
+      }
+    };
+    if (BIAS_MODE == 1) fetch_bias(0);                                     // in flight while the loads and the score MMA run
     tc::mbar_wait(&s_full, 0);
     tc::tc_fence_after_sync();
     if (BIAS_MODE == 2) {
@@ -162,19 +175,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     for (int c = 0; c < nchunk; ++c) {
       float v[32];
       tc::tmem_ld32(t_addr + c * 32, v);
+      if (BIAS_MODE == 3) fetch_bias(c);
       if (BIAS_MODE == 1 || BIAS_MODE == 3) {
-        // coalesced bias tile: for each of the warp's 32 rows the lanes read 32 consecutive columns (one 128-byte line)
-        const int col = c * 32 + lane;
-        const size_t rowbase = ((size_t)b * a.H + h) * a.Sq;
-        float bl[32];
-#pragma unroll
-        for (int rr = 0; rr < 32; ++rr) {                      // 32 independent 128-byte requests in flight per warp
-          const int nn = min(n0 + warp * 32 + rr, a.Sq - 1);
-          bl[rr] = (col < Sk) ? __ldg(a.bias + (rowbase + nn) * Sk + col) : 0.f;
-        }
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) my_stage[rr * 33 + lane] = bl[rr];
         __syncwarp();
+        if (BIAS_MODE == 1 && c + 1 < nchunk) fetch_bias(c + 1);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -359,30 +359,41 @@ __global__ void __launch_bounds__(256) ball_query_pair_kernel(const float* __res
     for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) sp[i] = p[(size_t)base * 3 + i];
     __syncthreads();
     if (j < m && (ca < nsa || cb < nsb)) {
-      for (int k0 = 0; k0 < tn && (ca < nsa || cb < nsb); k0 += 32) {
-        int k = k0 + lane;
-        float d2 = INFINITY;
-        if (k < tn) {
-          float dx = nx - sp[k * 3 + 0], dy = ny - sp[k * 3 + 1], dz = nz - sp[k * 3 + 2];
-          d2 = __fmul_rn(dx, dx);
-          d2 = __fmaf_rn(dy, dy, d2);
-          d2 = __fmaf_rn(dz, dz, d2);
-        }
-        const bool ha = d2 < ra2, hb = d2 < rb2;
-        const unsigned mb = __ballot_sync(0xffffffffu, hb);
-        if (mb) {
-          if (cb < nsb) {
-            if (cb == 0) fb = base + k0 + __ffs(mb) - 1;
-            int pos = cb + __popc(mb & below);
-            if (hb && pos < nsb) ob[pos] = base + k;
-            cb += __popc(mb);
+      // two groups of 32 candidates per step: both distances and all four ballots are issued before the (serial) list
+      // bookkeeping, which halves the dependent-latency chain of the scan
+      for (int k0 = 0; k0 < tn && (ca < nsa || cb < nsb); k0 += 64) {
+        float d2[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = k0 + u * 32 + lane;
+          d2[u] = INFINITY;
+          if (k < tn) {
+            float dx = nx - sp[k * 3 + 0], dy = ny - sp[k * 3 + 1], dz = nz - sp[k * 3 + 2];
+            float d = __fmul_rn(dx, dx);
+            d = __fmaf_rn(dy, dy, d);
+            d2[u] = __fmaf_rn(dz, dz, d);
           }
-          const unsigned ma = __ballot_sync(0xffffffffu, ha);
-          if (ma && ca < nsa) {
-            if (ca == 0) fa = base + k0 + __ffs(ma) - 1;
-            int pos = ca + __popc(ma & below);
-            if (ha && pos < nsa) oa[pos] = base + k;
-            ca += __popc(ma);
+        }
+        unsigned mb[2], ma[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          mb[u] = __ballot_sync(0xffffffffu, d2[u] < rb2);
+          ma[u] = __ballot_sync(0xffffffffu, d2[u] < ra2);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = k0 + u * 32 + lane;
+          if (mb[u] && cb < nsb) {
+            if (cb == 0) fb = base + k0 + u * 32 + __ffs(mb[u]) - 1;
+            int pos = cb + __popc(mb[u] & below);
+            if (d2[u] < rb2 && pos < nsb) ob[pos] = base + k;
+            cb += __popc(mb[u]);
+          }
+          if (ma[u] && ca < nsa) {
+            if (ca == 0) fa = base + k0 + u * 32 + __ffs(ma[u]) - 1;
+            int pos = ca + __popc(ma[u] & below);
+            if (d2[u] < ra2 && pos < nsa) oa[pos] = base + k;
+            ca += __popc(ma[u]);
           }
         }
       }

@@ -186,6 +186,9 @@ class GeometricTransformer(nn.Module):
                 wq_c=_W(ca.proj_q.weight), bq_c=_f32(ca.proj_q.bias),
                 wkv_c=_W(torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_v.weight)], dim=0)),
                 bkv_c=torch.cat([_f32(ca.proj_k.bias), _f32(ca.proj_v.bias)], dim=0).contiguous(),
+                # cloud 1 is the memory of the first cross layer and the query of the second: one projection [k | q | v]
+                wkqv_c=_W(torch.cat([_f32(ca.proj_k.weight), _f32(ca.proj_q.weight), _f32(ca.proj_v.weight)], dim=0)),
+                bkqv_c=torch.cat([_f32(ca.proj_k.bias), _f32(ca.proj_q.bias), _f32(ca.proj_v.bias)], dim=0).contiguous(),
                 tail_cross=_pack_tail(self.layers[1]))
             self._packed.key = key
         return self._packed.w
@@ -248,23 +251,23 @@ class GeometricTransformer(nn.Module):
         hid = ops.attn_tc(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
         return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
 
-    def _cross_bf16(self, x, mem, w, out):
-        B, S, C = x.shape
-        Sm = mem.shape[1]
-        d = C // NUM_HEADS
-        x2d = x.view(B * S, C)
-        q = ops.gemm_tma(x2d, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
-        k, vt = ops.gemm_tma_vt(mem.view(B * Sm, C), w["wkv_c"].bf16, w["bkv_c"], C, Sm, slot=1)   # keys and V^T
-        hid = ops.attn_tc(q, 0, k, 0, vt, B, NUM_HEADS, S, Sm, d, 1.0 / math.sqrt(d), out_dtype=torch.bfloat16)
-        self._tail_bf16(x2d, hid, w["tail_cross"], out=out.view(B * S, C))
-
     def _forward_bf16(self, f, emb, w):
         """f (2B,S,C) bf16 = [cloud 0 ; cloud 1], emb (2B,S,S,256) -> same layout"""
-        B = f.shape[0] // 2
+        B, S, C = f.shape[0] // 2, f.shape[1], f.shape[2]
+        d = C // NUM_HEADS
+        scale = 1.0 / math.sqrt(d)
         f = self._self_bf16(f, emb, w)
         out = torch.empty_like(f)
-        self._cross_bf16(f[:B], f[B:], w, out[:B])
-        self._cross_bf16(f[B:], out[:B], w, out[B:])        # sequential: sees the updated cloud 0 (transformer.py:505-507)
+        x0, x1 = f[:B].view(B * S, C), f[B:].view(B * S, C)
+        # cross layer 0: cloud 0 attends to cloud 1.  Cloud 1's projection also yields its queries for the second layer.
+        q0 = ops.gemm_tma(x0, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
+        kq1, vt1 = ops.gemm_tma_vt(x1, w["wkqv_c"].bf16, w["bkqv_c"], 2 * C, S, slot=1)            # (B*S, k | q) and V^T
+        hid = ops.attn_tc(q0, 0, kq1, 0, vt1, B, NUM_HEADS, S, S, d, scale, out_dtype=torch.bfloat16)
+        self._tail_bf16(x0, hid, w["tail_cross"], out=out[:B].view(B * S, C))
+        # cross layer 1: cloud 1 attends to the updated cloud 0 (sequential, transformer.py:505-507)
+        k0, vt0 = ops.gemm_tma_vt(out[:B].view(B * S, C), w["wkv_c"].bf16, w["bkv_c"], C, S, slot=2)
+        hid = ops.attn_tc(kq1, C, k0, 0, vt0, B, NUM_HEADS, S, S, d, scale, out_dtype=torch.bfloat16)
+        self._tail_bf16(x1, hid, w["tail_cross"], out=out[B:].view(B * S, C))
         return out
 
     @torch.no_grad()
