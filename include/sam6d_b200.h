@@ -192,6 +192,13 @@ int sam6d_weighted_procrustes(const float* src, const float* ref, const float* w
 int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, const float* R, const float* t, const float* model,
                      int nm, float dis_thres, const float* radius, float* score, float* t_scaled, void* stream);
 
+/* ---- PEM RGB branch: pixel features at the chosen pixels without the (B,C,H,W) feature map ------------- */
+/* up (B, G*G, sub*sub*C) fp32 / bf16 = ViT_AE.output_upscaling's output (PEM/model/feature_extraction.py:100-108); choose (B,K)
+ * int64 pixel indices y*W + x -> out (B,K,C) fp32 = get_chosen_pixel_feats(F.interpolate(map, (H,W), bilinear), choose)
+ * (PEM/utils/model_utils.py:69-81). */
+int sam6d_bilinear_gather(const void* up, int up_is_bf16, const long long* choose, int B, int K, int G, int sub, int C, int H, int W,
+                          float* out, void* stream);
+
 /* ---- SAM ViT image encoder attention (ISM/segment_anything/modeling/image_encoder.py:224-240,325-361) ---------------- */
 /* softmax((q*scale) k^T + q.Rh + q.Rw) v per window and head (head_dim 80), flash-style.  qkv: (nW*Hs*Ws, 3*nH*80) rows
  * [q|k|v], rel_h (2Hs-1,80), rel_w (2Ws-1,80), out (nW*Hs*Ws, nH*80).  Hs, Ws <= 64. */

@@ -89,6 +89,48 @@ __global__ void __launch_bounds__(256) layernorm256_bf16_kernel(const __nv_bfloa
   *reinterpret_cast<uint4*>(y + yv.off(r) + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// fp32 rows -> bf16 rows with C % 128 == 0 (the ViT-H LayerNorms, C = 1280): lane l owns floats [128 i + 4 l, +4), 16-byte
+// loads and 8-byte stores instead of the 4 / 2-byte accesses of the generic kernel
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_f32_bf16_kernel(const float* __restrict__ x, RowView xv, __nv_bfloat16* __restrict__ y,
+                                                                     RowView yv, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, long long rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  s6_pdl_trigger();
+  s6_pdl_wait();
+  if (r >= rows) return;
+  const float* xp = x + xv.off(r) + lane * 4;
+  __nv_bfloat16* yp = y + yv.off(r) + lane * 4;
+  const int nv = C >> 7;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) { v[i] = *reinterpret_cast<const float4*>(xp + 128 * i); s += (v[i].x + v[i].y) + (v[i].z + v[i].w); }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (i < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + lane * 4 + 128 * i));
+      const __nv_bfloat162 lo = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&lo);
+      o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(yp + 128 * i) = o;
+    }
+}
+
 // F.normalize(x, p=2, dim=-1): x / max(||x||, 1e-12)   (PEM/utils/model_utils.py:124-126)
 template <int MAXV, typename OT = float>
 __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ x, RowView xv, OT* __restrict__ y, RowView yv,
@@ -215,6 +257,17 @@ S6_API int sam6d_layernorm_bf16(const float* x, long long x_rpb, long long x_bst
                                 float eps, void* stream) {
   S6_REQUIRE(x && y && gamma && beta && rows >= 0 && ROW_ARGS_OK(C));
   if (rows == 0) return 0;
+  if ((C % 128) == 0 && (x_ld % 4) == 0 && (y_ld % 4) == 0 && (x_bstride % 4) == 0 && (y_bstride % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0) {
+    const RowView xv{x_rpb, x_bstride, x_ld}, yv{y_rpb, y_bstride, y_ld};
+    __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y);
+    if (C <= 512) S6_CHECK(s6_launch_pdl(layernorm_vec_f32_bf16_kernel<4>, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, xv, yb, yv, gamma, beta, rows, C, eps));
+    else if (C <= 1280) S6_CHECK(s6_launch_pdl(layernorm_vec_f32_bf16_kernel<10>, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, xv, yb, yv, gamma, beta, rows, C, eps));
+    else S6_CHECK(s6_launch_pdl(layernorm_vec_f32_bf16_kernel<16>, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, xv, yb, yv, gamma, beta, rows, C, eps));
+    S6_LAUNCH_CHECK();
+    return 0;
+  }
   LN_DISPATCH(C, float, __nv_bfloat16, dim3(s6_cdiv(rows, 8)), dim3(256), 0, s6_stream(stream), x, RowView{x_rpb, x_bstride, x_ld},
               reinterpret_cast<__nv_bfloat16*>(y), RowView{y_rpb, y_bstride, y_ld}, gamma, beta, rows, C, eps);
   S6_LAUNCH_CHECK();

@@ -675,6 +675,22 @@ def attn_relpos(qkv: Tensor, nW: int, Hs: int, Ws: int, nH: int, rel_h: Tensor, 
 
 
 # ---------------------------------------------------------------------------------------------- ISM scoring
+def bilinear_gather(up: Tensor, choose: Tensor, G: int, sub: int, C: int, H: int, W: int) -> Tensor:
+    """up (B, G*G, sub*sub*C) fp32|bf16, choose (B,K) int64 -> (B,K,C) fp32: bilinear (align_corners=False) samples of the
+    (B,C,G*sub,G*sub) map the reference would upsample to (H,W), taken only at the chosen pixels"""
+    if up.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError("bilinear_gather: up must be float32 or bfloat16")
+    _check(up, up.dtype, "up", 3)
+    _check(choose, torch.int64, "choose", 2)
+    B, K = choose.shape
+    if up.shape != (B, G * G, sub * sub * C):
+        raise RuntimeError("bilinear_gather: shape mismatch")
+    out = torch.empty(B, K, C, dtype=torch.float32, device=up.device)
+    _lib.call("sam6d_bilinear_gather", _p(up), int(up.dtype == torch.bfloat16), _p(choose), int(B), int(K), int(G), int(sub), int(C),
+              int(H), int(W), _p(out), _s())
+    return out
+
+
 def template_score(Qn: Tensor, Rn: Tensor, want_sim: bool = True):
     """Qn (P,C), Rn (O,T,C): F.normalize'd descriptors -> sim (P,O,T), obj_score (P,O), best_obj, best_score, best_tmpl."""
     _check(Qn, torch.float32, "query", 2)

@@ -672,3 +672,14 @@ def test_fine_assign_tensor_core_fused(ops, B, S):
     assert torch.equal(lab2.cpu().long(), lab2_ref)
     torch.testing.assert_close(wts.cpu().double(), w_ref, atol=1e-6, rtol=2e-3)
     torch.testing.assert_close(pred.cpu().double(), pred_ref, atol=2e-5, rtol=2e-3)
+
+
+@pytest.mark.parametrize("C", [96, 256, 384, 1280, 2048])
+def test_layernorm_f32_to_bf16(ops, C):
+    """LayerNorm writing bf16 rows (A operand of the next GEMM): vector kernel for C % 128 == 0, generic otherwise"""
+    x = torch.randn(3, 41, C, generator=G(C)) * 2 + 0.5
+    g, b = torch.randn(C, generator=G(2)), torch.randn(C, generator=G(3))
+    ref = torch.nn.functional.layer_norm(x, (C,), g, b, eps=1e-6)
+    got = ops.layernorm_bf16(x.cuda(), g.cuda(), b.cuda(), eps=1e-6).cpu()
+    assert got.dtype == torch.bfloat16 and got.shape == x.shape
+    torch.testing.assert_close(got.float(), ref, atol=3e-2, rtol=1e-2)
