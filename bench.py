@@ -239,6 +239,9 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core exact path")
+    ap.add_argument("--rgb", action="store_true",
+                    help="PEM workload including the RGB branch (SURVEY 8f row N1): ViT-B/16 features of 224x224 crops + pixel "
+                         "gather replace the given dense_fm; not the BASELINE configuration, reported as its own workload name")
     ap.add_argument("--workload", default="pem", choices=["pem", "ism"],
                     help="pem: BASELINE config #2 (headline); ism: config #3, SAM ViT-H encoder + template scoring")
     args = ap.parse_args()
@@ -262,11 +265,26 @@ def main():
     dev = torch.device("cuda", local_rank)
     B = args.batch
 
-    net = Net(precision=args.precision).to(dev).eval()
-    net.load_state_dict(po.make_state_dict(seed=1), strict=True)
-    keys = ("pts", "dense_fm", "dense_po", "dense_fo", "model")
+    if args.rgb:
+        from oracle import vit_oracle as vo       # seeded weights only
+        from sam6d_b200.vit import ViTEncoder
+        enc = ViTEncoder(npoint=N_PTS, precision=args.precision)
+        enc.load_state_dict(vo.make_state_dict(seed=1), strict=True)
+        net = Net(feature_extraction=enc, precision=args.precision).to(dev).eval()
+        net.load_state_dict({**po.make_state_dict(seed=1), **{"feature_extraction." + k: v for k, v in enc.state_dict().items()}},
+                            strict=True)
+        keys = ("pts", "dense_po", "dense_fo", "model")
+    else:
+        net = Net(precision=args.precision).to(dev).eval()
+        net.load_state_dict(po.make_state_dict(seed=1), strict=True)
+        keys = ("pts", "dense_fm", "dense_po", "dense_fo", "model")
     host = [{k: v.pin_memory() for k, v in po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=100 + rank * 7 + s).items()
              if k in keys} for s in range(2)]
+    if args.rgb:
+        g_rgb = torch.Generator().manual_seed(5 + rank)
+        for h in host:
+            h["rgb"] = torch.randn(B, 3, 224, 224, generator=g_rgb).pin_memory()
+            h["rgb_choose"] = torch.randint(0, 224 * 224, (B, N_PTS), generator=g_rgb).pin_memory()
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -390,7 +408,7 @@ def main():
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
-            config=dict(workload=WORKLOAD, proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
+            config=dict(workload=WORKLOAD + ("+vitb_rgb_branch" if args.rgb else ""), proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
                         feat_dim=C_FEAT, model_points=N_MODEL, parallelism=f"proposal-sharded x{world}, 1 all-gather of poses",
                         cache="inputs+intermediates per step (>1 GB) exceed the 126 MB L2; two input sets alternate"),
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=world * B * sdist.POSE_FLOATS * 4,
