@@ -4,13 +4,16 @@
 
 Same constructor signature, same parameter names (so `sam_vit_h_4b8939.pth: image_encoder.*` loads unchanged), same
 forward contract: (B,3,1024,1024) normalised image -> (B,256,64,64).  The torch sub-modules are parameter containers; the
-forward runs sm_100a kernels through the C ABI:
-    every Linear / conv (patch embed 16x16/16, qkv, proj, MLP, neck 1x1 and 3x3 as 9 shifted GEMMs) -> sam6d_gemm_bf16
-                       (tcgen05, bf16 operands, fp32 accumulate; GELU / bias / residual / pos-embed add in the epilogue)
-                       or sam6d_gemm_f32 with precision='fp32'
-    LayerNorm / LayerNorm2d                                  -> sam6d_layernorm (channel-last rows)
+forward runs sm_100a kernels through the C ABI.  precision="bf16" (default):
+    every Linear (qkv, proj, MLP)        -> sam6d_gemm_tma (persistent TMA-fed tcgen05 GEMM; GELU / bias / fp32 residual in the
+                                            epilogue; the qkv projection writes V^T itself, sam6d_gemm_tma_vt)
+    LayerNorm                            -> sam6d_layernorm_bf16 (fp32 residual stream -> bf16 GEMM operand)
     window partition (pad 64 -> 70 AFTER norm1) / unpartition -> sam6d_gather_rows with a static index map (-1 = zero pad row)
-    attention + decomposed rel-pos bias                      -> sam6d_attn_relpos (flash-style, no HWxHW score tensor)
+    windowed attention (14 x 14 tokens)  -> sam6d_attn_tc with the decomposed rel-pos bias (tables from two extra MMAs)
+    global attention (64 x 64 tokens)    -> sam6d_attn_global_tc (online softmax, scores never leave TMEM)
+    patch embed 16x16/16, neck 1x1 and 3x3 (9 shifted GEMMs) -> sam6d_gemm_bf16 / sam6d_gemm_tma, LayerNorm2d -> sam6d_layernorm
+precision="fp32" keeps everything on the CUDA-core kernels (sam6d_gemm_f32, sam6d_attn_relpos: flash-style, no HW x HW score
+tensor) and is the exact-parity comparator (max error 8e-6 against the reference module).
 """
 from typing import Optional, Tuple, Type
 
