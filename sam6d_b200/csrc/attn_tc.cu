@@ -41,10 +41,20 @@ struct AttnArgs {
   float scale;
 };
 
+// COMPACT (head dim 64, no / dense bias: the PEM layers): P and the bias staging alias the Q / K slabs (dead once the score MMA
+// has completed) and O aliases the first columns of S in TMEM (dead once P is published), so a CTA needs 97 KB of shared memory
+// and 256 TMEM columns and two CTAs share an SM -- one CTA's serial load -> MMA -> softmax -> MMA -> store chain hides behind
+// the other's.
+template <int D, int BIAS_MODE>
+constexpr bool kCompact = (D == 64) && (BIAS_MODE == 0 || BIAS_MODE == 1);
+
 template <int D, int BIAS_MODE, typename OT>
-__global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
-                                                                 const __grid_constant__ CUtensorMap tmK,
-                                                                 const __grid_constant__ CUtensorMap tmVt, AttnArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                                             const __grid_constant__ CUtensorMap tmK,
+                                                                                             const __grid_constant__ CUtensorMap tmVt,
+                                                                                             AttnArgs a) {
+  constexpr bool COMPACT = kCompact<D, BIAS_MODE>;
+  constexpr uint32_t TM_O = COMPACT ? 0u : 256u, TM_COLS = COMPACT ? 256u : 512u;
   constexpr int DS = (D + 63) / 64;                 // 64-channel slabs of Q / K
   constexpr int Q_SLAB = QT * 128, V_SLAB = D * 128, P_SLAB = QT * 128;
   constexpr int Q_BYTES = DS * Q_SLAB, V_BYTES = 4 * V_SLAB;
@@ -52,10 +62,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
   const int K_BYTES = DS * K_SLAB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* q_s = smem;
+  // default layout: [Q][K][V^T][P][bias stage | rel tables];  COMPACT: [V^T][Q, K -> bias stage -> P]
+  uint8_t* q_s = COMPACT ? smem + V_BYTES : smem;
   uint8_t* k_s = q_s + Q_BYTES;
-  uint8_t* v_s = k_s + K_BYTES;                     // 4 slabs [D rows][64 keys]; V_SLAB is a multiple of 1024 for D = 64, 80
-  uint8_t* p_s = v_s + ((V_BYTES + 1023) & ~1023);  // 4 slabs [128 rows][64 keys]
+  uint8_t* v_s = COMPACT ? smem : k_s + K_BYTES;    // 4 slabs [D rows][64 keys]; V_SLAB is a multiple of 1024 for D = 64, 80
+  uint8_t* p_s = COMPACT ? q_s : v_s + ((V_BYTES + 1023) & ~1023);        // 4 slabs [128 rows][64 keys]
   float* bstage = reinterpret_cast<float*>(p_s + 4 * P_SLAB);             // BIAS_MODE 1/3: 4 warps x [32][33] bias tiles
   uint8_t* rel_s = p_s + 4 * P_SLAB;                                       // BIAS_MODE 2: rel_h, rel_w as UMMA B operands:
   constexpr int REL_SLAB = 32 * 128;                                       //   2 tables x DS slabs of [32 rows][64 ch] bf16
@@ -73,7 +84,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     tc::mbar_fence_init();
   }
   s6_pdl_trigger();
-  if (warp == 4) tc::tmem_alloc(&tmem_slot, 512);
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, TM_COLS);
   tc::tc_fence_before_sync();
   __syncthreads();
   tc::tc_fence_after_sync();
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
       const int ksteps = a.N1 / 16;
       for (int k = 0; k < ksteps; ++k) {
         const int s = k >> 2, kk = k & 3;
-        tc::umma_bf16(tmem_base + 256, tc::umma_desc_sw128(tc::smem_u32(p_s + s * P_SLAB) + kk * 32),
+        tc::umma_bf16(tmem_base + TM_O, tc::umma_desc_sw128(tc::smem_u32(p_s + s * P_SLAB) + kk * 32),
                       tc::umma_desc_sw128(tc::smem_u32(v_s + s * V_SLAB) + kk * 32), idesc2, k ? 1u : 0u);
       }
       tc::umma_commit(&o_full);
@@ -137,8 +148,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     float* my_tab = nullptr;
     (void)my_tab;
     const int nchunk = (a.N1 + 31) / 32;
-    // dense bias: a chunk's tile is fetched one chunk ahead (32 independent 128-byte requests per warp: for each of the warp's
-    // 32 rows the lanes read 32 consecutive columns), so its latency hides behind the previous chunk's arithmetic
+    // dense bias tile of a chunk: 32 independent 128-byte requests per warp (for each of the warp's 32 rows the lanes read 32
+    // consecutive columns), transposed through shared memory
     float bl[32];
     auto fetch_bias = [&](int c) {
       const int col = c * 32 + lane;
@@ -149,7 +160,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
         bl[rr] = (col < Sk) ? __ldg(a.bias + (rowbase + nn) * Sk + col) : 0.f;
       }
     };
-    if (BIAS_MODE == 1) fetch_bias(0);                                     // in flight while the loads and the score MMA run
     tc::mbar_wait(&s_full, 0);
     tc::tc_fence_after_sync();
     if (BIAS_MODE == 2) {
@@ -170,17 +180,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
     }
     // pass 1: x = (s + bias) * scale (+ rel-pos), row max; x is written back over S so pass 2 needs no bias
     float mx = -INFINITY;
-    float* my_stage = bstage + warp * (32 * 33);
+    // COMPACT: the warp's 32 x 32 tile lives in the rows of P slab 0 only this warp will write (XOR-swizzled, 4 KB exactly)
+    float* my_stage = COMPACT ? reinterpret_cast<float*>(p_s + warp * 32 * 128) : bstage + warp * (32 * 33);
+    auto st_w = [&](int rr, int col) { return COMPACT ? rr * 32 + (col ^ rr) : rr * 33 + col; };
     int kh_run = 0, kw_run = 0;                                            // (kh, kw) of the running key column, no div / mod
     for (int c = 0; c < nchunk; ++c) {
       float v[32];
       tc::tmem_ld32(t_addr + c * 32, v);
-      if (BIAS_MODE == 3) fetch_bias(c);
       if (BIAS_MODE == 1 || BIAS_MODE == 3) {
+        fetch_bias(c);
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) my_stage[rr * 33 + lane] = bl[rr];
+        for (int rr = 0; rr < 32; ++rr) my_stage[st_w(rr, lane)] = bl[rr];
         __syncwarp();
-        if (BIAS_MODE == 1 && c + 1 < nchunk) fetch_bias(c + 1);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
         float x = -INFINITY;
         if (col < Sk) {
           x = v[j];
-          if (BIAS_MODE == 1 || BIAS_MODE == 3) x += my_stage[lane * 33 + j];
+          if (BIAS_MODE == 1 || BIAS_MODE == 3) x += my_stage[st_w(lane, j)];
           x *= a.scale;
           if (BIAS_MODE == 2) {
             x += my_tab[kh_run] + my_tab[a.Hs + kw_run];
@@ -215,7 +226,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
           bl[rr] = (col < Sk) ? __ldg(a.bias + (rowbase + nn) * Sk + col) : 0.f;
         }
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr) my_stage[rr * 33 + lane] = bl[rr];
+        for (int rr = 0; rr < 32; ++rr) my_stage[st_w(rr, lane)] = bl[rr];
         __syncwarp();
       }
 #pragma unroll
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
         if (col < Sk) {
           float x = v[j];
           if (BIAS_MODE == 0) x *= a.scale;
-          if (BIAS_MODE == 3) x = (x + my_stage[lane * 33 + j]) * a.scale;
+          if (BIAS_MODE == 3) x = (x + my_stage[st_w(lane, j)]) * a.scale;
           p = __expf(x - mx);
         }
         sum += p;
@@ -256,7 +267,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
 #pragma unroll 1
     for (int c = 0; c < (D + 31) / 32; ++c) {
       float v[32];
-      tc::tmem_ld32(t_addr + 256 + c * 32, v);
+      tc::tmem_ld32(t_addr + TM_O + c * 32, v);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= inv;
       const int col0 = h * D + c * 32;
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) attn_tc_kernel(const __grid_co
   }
   tc::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem_base, 512);
+  if (warp == 4) tc::tmem_dealloc(tmem_base, TM_COLS);
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -306,6 +317,10 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   size_t smem = (size_t)DS * QT * 128 + (size_t)DS * a.N1 * 128 + (((size_t)4 * D * 128 + 1023) & ~(size_t)1023) + 4 * QT * 128 + 1024;
   if (BM == 2) smem += (size_t)QT * TW * sizeof(float) + (size_t)2 * DS * 32 * 128;
   if (BM == 1 || BM == 3) smem += (size_t)4 * 32 * 33 * sizeof(float);
+  if (kCompact<D, BM>) {                              // [V^T][max(Q + K, P)]
+    const size_t qk = (size_t)DS * QT * 128 + (size_t)DS * a.N1 * 128, pp = (size_t)4 * QT * 128;
+    smem = (size_t)4 * D * 128 + (qk > pp ? qk : pp) + 1024;
+  }
   if (smem > 227 * 1024) return S6_EINVAL;
   auto kern = attn_tc_kernel<D, BM, OT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
