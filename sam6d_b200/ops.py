@@ -196,7 +196,7 @@ _VT_CACHE = {}
 def _vt_buffer(rows: int, n1: int, device, slot: int) -> Tensor:
     """V^T operand buffers are reused across layers (stream order keeps producer and consumer apart); they are zeroed once so
     the key-padding columns, which the GEMM epilogue never writes, stay finite"""
-    key = (rows, n1, str(device), slot)
+    key = (rows, n1, str(device), slot, torch.cuda.current_stream(device).cuda_stream)   # one buffer per stream: no cross-stream reuse
     buf = _VT_CACHE.get(key)
     if buf is None:
         if len(_VT_CACHE) > 64:
