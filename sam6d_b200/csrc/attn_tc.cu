@@ -151,13 +151,16 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
     // dense bias tile of a chunk: 32 independent 128-byte requests per warp (for each of the warp's 32 rows the lanes read 32
     // consecutive columns), transposed through shared memory
     float bl[32];
+    // warp-uniform 64-bit base + 32-bit per-lane offsets: the 32 row loads need no per-thread 64-bit address arithmetic
+    // (with it the register allocator serialised them into a few dependent batches, see profiles/r01_attn_bias_notes.md)
+    const int wrow0 = min(n0 + warp * 32, a.Sq - 1), rows_ok = max(1, min(32, a.Sq - (n0 + warp * 32)));
+    const float* wbase = a.bias + (((size_t)b * a.H + h) * a.Sq + wrow0) * Sk;
     auto fetch_bias = [&](int c) {
       const int col = c * 32 + lane;
-      const size_t rowbase = ((size_t)b * a.H + h) * a.Sq;
 #pragma unroll
       for (int rr = 0; rr < 32; ++rr) {
-        const int nn = min(n0 + warp * 32 + rr, a.Sq - 1);
-        bl[rr] = (col < Sk) ? __ldg(a.bias + (rowbase + nn) * Sk + col) : 0.f;
+        const int off = min(rr, rows_ok - 1) * Sk + col;
+        bl[rr] = (col < Sk) ? __ldg(wbase + off) : 0.f;
       }
     };
     tc::mbar_wait(&s_full, 0);
