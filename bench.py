@@ -159,8 +159,7 @@ def run_reference(args):
 def run_ism(args):
     """BASELINE.json config #3: SAM ViT-H image encoder + 42-template cosine scoring on a batch of synthetic frames.
     Secondary line (the headline metric of the repo is the PEM poses/s line): python bench.py --workload ism"""
-    from oracle import sam_oracle as so, ism_oracle as io
-    from sam6d_b200 import _lib, ism
+    from sam6d_b200 import _lib, ism, synth
     from sam6d_b200.sam import build_image_encoder
     assert torch.cuda.is_available()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
@@ -174,9 +173,9 @@ def run_ism(args):
         for m in enc.modules():
             if isinstance(m, torch.nn.LayerNorm) or m.__class__.__name__ == "LayerNorm2d":
                 m.weight.fill_(1.0); m.bias.zero_()
-    host = [so.make_images(B=F_, seed=10 + s).pin_memory() for s in range(2)]
+    host = [synth.make_images(B=F_, seed=10 + s).pin_memory() for s in range(2)]
     resident = [h.to(dev) for h in host]
-    q, r = io.make_descriptors(P=F_ * P, O=O, T=T, C=1024, seed=3)
+    q, r = synth.make_descriptors(P=F_ * P, O=O, T=T, C=1024, seed=3)
     qd, rd = q.to(dev), r.to(dev)
     qh = q.pin_memory()
 
@@ -217,6 +216,7 @@ def run_ism(args):
                 roofline=dict(kernel="whole encoder (tcgen05 GEMMs + attention)", bound="tensor", achieved=ach, peak=pk["tensor"], unit="TFLOP/s",
                               frac=ach / pk["tensor"], traffic=None, peak_source=pk["source"] + " bf16_tflops_sustained"))
     if not args.no_cpu_baseline:
+        from oracle import sam_oracle as so                # CPU leg only: the oracle port is the thing timed here
         threads = host_threads()
         torch.set_num_threads(threads)
         sd = {k: v.detach().cpu() for k, v in enc.state_dict().items()}
@@ -251,7 +251,7 @@ def main():
         return run_ism(args)
 
     import torch.distributed as dist
-    from oracle import pem_oracle as po           # synthetic inputs + seeded weights only (generator, not a compute path)
+    from sam6d_b200 import synth                  # seeded weights + synthetic inputs (no oracle code on this arm)
     from sam6d_b200 import _lib, dist as sdist
     from sam6d_b200.pem import Net
 
@@ -266,19 +266,18 @@ def main():
     B = args.batch
 
     if args.rgb:
-        from oracle import vit_oracle as vo       # seeded weights only
         from sam6d_b200.vit import ViTEncoder
         enc = ViTEncoder(npoint=N_PTS, precision=args.precision)
-        enc.load_state_dict(vo.make_state_dict(seed=1), strict=True)
+        enc.load_state_dict(synth.make_vit_state_dict(seed=1), strict=True)
         net = Net(feature_extraction=enc, precision=args.precision).to(dev).eval()
-        net.load_state_dict({**po.make_state_dict(seed=1), **{"feature_extraction." + k: v for k, v in enc.state_dict().items()}},
+        net.load_state_dict({**synth.make_pem_state_dict(seed=1), **{"feature_extraction." + k: v for k, v in enc.state_dict().items()}},
                             strict=True)
         keys = ("pts", "dense_po", "dense_fo", "model")
     else:
         net = Net(precision=args.precision).to(dev).eval()
-        net.load_state_dict(po.make_state_dict(seed=1), strict=True)
+        net.load_state_dict(synth.make_pem_state_dict(seed=1), strict=True)
         keys = ("pts", "dense_fm", "dense_po", "dense_fo", "model")
-    host = [{k: v.pin_memory() for k, v in po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=100 + rank * 7 + s).items()
+    host = [{k: v.pin_memory() for k, v in synth.make_pem_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=100 + rank * 7 + s).items()
              if k in keys} for s in range(2)]
     if args.rgb:
         g_rgb = torch.Generator().manual_seed(5 + rank)
@@ -291,7 +290,7 @@ def main():
 
     def step_resident(i):
         ep = dict(resident[i % 2])
-        rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev, generator=gen)
+        rand = torch.rand(B, synth.N_PROPOSAL1 * 3, device=dev, generator=gen)
         out = net(ep, rand=rand)
         poses = sdist.pack_poses(out)
         return sdist.all_gather_poses(poses)
@@ -322,7 +321,7 @@ def main():
         torch.cuda.current_stream().wait_event(copied[i % 2])
         if i + 1 < args.steps:
             issue_copy(i + 1)
-        rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev, generator=gen)
+        rand = torch.rand(B, synth.N_PROPOSAL1 * 3, device=dev, generator=gen)
         out = net(dict(dev_in[i % 2]), rand=rand)
         poses = sdist.all_gather_poses(sdist.pack_poses(out))
         host_out.copy_(poses, non_blocking=True)

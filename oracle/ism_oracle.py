@@ -38,16 +38,4 @@ def compute_semantic_score(desc: torch.Tensor, ref_desc: torch.Tensor, confidenc
     return idx_sel, pred_obj, sem, best_template, scores, per_obj
 
 
-def make_descriptors(P=64, O=8, T=42, C=1024, seed=1):
-    """queries with planted matches: proposal p looks like template (p % T) of object (p % O), plus clutter proposals"""
-    g = torch.Generator().manual_seed(seed)
-    ref = torch.randn(O, T, C, generator=g)
-    obj_mean = torch.randn(O, 1, C, generator=g)
-    ref = ref + 1.5 * obj_mean
-    q = torch.empty(P, C)
-    for p in range(P):
-        if p % 5 == 4:
-            q[p] = torch.randn(C, generator=g)                     # clutter: should fall under the threshold
-        else:
-            q[p] = ref[p % O, (3 * p) % T] + 0.6 * torch.randn(C, generator=g)
-    return q, ref
+from sam6d_b200.synth import make_descriptors  # noqa: E402,F401  (synthetic descriptors: shared with bench.py)

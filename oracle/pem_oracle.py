@@ -438,110 +438,6 @@ def pem_forward(sd: SD, pts, dense_fm, dense_po, dense_fo, model,
 
 
 # --------------------------------------------------------------------------------------
-# seeded weights with the reference's state_dict layout
+# seeded weights and synthetic proposals: shared with bench.py, so they live in the product package (data, not algorithm)
 # --------------------------------------------------------------------------------------
-def _init_linear(sd: SD, name: str, out_f: int, in_f: int, g: torch.Generator, bias: bool = True):
-    bound = 1.0 / math.sqrt(in_f)
-    sd[name + ".weight"] = (torch.rand(out_f, in_f, generator=g) * 2 - 1) * bound
-    if bias:
-        sd[name + ".bias"] = (torch.rand(out_f, generator=g) * 2 - 1) * bound
-
-
-def _init_ln(sd: SD, name: str, c: int, g: torch.Generator):
-    sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-    sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
-
-
-def _init_geo_transformer(sd: SD, p: str, c: int, g: torch.Generator):
-    for li, kinds in ((0, "qkvp"), (1, "qkv")):
-        a = f"{p}.layers.{li}.attention"
-        for kch in kinds:
-            _init_linear(sd, f"{a}.attention.proj_{kch}", c, c, g)
-        _init_linear(sd, a + ".linear", c, c, g)
-        _init_ln(sd, a + ".norm", c, g)
-        o = f"{p}.layers.{li}.output"
-        _init_linear(sd, o + ".expand", 2 * c, c, g)
-        _init_linear(sd, o + ".squeeze", c, 2 * c, g)
-        _init_ln(sd, o + ".norm", c, g)
-
-
-def make_state_dict(seed: int = 1, c: int = 256, nblock: int = 3) -> SD:
-    """Seeded random weights under the reference's parameter names (matching path only).
-    BatchNorm running statistics and LayerNorm affine terms are randomised so that folding
-    and affine paths are exercised (freshly constructed reference modules would hide them)."""
-    g = torch.Generator().manual_seed(seed)
-    sd: SD = {}
-    sd["geo_embedding.embedding.div_term"] = torch.exp(torch.arange(0, c, 2).float() * (-math.log(10000.0) / c))
-    _init_linear(sd, "geo_embedding.proj_d", c, c, g)
-    _init_linear(sd, "geo_embedding.proj_a", c, c, g)
-    for stage in ("coarse_point_matching", "fine_point_matching"):
-        _init_linear(sd, stage + ".in_proj", c, c, g)
-        _init_linear(sd, stage + ".out_proj", c, c, g)
-        sd[stage + ".bg_token"] = torch.randn(1, 1, c, generator=g) * 0.02
-    for i in range(nblock):
-        _init_geo_transformer(sd, f"coarse_point_matching.transformers.{i}", c, g)
-        t = f"fine_point_matching.transformers.{i}"
-        _init_geo_transformer(sd, t + ".sparse_layer", c, g)
-        a = t + ".dense_layer.attention"
-        for kch in "qkv":
-            _init_linear(sd, f"{a}.attention.proj_{kch}", c, c, g)
-        sd[a + ".attention.scale"] = 0.2 * torch.randn(1, 1, c, generator=g)
-        _init_linear(sd, a + ".linear", c, c, g)
-        _init_ln(sd, a + ".norm", c, g)
-        o = t + ".dense_layer.output"
-        _init_linear(sd, o + ".expand", 2 * c, c, g)
-        _init_linear(sd, o + ".squeeze", c, 2 * c, g)
-        _init_ln(sd, o + ".norm", c, g)
-    pe = "fine_point_matching.PE"
-    for m in ("mlp1", "mlp2"):
-        dims = [6, 32, 64, 128]
-        for j in range(3):
-            lp = f"{pe}.{m}.layer{j}"
-            sd[lp + ".conv.weight"] = torch.randn(dims[j + 1], dims[j], 1, 1, generator=g) * math.sqrt(2.0 / dims[j])
-            sd[lp + ".normlayer.bn.weight"] = 1.0 + 0.1 * torch.randn(dims[j + 1], generator=g)
-            sd[lp + ".normlayer.bn.bias"] = 0.1 * torch.randn(dims[j + 1], generator=g)
-            sd[lp + ".normlayer.bn.running_mean"] = 0.1 * torch.randn(dims[j + 1], generator=g)
-            sd[lp + ".normlayer.bn.running_var"] = 0.5 + torch.rand(dims[j + 1], generator=g)
-            sd[lp + ".normlayer.bn.num_batches_tracked"] = torch.tensor(1)
-    sd[pe + ".mlp3.conv.weight"] = torch.randn(c, c, 1, generator=g) * math.sqrt(2.0 / c)
-    sd[pe + ".mlp3.conv.bias"] = 0.1 * torch.randn(c, generator=g)
-    return sd
-
-
-# --------------------------------------------------------------------------------------
-# synthetic proposals of the named shapes (SURVEY.md 8d, config #2)
-# --------------------------------------------------------------------------------------
-def random_rotation(B: int, g: torch.Generator) -> torch.Tensor:
-    q = torch.randn(B, 4, generator=g)
-    q = q / q.norm(dim=1, keepdim=True)
-    w, x, y, z = q.unbind(1)
-    return torch.stack([
-        1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
-        2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
-        2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], dim=1).view(B, 3, 3)
-
-
-def make_inputs(B: int = 2, n: int = FINE_NPOINT, c: int = 256, n_model: int = 1024, seed: int = 1):
-    """Synthetic RGB-D+CAD proposal batch: a blob-shaped CAD template cloud, an observed cloud that
-    is the template under a random rigid pose + 1 mm noise + 20% outliers, features correlated
-    through the ground-truth correspondence."""
-    g = torch.Generator().manual_seed(seed)
-    d = torch.randn(B, n + n_model, 3, generator=g)
-    d = d / d.norm(dim=2, keepdim=True)
-    bump = 1.0 + 0.3 * torch.sin(3.0 * d[..., 0:1]) * torch.cos(2.0 * d[..., 1:2]) + 0.2 * d[..., 2:3]
-    axes = 0.6 + 0.4 * torch.rand(B, 1, 3, generator=g)
-    size = 0.05 + 0.10 * torch.rand(B, 1, 1, generator=g)
-    surf = d * bump * axes * size
-    dense_po, model = surf[:, :n].contiguous(), surf[:, n:].contiguous()
-    R = random_rotation(B, g)
-    t = (torch.rand(B, 3, generator=g) * 0.2 - 0.1) + torch.tensor([0.0, 0.0, 0.8])
-    perm = torch.stack([torch.randperm(n, generator=g) for _ in range(B)])
-    src = torch.gather(dense_po, 1, perm.unsqueeze(2).expand(B, n, 3))
-    pts = src @ R.transpose(1, 2) + t.unsqueeze(1) + 0.001 * torch.randn(B, n, 3, generator=g)
-    n_out = n // 5
-    pts[:, :n_out] = pts[:, :n_out] + 0.05 * torch.randn(B, n_out, 3, generator=g)
-    latent = torch.randn(B, n, c, generator=g)
-    dense_fo = latent + 0.5 * torch.randn(B, n, c, generator=g)
-    dense_fm = torch.gather(latent, 1, perm.unsqueeze(2).expand(B, n, c)) + 0.5 * torch.randn(B, n, c, generator=g)
-    return dict(pts=pts.contiguous(), dense_fm=dense_fm.contiguous(), dense_po=dense_po, dense_fo=dense_fo.contiguous(),
-                model=model, gt_R=R, gt_t=t)
+from sam6d_b200.synth import make_pem_state_dict as make_state_dict, make_pem_inputs as make_inputs, random_rotation  # noqa: E402,F401

@@ -109,51 +109,5 @@ def image_encoder(sd: SD, img: torch.Tensor, num_heads: int, global_attn_indexes
     return layernorm2d(x, sd[prefix + "neck.3.weight"], sd[prefix + "neck.3.bias"])
 
 
-def make_state_dict(embed_dim=1280, depth=2, num_heads=16, global_attn_indexes=(1,), img_size=1024, patch=16, window=14,
-                    out_chans=256, seed=1) -> SD:
-    """seeded weights under the reference's names; rel-pos tables are NOT zero (the reference zero-inits them, which would
-    hide the bias path)"""
-    g = torch.Generator().manual_seed(seed)
-    hd = embed_dim // num_heads
-    grid = img_size // patch
-
-    def lin(name, o, i, bias=True, scale=None):
-        s = scale if scale is not None else 1.0 / math.sqrt(i)
-        sd[name + ".weight"] = torch.randn(o, i, generator=g) * s
-        if bias:
-            sd[name + ".bias"] = torch.randn(o, generator=g) * 0.02
-
-    sd: SD = {}
-    sd["patch_embed.proj.weight"] = torch.randn(embed_dim, 3, patch, patch, generator=g) / math.sqrt(3 * patch * patch)
-    sd["patch_embed.proj.bias"] = torch.randn(embed_dim, generator=g) * 0.02
-    sd["pos_embed"] = torch.randn(1, grid, grid, embed_dim, generator=g) * 0.02
-    for i in range(depth):
-        p = f"blocks.{i}"
-        size = grid if i in global_attn_indexes else window
-        for n in ("norm1", "norm2"):
-            sd[f"{p}.{n}.weight"] = 1.0 + 0.1 * torch.randn(embed_dim, generator=g)
-            sd[f"{p}.{n}.bias"] = 0.1 * torch.randn(embed_dim, generator=g)
-        lin(p + ".attn.qkv", 3 * embed_dim, embed_dim)
-        lin(p + ".attn.proj", embed_dim, embed_dim)
-        sd[p + ".attn.rel_pos_h"] = torch.randn(2 * size - 1, hd, generator=g) * 0.05
-        sd[p + ".attn.rel_pos_w"] = torch.randn(2 * size - 1, hd, generator=g) * 0.05
-        lin(p + ".mlp.lin1", 4 * embed_dim, embed_dim)
-        lin(p + ".mlp.lin2", embed_dim, 4 * embed_dim)
-    sd["neck.0.weight"] = torch.randn(out_chans, embed_dim, 1, 1, generator=g) / math.sqrt(embed_dim)
-    sd["neck.1.weight"] = 1.0 + 0.1 * torch.randn(out_chans, generator=g)
-    sd["neck.1.bias"] = 0.1 * torch.randn(out_chans, generator=g)
-    sd["neck.2.weight"] = torch.randn(out_chans, out_chans, 3, 3, generator=g) / math.sqrt(9 * out_chans)
-    sd["neck.3.weight"] = 1.0 + 0.1 * torch.randn(out_chans, generator=g)
-    sd["neck.3.bias"] = 0.1 * torch.randn(out_chans, generator=g)
-    return sd
-
-
-def make_images(B=1, size=1024, seed=1) -> torch.Tensor:
-    """Sam.preprocess-like input: normalised uint8 noise with smooth structure, padded region zero (frames are 640x480 ->
-    1024x768 -> pad to 1024^2, ISM/segment_anything/modeling/sam.py:164-174)"""
-    g = torch.Generator().manual_seed(seed)
-    img = torch.randint(0, 256, (B, 3, size * 3 // 4, size), generator=g).float()
-    mean = torch.tensor([123.675, 116.28, 103.53]).view(1, 3, 1, 1)
-    std = torch.tensor([58.395, 57.12, 57.375]).view(1, 3, 1, 1)
-    img = (img - mean) / std
-    return F.pad(img, (0, 0, 0, size - img.shape[2])).contiguous()
+# seeded weights / images: shared with bench.py (data, not algorithm)
+from sam6d_b200.synth import make_sam_state_dict as make_state_dict, make_images  # noqa: E402,F401

@@ -22,38 +22,7 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
-
-def make_state_dict(embed_dim=768, depth=12, out_dim=256, n_patches=196, num_classes=1000, seed=1, prefix="rgb_net.") -> SD:
-    g = torch.Generator().manual_seed(seed)
-    sd: SD = {}
-    v = prefix + "vit."
-
-    def lin(name, o, i, scale=None):
-        s = scale if scale is not None else 1.0 / math.sqrt(i)
-        sd[name + ".weight"] = (torch.rand(o, i, generator=g) * 2 - 1) * s
-        sd[name + ".bias"] = (torch.rand(o, generator=g) * 2 - 1) * s
-
-    def ln(name, c):
-        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
-
-    sd[v + "cls_token"] = torch.randn(1, 1, embed_dim, generator=g) * 0.02
-    sd[v + "pos_embed"] = torch.randn(1, n_patches + 1, embed_dim, generator=g) * 0.02
-    sd[v + "patch_embed.proj.weight"] = (torch.rand(embed_dim, 3, 16, 16, generator=g) * 2 - 1) / math.sqrt(768)
-    sd[v + "patch_embed.proj.bias"] = (torch.rand(embed_dim, generator=g) * 2 - 1) / math.sqrt(768)
-    for i in range(depth):
-        b = f"{v}blocks.{i}."
-        ln(b + "norm1", embed_dim)
-        lin(b + "attn.qkv", 3 * embed_dim, embed_dim)
-        lin(b + "attn.proj", embed_dim, embed_dim)
-        ln(b + "norm2", embed_dim)
-        lin(b + "mlp.fc1", 4 * embed_dim, embed_dim)
-        lin(b + "mlp.fc2", embed_dim, 4 * embed_dim)
-    ln(v + "norm", embed_dim)
-    if num_classes:
-        lin(v + "head", num_classes, embed_dim)
-    lin(prefix + "output_upscaling", 16 * out_dim, 4 * embed_dim)
-    return sd
+from sam6d_b200.synth import make_vit_state_dict as make_state_dict  # noqa: E402,F401  (seeded weights: shared with bench.py)
 
 
 def vit_forward(sd: SD, x: torch.Tensor, depth: int, num_heads: int, prefix="rgb_net.vit.") -> List[torch.Tensor]:
