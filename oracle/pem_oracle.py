@@ -169,8 +169,43 @@ def feature_similarity(f1: torch.Tensor, f2: torch.Tensor) -> torch.Tensor:
     return (f1 @ f2.transpose(1, 2)) / TEMP
 
 
-def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5):
-    """model_utils.py:287-363: R, t with ref ~= R src + t."""
+def _any_orth(a: torch.Tensor) -> torch.Tensor:
+    """unit vector orthogonal to the unit vectors a (n,3): a x e_k, k = the smallest |component| (first on ties)"""
+    ab = a.abs()
+    k = torch.where((ab[:, 0] <= ab[:, 1]) & (ab[:, 0] <= ab[:, 2]), 0, torch.where(ab[:, 1] <= ab[:, 2], 1, 2))
+    e = torch.nn.functional.one_hot(k, 3).to(a.dtype)
+    o = torch.linalg.cross(a, e)
+    return o / o.norm(dim=1, keepdim=True)
+
+
+def rank1_rotation(H: torch.Tensor) -> torch.Tensor:
+    """THE documented deviation from model_utils.py:352-358 (sam6d_b200/csrc/svd3.cuh: rank1_rotation).
+
+    H (n,3,3) float64 with one singular value above rounding noise: sigma u1 v1^T (u1 on the source side).  The reference's
+    R = V diag(1,1,det) U^T then rotates about the v1 axis by whatever angle LAPACK's noise-level second singular pair
+    implies.  The deterministic completion is the least rotation taking u1 to v1:
+        R = c I + [w]x + w w^T / (1 + c),  w = u1 x v1,  c = u1 . v1      (half turn about any_orth(u1) when c -> -1)."""
+    U, S, Vh = torch.linalg.svd(H)
+    u1, v1 = U[:, :, 0], Vh[:, 0, :]
+    c = (u1 * v1).sum(1)
+    w = torch.linalg.cross(u1, v1)
+    eye = torch.eye(3, dtype=H.dtype).expand_as(H)
+    K = torch.zeros_like(H)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
+    R = c[:, None, None] * eye + K + w[:, :, None] * w[:, None, :] / (1.0 + c).clamp_min(1e-300)[:, None, None]
+    flip = (1.0 + c) < 1e-9
+    if flip.any():
+        a = _any_orth(u1[flip])
+        R[flip] = 2.0 * a[:, :, None] * a[:, None, :] - torch.eye(3, dtype=H.dtype)
+    zero = ~(S[:, 0] > 0)
+    R[zero] = torch.eye(3, dtype=H.dtype)
+    return R
+
+
+def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5, rank1=None, rank0=None):
+    """model_utils.py:287-363: R, t with ref ~= R src + t.
+    rank1 / rank0 (bool masks over the batch, default None = the reference's behaviour for every element): elements
+    whose rotation the caller wants from the deterministic completion (rank1_rotation) / set to the identity."""
     bsz = src.shape[0]
     if weights is None:
         weights = torch.ones_like(src[:, :, 0])
@@ -184,6 +219,11 @@ def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5):
     eye = torch.eye(3).unsqueeze(0).repeat(bsz, 1, 1)
     eye[:, -1, -1] = torch.sign(torch.det(V @ Ut))
     R = V @ eye @ Ut
+    if rank1 is not None and rank1.any():
+        H64 = (src[rank1] - c_s[rank1]).double().permute(0, 2, 1) @ (weights[rank1] * (ref[rank1] - c_r[rank1])).double()
+        R[rank1] = rank1_rotation(H64).float()
+    if rank0 is not None and rank0.any():
+        R[rank0] = torch.eye(3)
     t = (c_r.permute(0, 2, 1) - R @ c_s.permute(0, 2, 1)).squeeze(2)
     return R, t
 
@@ -199,9 +239,23 @@ def soft_assignment(atten: torch.Tensor):
     return inner, w1, w2, lab1, lab2
 
 
+def _triplet_ranks(i1, i2, B, n1):
+    """(rank1, rank0) masks (B*n1,) of the hypotheses whose triplet repeats a point of either cloud: their centred points
+    are collinear (rank-1 cross-covariance), or a single point on one side (rank 0)."""
+    t1, t2 = i1.reshape(B * n1, 3), i2.reshape(B * n1, 3)
+    eq = lambda a: (a[:, 0] == a[:, 1]).int() + (a[:, 0] == a[:, 2]).int() + (a[:, 1] == a[:, 2]).int()  # noqa: E731
+    e1, e2 = eq(t1), eq(t2)
+    rank0 = (e1 == 3) | (e2 == 3)
+    return ~rank0 & ((e1 + e2) > 0), rank0
+
+
 def coarse_Rt(atten, pts1, pts2, model_pts, rand: Optional[torch.Tensor] = None,
-              n1: int = N_PROPOSAL1, n2: int = N_PROPOSAL2, return_debug: bool = False):
-    """compute_coarse_Rt, model_utils.py:187-246.  `rand` replaces torch.rand(B, 3*n1)."""
+              n1: int = N_PROPOSAL1, n2: int = N_PROPOSAL2, return_debug: bool = False, completion: str = "reference"):
+    """compute_coarse_Rt, model_utils.py:187-246.  `rand` replaces torch.rand(B, 3*n1).
+    completion="reference": every hypothesis through torch.svd like the reference.  completion="deterministic": the
+    rank-deficient hypotheses (triplets that repeat a point) get the rotation the CUDA path gives them (rank1_rotation /
+    identity) -- the one place where the reference's output is not a function of its inputs."""
+    assert completion in ("reference", "deterministic")
     B, N1, _ = pts1.shape
     N2 = pts2.shape[1]
     inner, w1, _, _, _ = soft_assignment(atten)
@@ -215,7 +269,11 @@ def coarse_Rt(atten, pts1, pts2, model_pts, rand: Optional[torch.Tensor] = None,
     i2 = (idx % N2).clamp(max=N2 - 1)
     p1 = torch.gather(pts1, 1, i1.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
     p2 = torch.gather(pts2, 1, i2.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
-    Rs, ts = weighted_procrustes(p2, p1, None, weight_thresh=0.5)
+    if completion == "deterministic":
+        r1, r0 = _triplet_ranks(i1, i2, B, n1)
+        Rs, ts = weighted_procrustes(p2, p1, None, weight_thresh=0.5, rank1=r1, rank0=r0)
+    else:
+        Rs, ts = weighted_procrustes(p2, p1, None, weight_thresh=0.5)
     Rs = Rs.reshape(B, n1, 3, 3)
     ts = ts.reshape(B, n1, 1, 3)
     p1 = p1.reshape(B, n1, 3, 3)
@@ -278,10 +336,11 @@ def coarse_features(sd: SD, f1, geo1, f2, geo2, prefix: str = "coarse_point_matc
 
 def coarse_point_matching(sd: SD, p1, f1, geo1, p2, f2, geo2, radius, model,
                           rand: Optional[torch.Tensor] = None, prefix: str = "coarse_point_matching",
-                          return_debug: bool = False):
+                          return_debug: bool = False, completion: str = "reference"):
     f1, f2 = coarse_features(sd, f1, geo1, f2, geo2, prefix)
     atten = feature_similarity(_lin(sd, prefix + ".out_proj", f1), _lin(sd, prefix + ".out_proj", f2))
-    init_R, init_t, dbg = coarse_Rt(atten, p1, p2, model / (radius.reshape(-1, 1, 1) + 1e-6), rand, return_debug=True)
+    init_R, init_t, dbg = coarse_Rt(atten, p1, p2, model / (radius.reshape(-1, 1, 1) + 1e-6), rand, return_debug=True,
+                                    completion=completion)
     if return_debug:
         return init_R, init_t, atten, dbg
     return init_R, init_t, atten
@@ -412,9 +471,11 @@ def fine_point_matching(sd: SD, p1, f1, geo1, idx1, p2, f2, geo2, idx2, radius, 
 # --------------------------------------------------------------------------------------
 def pem_forward(sd: SD, pts, dense_fm, dense_po, dense_fo, model,
                 rand: Optional[torch.Tensor] = None, coarse_npoint: int = COARSE_NPOINT,
-                return_stages: bool = False):
+                return_stages: bool = False, completion: str = "reference"):
     """pts (B,N,3) observed cloud, dense_fm (B,N,C) its features, dense_po/dense_fo the template
-    bank, model (B,Nm,3) CAD samples -> dict(init_R, init_t, pred_R, pred_t, pred_pose_score)."""
+    bank, model (B,Nm,3) CAD samples -> dict(init_R, init_t, pred_R, pred_t, pred_pose_score).
+    completion: see coarse_Rt ("reference" = the reference's behaviour; "deterministic" = the CUDA path's rule for
+    rank-deficient pose hypotheses, the single documented deviation)."""
     B = pts.shape[0]
     radius = torch.norm(dense_po, dim=2).max(1)[0]
     dense_pm = pts / (radius.reshape(-1, 1, 1) + 1e-6)
@@ -424,12 +485,26 @@ def pem_forward(sd: SD, pts, dense_fm, dense_po, dense_fo, model,
     geo_m = geo_embedding(sd, torch.cat([bg_point, sp_m], dim=1))
     sp_o, sf_o, idx_o = sample_pts_feats(dense_po, dense_fo, coarse_npoint)
     geo_o = geo_embedding(sd, torch.cat([bg_point, sp_o], dim=1))
+    first = "reference" if completion == "both" else completion
     init_R, init_t, atten_c, cdbg = coarse_point_matching(sd, sp_m, sf_m, geo_m, sp_o, sf_o, geo_o, radius, model, rand,
-                                                          return_debug=True)
+                                                          return_debug=True, completion=first)
     pred_R, pred_t, score, atten_f = fine_point_matching(
         sd, dense_pm, dense_fm, geo_m, idx_m, dense_po, dense_fo, geo_o, idx_o, radius, model,
         init_R, init_t, return_atten=True)
     out = dict(init_R=init_R, init_t=init_t, pred_R=pred_R, pred_t=pred_t, pred_pose_score=score)
+    if completion == "both":
+        # the same coarse score matrix through the deterministic completion; the fine stage is re-run only for the
+        # proposals whose initial pose changed (proposals are independent)
+        dR, dt, ddbg = coarse_Rt(atten_c, sp_m, sp_o, model / (radius.reshape(-1, 1, 1) + 1e-6), rand, return_debug=True,
+                                 completion="deterministic")
+        ch = ((dR - init_R).abs().amax(dim=(1, 2)) > 0) | ((dt - init_t).abs().amax(dim=1) > 0)
+        pR, pt, ps = pred_R.clone(), pred_t.clone(), score.clone()
+        if ch.any():
+            pR[ch], pt[ch], ps[ch] = fine_point_matching(
+                sd, dense_pm[ch], dense_fm[ch], geo_m[ch], idx_m[ch], dense_po[ch], dense_fo[ch], geo_o[ch], idx_o[ch],
+                radius[ch], model[ch], dR[ch], dt[ch])
+        out.update(det_init_R=dR, det_init_t=dt, det_pred_R=pR, det_pred_t=pt, det_pred_pose_score=ps,
+                   det_init_score=ddbg["best_score"], det_init_degenerate=ddbg["winner_degenerate"])
     if return_stages:
         out.update(fps_idx_m=idx_m, fps_idx_o=idx_o, sparse_pm=sp_m, sparse_po=sp_o, geo_m=geo_m, geo_o=geo_o,
                    atten_coarse=atten_c, atten_fine=atten_f, radius=radius,

@@ -125,15 +125,23 @@ __global__ void __launch_bounds__(128) coarse_hyp_kernel(const int* __restrict__
   if (hpt >= n1) return;
   const int* id = idx + ((size_t)b * n1 + hpt) * 3;
   float p1[3][3], p2[3][3];
+  int i1s[3], i2s[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     int v = id[k];
     int i1 = min(v / n, n - 1), i2 = min(v % n, n - 1);
+    i1s[k] = i1; i2s[k] = i2;
     const float* a = pts1 + ((size_t)b * n + i1) * 3;
     const float* c = pts2 + ((size_t)b * n + i2) * 3;
 #pragma unroll
     for (int d = 0; d < 3; ++d) { p1[k][d] = a[d]; p2[k][d] = c[d]; }
   }
+  // The triplet is drawn with replacement (model_utils.py:218-226).  A repeated point in either cloud leaves collinear
+  // centred points, i.e. a rank-1 cross-covariance (rank 0 when one cloud contributes a single point): svd3.cuh.
+  const int eq1 = (i1s[0] == i1s[1]) + (i1s[0] == i1s[2]) + (i1s[1] == i1s[2]);
+  const int eq2 = (i2s[0] == i2s[1]) + (i2s[0] == i2s[2]) + (i2s[1] == i2s[2]);
+  const bool rank0 = (eq1 == 3) || (eq2 == 3);
+  const bool rank1 = !rank0 && (eq1 + eq2 > 0);
   // weighted_procrustes(src = p2, ref = p1, weights = 1, thresh 0.5, eps 1e-5): w = 1 / (3 + 1e-5)
   const float w = 1.f / (3.f + 1e-5f);
   float cs[3], cr[3];
@@ -153,7 +161,14 @@ __global__ void __launch_bounds__(128) coarse_hyp_kernel(const int* __restrict__
       H[i][j] = s;
     }
   double Rd[3][3];
-  procrustes_rotation(H, Rd);
+  if (rank0) {   // H is zero up to the 1e-5 of the weight normalisation: the reference's svd(0) gives U = V = I
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Rd[i][j] = (i == j) ? 1.0 : 0.0;
+  } else {
+    procrustes_rotation(H, Rd, rank1);
+  }
   float R[3][3], t[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)

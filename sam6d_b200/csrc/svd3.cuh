@@ -54,8 +54,35 @@ __device__ __forceinline__ void any_orth(const double a[3], double o[3]) {
   o[0] /= n; o[1] /= n; o[2] /= n;
 }
 
-// H (row-major 3x3, double) -> R (row-major 3x3) as the reference's V diag(1,1,d) U^T
-__device__ inline void procrustes_rotation(const double H[3][3], double R[3][3]) {
+// Rank-1 cross-covariance (a hypothesis whose three sampled correspondences repeat a point: its centred points are
+// collinear).  Only the leading singular pair (u1 on the source side, v1 = direction of H^T u1 on the reference side) is
+// defined by the data; the reference's rotation about that axis is LAPACK / cuSOLVER rounding noise.  The single
+// documented deviation from model_utils.py:352-358: complete with the LEAST rotation that takes u1 to v1,
+//     R = c I + [w]x + w w^T / (1 + c),   w = u1 x v1,  c = u1 . v1
+// (invariant under the joint sign flip of the pair; for c -> -1 the half turn about a fixed axis orthogonal to u1).
+// oracle/pem_oracle.py: coarse_Rt(completion="deterministic") restates exactly this rule.
+__device__ inline void rank1_rotation(const double u1[3], const double v1[3], double R[3][3]) {
+  const double c = u1[0] * v1[0] + u1[1] * v1[1] + u1[2] * v1[2];
+  if (1.0 + c < 1e-9) {
+    double a[3];
+    any_orth(u1, a);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) R[i][j] = 2.0 * a[i] * a[j] - ((i == j) ? 1.0 : 0.0);
+    return;
+  }
+  double w[3];
+  cross3(u1, v1, w);
+  const double k = 1.0 / (1.0 + c);
+  R[0][0] = c + w[0] * w[0] * k;     R[0][1] = -w[2] + w[0] * w[1] * k; R[0][2] = w[1] + w[0] * w[2] * k;
+  R[1][0] = w[2] + w[1] * w[0] * k;  R[1][1] = c + w[1] * w[1] * k;     R[1][2] = -w[0] + w[1] * w[2] * k;
+  R[2][0] = -w[1] + w[2] * w[0] * k; R[2][1] = w[0] + w[2] * w[1] * k;  R[2][2] = c + w[2] * w[2] * k;
+}
+
+// H (row-major 3x3, double) -> R (row-major 3x3) as the reference's V diag(1,1,d) U^T.
+// rank1: the caller knows (from repeated sample indices) that H has a single singular value above rounding noise.
+__device__ inline void procrustes_rotation(const double H[3][3], double R[3][3], bool rank1 = false) {
   double S[3][3], V[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -92,6 +119,10 @@ __device__ inline void procrustes_rotation(const double H[3][3], double R[3][3])
     return;
   }
   u1[0] /= n1; u1[1] /= n1; u1[2] /= n1;
+  if (rank1) {  // R maps the source direction u1 onto the reference direction v1
+    rank1_rotation(u1, v1, R);
+    return;
+  }
   // Gram-Schmidt u2 against u1 (exactly orthogonal in exact arithmetic)
   double d12 = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];
   u2[0] -= d12 * u1[0]; u2[1] -= d12 * u1[1]; u2[2] -= d12 * u1[2];

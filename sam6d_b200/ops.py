@@ -398,6 +398,19 @@ def rpe_scores(E: Tensor, U: Tensor, u_ptr: Optional[int] = None, u_ld: int = 10
     return SP
 
 
+def rpe_scores_tc(E: Tensor, U: Tensor) -> Tensor:
+    """E (B,S,S,256) bf16, U (B*S, 1024) bf16 = the four folded per-head queries of every token -> (B,4,S,S) f32.
+    TMA + tcgen05 stream over E (csrc/rpe_tc.cu); S <= 200."""
+    _check(E, torch.bfloat16, "E", 4)
+    _check(U, torch.bfloat16, "U", 2)
+    B, S = E.shape[0], E.shape[1]
+    if U.shape != (B * S, 1024) or E.shape[3] != 256 or E.shape[2] != S:
+        raise RuntimeError("rpe_scores_tc: E (B,S,S,256), U (B*S,1024)")
+    SP = torch.empty(B, 4, S, S, dtype=torch.float32, device=E.device)
+    _lib.call("sam6d_rpe_scores_tc", _p(E), _p(U), B, S, _p(SP), _s())
+    return SP
+
+
 def mha_raw(q_ptr, q_ld, q_bs, k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, bias: Optional[Tensor], B, H, Sq, Sk, scale,
             o_ptr, o_ld, o_bs):
     _lib.call("sam6d_mha", ctypes.c_void_p(q_ptr), _ll(q_ld), _ll(q_bs), ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs),

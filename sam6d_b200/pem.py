@@ -246,8 +246,13 @@ class GeometricTransformer(nn.Module):
         d = C // NUM_HEADS
         x2d = x.view(B * S, C)
         qk, vt = ops.gemm_tma_vt(x2d, w["w_qkv"].bf16, w["b_qkv"], 2 * C, S)                        # (B*S, q|k) and V^T
-        u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                              # (B*S, 4*C) fp32
-        sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
+        if S <= 200 and emb.dtype == torch.bfloat16:
+            # the folded rel-pos queries as bf16 rows: B operand of the TMA / tcgen05 stream over E (csrc/rpe_tc.cu)
+            u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"], out_dtype=torch.bfloat16)                # (B*S, 4*C) bf16
+            sp = ops.rpe_scores_tc(emb, u)
+        else:
+            u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                          # (B*S, 4*C) fp32
+            sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
         hid = ops.attn_tc(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
         return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
 

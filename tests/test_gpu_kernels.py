@@ -207,6 +207,24 @@ def test_rpe_scores_and_mha(ops):
     torch.testing.assert_close(out.cpu(), ref, atol=2e-5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,S", [(2, 197), (3, 65), (5, 129), (1, 200), (64, 197)])
+def test_rpe_scores_tensor_core(ops, B, S):
+    """TMA + tcgen05 stream over E (csrc/rpe_tc.cu) against the einsum on the same bf16 operands; B = 64, S = 197 is the
+    launch shape of the bench step (more query rows than SMs: every CTA walks a range, both TMEM buffers and ring stages wrap)"""
+    E = (torch.randn(B, S, S, 256, generator=G(1)) * 0.7).bfloat16()
+    U = torch.randn(B * S, 1024, generator=G(2)).bfloat16()
+    got = ops.rpe_scores_tc(E.cuda(), U.cuda())
+    if B <= 8:
+        ref = torch.einsum("bnhc,bnmc->bhnm", U.float().view(B, S, 4, 256), E.float())
+        torch.testing.assert_close(got.cpu(), ref, atol=2e-3, rtol=1e-4)
+    else:   # compare on the device in fp32 (the reference einsum of the full shape is slow on the host)
+        ref = torch.einsum("bnhc,bnmc->bhnm", U.cuda().float().view(B, S, 4, 256), E.cuda().float())
+        torch.testing.assert_close(got, ref, atol=2e-3, rtol=1e-4)
+    # and the CUDA-core kernel agrees on the same operands
+    old = ops.rpe_scores(E.cuda(), U.cuda().float().view(B, S, 4, 256).contiguous())
+    torch.testing.assert_close(got, old, atol=2e-3, rtol=1e-4)
+
+
 def test_linear_attention(ops):
     sd = po.make_state_dict(seed=4)
     p = "fine_point_matching.transformers.0.dense_layer.attention.attention"
@@ -323,21 +341,24 @@ def test_hypotheses_topk_select(ops):
     idx = (i1 * n + i2).int()
     p1 = torch.gather(pts1, 1, i1.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
     p2 = torch.gather(pts2, 1, i2.unsqueeze(2).repeat(1, 1, 3)).reshape(B * n1, 3, 3)
-    Rs, ts = po.weighted_procrustes(p2, p1, None, weight_thresh=0.5)
+    # rank-deficient triplets (a repeated point on either side) follow the deterministic completion -- the one documented
+    # deviation (oracle: rank1_rotation); with it EVERY hypothesis is comparable
+    r1, r0 = po._triplet_ranks(i1, i2, B, n1)
+    assert 0.02 < r1.float().mean() < 0.2
+    Rs, ts = po.weighted_procrustes(p2, p1, None, weight_thresh=0.5, rank1=r1, rank0=r0)
     resid_ref = torch.norm((p1 - ts.unsqueeze(1)) @ Rs - p2, dim=2).mean(1).reshape(B, n1)
     Rt, resid = ops.coarse_hypotheses(idx.cuda(), pts1.cuda(), pts2.cuda())
     Rt, resid = Rt.cpu(), resid.cpu()
-    # degenerate triplets (repeated correspondences -> rank-deficient H) have no unique rotation in any SVD: exclude them
-    tri1 = i1.reshape(B, n1, 3)
-    tri2 = i2.reshape(B, n1, 3)
-    distinct = ((tri1[..., 0] != tri1[..., 1]) & (tri1[..., 0] != tri1[..., 2]) & (tri1[..., 1] != tri1[..., 2]) &
-                (tri2[..., 0] != tri2[..., 1]) & (tri2[..., 0] != tri2[..., 2]) & (tri2[..., 1] != tri2[..., 2]))
-    assert distinct.float().mean() > 0.9
     dR = (Rt[..., :9].reshape(B, n1, 3, 3) - Rs.reshape(B, n1, 3, 3)).abs().amax(dim=(2, 3))
     dt = (Rt[..., 9:] - ts.reshape(B, n1, 3)).abs().amax(dim=2)
-    assert dR[distinct].quantile(0.999).item() < 2e-3 and dR[distinct].median().item() < 1e-5
-    assert dt[distinct].quantile(0.999).item() < 2e-3
-    torch.testing.assert_close(resid[distinct], resid_ref[distinct], atol=2e-5, rtol=1e-3)
+    deg = (r1 | r0).reshape(B, n1)
+    print(f"hypotheses: {int(deg.sum())} rank-deficient of {deg.numel()}; max dR on them {dR[deg].max().item():.2e}, "
+          f"on the others median {dR[~deg].median().item():.2e} / q99.9 {dR[~deg].quantile(0.999).item():.2e}")
+    assert dR[deg].max().item() < 1e-4 and dt[deg].max().item() < 1e-4
+    # full-rank triplets: the reference's fp32 svd against the fp64 Jacobi (nearly collinear triplets are ill-conditioned)
+    assert dR[~deg].quantile(0.999).item() < 2e-3 and dR[~deg].median().item() < 1e-5
+    assert dt[~deg].quantile(0.999).item() < 2e-3
+    torch.testing.assert_close(resid, resid_ref, atol=2e-5, rtol=1e-3)
     # top-k: same set as torch.topk on the same values, ascending (value, index) order
     top = ops.topk_smallest(resid.cuda(), n2).cpu().long()
     vals = torch.gather(resid, 1, top)
@@ -362,16 +383,37 @@ def test_hypotheses_topk_select(ops):
     torch.testing.assert_close(Rb.cpu(), R, atol=2e-2, rtol=0)
 
 
-def test_procrustes_degenerate_is_finite(ops):
-    # all three correspondences identical / two identical: R must still be a proper rotation
-    pts1 = torch.randn(1, 10, 3, generator=G(1))
-    pts2 = torch.randn(1, 10, 3, generator=G(2))
-    idx = torch.tensor([[3 * 10 + 4] * 3 + [3 * 10 + 4, 3 * 10 + 4, 5 * 10 + 6] + [11, 23, 35]], dtype=torch.int32)
+def test_procrustes_rank_deficient_completion(ops):
+    """all three correspondences identical -> identity; two identical (either side, or both at different slots) -> the least
+    rotation taking the source direction onto the reference direction; compared with the oracle's restatement of the rule"""
+    g = G(1)
+    n = 10
+    pts1 = torch.randn(1, n, 3, generator=g)
+    pts2 = torch.randn(1, n, 3, generator=g)
+    f = lambda a, b: a * n + b      # noqa: E731  flat index of the correspondence (point a of cloud 1, point b of cloud 2)
+    trip = [[f(3, 4)] * 3, [f(3, 4), f(3, 4), f(5, 6)], [f(3, 4), f(3, 7), f(5, 6)], [f(1, 4), f(2, 4), f(5, 6)],
+            [f(1, 4), f(1, 5), f(2, 5)], [f(1, 2), f(1, 3), f(1, 4)], [f(1, 1), f(2, 3), f(3, 5)]]
+    idx = torch.tensor([sum(trip, [])], dtype=torch.int32)
+    n1 = len(trip)
     Rt, resid = ops.coarse_hypotheses(idx.cuda(), pts1.cuda(), pts2.cuda())
-    R = Rt.cpu()[0, :, :9].reshape(3, 3, 3)
+    R = Rt.cpu()[0, :, :9].reshape(n1, 3, 3)
     assert torch.isfinite(R).all() and torch.isfinite(resid).all()
-    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand(3, 3, 3), atol=1e-5, rtol=0)
-    torch.testing.assert_close(torch.det(R), torch.ones(3), atol=1e-5, rtol=0)
+    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand(n1, 3, 3), atol=1e-5, rtol=0)
+    torch.testing.assert_close(torch.det(R), torch.ones(n1), atol=1e-5, rtol=0)
+    i1, i2 = (idx.long() // n), (idx.long() % n)
+    r1, r0 = po._triplet_ranks(i1, i2, 1, n1)
+    assert r0.tolist() == [True, False, False, False, False, True, False]
+    assert r1.tolist() == [False, True, True, True, True, False, False]
+    p1 = pts1[0][i1.reshape(-1)].reshape(n1, 3, 3)
+    p2 = pts2[0][i2.reshape(-1)].reshape(n1, 3, 3)
+    Rs, ts = po.weighted_procrustes(p2, p1, None, weight_thresh=0.5, rank1=r1, rank0=r0)
+    torch.testing.assert_close(R, Rs, atol=1e-5, rtol=0)
+    torch.testing.assert_close(Rt.cpu()[0, :, 9:], ts, atol=1e-5, rtol=0)
+    torch.testing.assert_close(R[0], torch.eye(3), atol=0, rtol=0)
+    # the rank-1 rotation maps the source segment direction onto the reference segment direction
+    d2 = torch.nn.functional.normalize(pts2[0, 6] - pts2[0, 4], dim=0)
+    d1 = torch.nn.functional.normalize(pts1[0, 5] - pts1[0, 3], dim=0)
+    torch.testing.assert_close(R[1] @ d2, d1, atol=1e-5, rtol=0)
 
 
 # ------------------------------------------------------------------------------------------------- fine stage pieces
@@ -425,6 +467,25 @@ def test_template_score(ops, P, O, T):
     assert torch.equal(g_t.cpu(), best_t)                         # bit-exact argmax template indices
     assert g_t.dtype == torch.int64 and g_obj.dtype == torch.int64
     torch.testing.assert_close(g_sem.cpu(), sem, atol=2e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["config5_ycbv", "config3_ism"])
+def test_template_score_matches_reference_golden(ops, golden_dir, case):
+    """the fused scoring kernel against the outputs of the reference's OWN PairwiseSimilarity / compute_semantic_score /
+    best_template_pose (tests/golden/ism_scoring.pt, tools/make_golden_ism.py): bit-exact object and template indices"""
+    import os
+    from sam6d_b200 import ism
+    c = torch.load(os.path.join(golden_dir, "ism_scoring.pt"), weights_only=False)["cases"][case]
+    q, r = io.make_descriptors(P=c["P"], O=c["O"], T=c["T"], C=c["C"], seed=c["seed"])
+    assert q.double().sum().item() == c["input_checksum"]["q"] and r.double().sum().item() == c["input_checksum"]["ref"]
+    scorer = ism.SemanticScorer(r.cuda())
+    g_sel, g_obj, g_sem, g_t = scorer.compute_semantic_score(q.cuda())
+    assert torch.equal(g_sel.cpu(), c["idx_selected"])
+    assert torch.equal(g_obj.cpu(), c["pred_idx_objects"])
+    assert torch.equal(g_t.cpu(), c["best_template"])
+    torch.testing.assert_close(g_sem.cpu(), c["semantic_score"], atol=2e-6, rtol=1e-5)
+    sim = scorer.matching_config.metric(q.cuda(), r.cuda()).cpu()
+    torch.testing.assert_close(sim, c["sim"], atol=2e-6, rtol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------- tcgen05 GEMM

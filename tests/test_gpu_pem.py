@@ -78,7 +78,7 @@ def test_coarse_stage(net_and_sd):
     torch.manual_seed(1)
     rand = torch.rand(2, po.N_PROPOSAL1 * 3)
     R_ref, t_ref, att_ref, dbg = po.coarse_point_matching(sd, sp_m, sf_m, geo_m, sp_o, sf_o, geo_o, radius, inp["model"], rand,
-                                                          return_debug=True)
+                                                          return_debug=True, completion="deterministic")
     cpm = net.coarse_point_matching
     cpm.return_feat = True
     ep, o1, o2 = cpm(sp_m.cuda(), sf_m.cuda(), geo_m.cuda(), sp_o.cuda(), sf_o.cuda(), geo_o.cuda(), radius.cuda(),
@@ -87,8 +87,10 @@ def test_coarse_stage(net_and_sd):
     from sam6d_b200.pem import compute_feature_similarity
     att = compute_feature_similarity(o1, o2, "cosine", 0.1, True).cpu()
     torch.testing.assert_close(att, att_ref, atol=5e-3, rtol=0)          # cosine / 0.1 after 3 transformer blocks
-    _check_init_pose(ep["init_R"].cpu(), ep["init_t"].cpu(), cpm.last_select_scores.cpu(), R_ref, t_ref,
-                     dbg["winner_degenerate"], dbg["best_score"])
+    # every proposal, rank-deficient winners included (oracle with the deterministic completion)
+    torch.testing.assert_close(ep["init_R"].cpu(), R_ref, atol=R_TOL, rtol=0)
+    torch.testing.assert_close(ep["init_t"].cpu(), t_ref, atol=T_TOL, rtol=0)
+    torch.testing.assert_close(cpm.last_select_scores.cpu().max(1)[0], dbg["best_score"], atol=0, rtol=5e-3)
 
 
 def test_fine_stage(net_and_sd):
@@ -111,38 +113,58 @@ def test_fine_stage(net_and_sd):
     torch.testing.assert_close(ep["pred_pose_score"].cpu(), s_ref, atol=5e-3, rtol=0)
 
 
-def _check_init_pose(R, t, my_scores, R_ref, t_ref, ref_degenerate, ref_best_score):
-    """Initial pose parity.  When the reference's winning hypothesis has three distinct correspondences its rotation is
-    well defined and we must reproduce it to 1e-3.  When a correspondence repeats inside the winning triplet (about 3/4 of
-    the hypotheses the reference retains), H has a single singular value above fp32 noise and the reference's rotation is
-    whatever LAPACK makes of rounding noise (it differs between the reference's own CPU and CUDA paths): there we require a
-    proper rotation whose selection score is comparable, not the same noise."""
-    for b in range(R.shape[0]):
-        if not bool(ref_degenerate[b]):
-            torch.testing.assert_close(R[b], R_ref[b], atol=R_TOL, rtol=0)
-            torch.testing.assert_close(t[b], t_ref[b], atol=T_TOL, rtol=0)
-        else:
-            torch.testing.assert_close(R[b] @ R[b].t(), torch.eye(3), atol=1e-5, rtol=0)
-            assert my_scores[b].max().item() >= 0.8 * ref_best_score[b].item()
+def _pose_report(out, gold, tag):
+    """max |gpu - comparator| per proposal for the two comparators a golden holds:
+       det_*  the oracle with the deterministic completion of rank-deficient hypotheses -- holds on EVERY proposal;
+       plain  the reference modules' own output -- comparable where the completion does not change the reference's pick."""
+    B = gold["init_R"].shape[0]
+    err = lambda a, b: (a.cpu() - b).abs().reshape(B, -1).amax(dim=1)     # noqa: E731
+    rep = {}
+    for k in ("init_R", "init_t", "pred_R", "pred_t", "pred_pose_score"):
+        rep["det_" + k] = err(out[k], gold["det_" + k])
+        rep[k] = err(out[k], gold[k])
+    same = ((gold["det_init_R"] - gold["init_R"]).abs().reshape(B, -1).amax(dim=1) == 0) & \
+           ((gold["det_init_t"] - gold["init_t"]).abs().reshape(B, -1).amax(dim=1) == 0)
+    print(f"[{tag}] {B} proposals; vs deterministic-completion oracle: " +
+          ", ".join(f"{k} {rep['det_' + k].max().item():.2e}" for k in ("init_R", "init_t", "pred_R", "pred_t")) +
+          f"; vs unmodified reference on the {int(same.sum())} proposals it defines: " +
+          ", ".join(f"{k} {rep[k][same].max().item() if same.any() else 0.0:.2e}" for k in ("init_R", "init_t", "pred_R", "pred_t")))
+    return rep, same
 
 
-def _end_to_end(net, gold, inputs):
+def _assert_poses(out, gold, tag, min_reference_defined=0):
+    """the north-star bar (R, t within 1e-3) on ALL proposals against the deterministic-completion oracle, and against the
+    unmodified reference output on every proposal whose reference pose is a function of its inputs"""
+    rep, same = _pose_report(out, gold, tag)
+    for k, tol in (("init_R", R_TOL), ("init_t", T_TOL), ("pred_R", R_TOL), ("pred_t", T_TOL), ("pred_pose_score", 5e-3)):
+        bad = (rep["det_" + k] > tol).nonzero().flatten().tolist()
+        assert not bad, f"{tag}: {k} off the deterministic-completion oracle on proposals {bad}: {rep['det_' + k][bad].tolist()}"
+        bad = ((rep[k] > tol) & same).nonzero().flatten().tolist()
+        assert not bad, f"{tag}: {k} off the reference on proposals {bad}: {rep[k][bad].tolist()}"
+    assert int(same.sum()) >= min_reference_defined
+    R = out["pred_R"].cpu()
+    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand_as(R), atol=1e-5, rtol=0)
+    torch.testing.assert_close(torch.det(R), torch.ones(R.shape[0]), atol=1e-5, rtol=0)
+
+
+def _golden_inputs(gold):
+    m = gold["meta"]
+    inputs = gold.get("inputs") or po.make_inputs(B=m["B"], n=m["n"], seed=m["seed"])
+    for k, v in gold["input_checksum"].items():        # regenerated inputs are the ones the fixture was made from
+        assert inputs[k].double().sum().item() == v, f"seeded input {k} differs from the fixture's"
     rand = gold["rand"]
     if rand is None:
         torch.manual_seed(1)
-        rand = torch.rand(gold["meta"]["B"], po.N_PROPOSAL1 * 3)
+        rand = torch.rand(m["B"], po.N_PROPOSAL1 * 3)
+    return inputs, rand
+
+
+def _end_to_end(net, gold, tag, min_reference_defined=0):
+    inputs, rand = _golden_inputs(gold)
     ep = {k: inputs[k].cuda() for k in ("pts", "dense_fm", "dense_po", "dense_fo", "model")}
     out = net(ep, rand=rand.cuda())
-    deg = gold["init_degenerate"]
-    _check_init_pose(out["init_R"].cpu(), out["init_t"].cpu(), net.coarse_point_matching.last_select_scores.cpu(),
-                     gold["init_R"], gold["init_t"], deg, gold["init_score"])
-    well = ~deg                       # proposals whose reference pose is well defined: the 1e-3 bar of the north star
-    for k, tol in (("pred_R", R_TOL), ("pred_t", T_TOL), ("pred_pose_score", 5e-3)):
-        torch.testing.assert_close(out[k].cpu()[well], gold[k][well], atol=tol, rtol=0, msg=lambda m, k=k: f"{k}: {m}")
-    # the others start the fine stage from a different (equally arbitrary) roll angle: translation still agrees
-    torch.testing.assert_close(out["pred_t"].cpu()[deg], gold["pred_t"][deg], atol=2e-2, rtol=0)
-    R = out["pred_R"].cpu()
-    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand_as(R), atol=1e-5, rtol=0)
+    _assert_poses(out, gold, tag, min_reference_defined)
+    return out
 
 
 def test_net_matches_reference_golden_full(golden_dir):
@@ -152,7 +174,21 @@ def test_net_matches_reference_golden_full(golden_dir):
     m = gold["meta"]
     net = Net().cuda().eval()
     net.load_state_dict(po.make_state_dict(seed=m["seed"]), strict=True)
-    _end_to_end(net, gold, po.make_inputs(B=m["B"], n=m["n"], seed=m["seed"]))
+    _end_to_end(net, gold, "fp32 full")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config2_b32_matches_oracle(golden_dir, precision):
+    """BASELINE config #2 -- the bench workload itself: 32 proposals x 2048 scene points x 2048 template points through
+    Net.forward, init_R/t and pred_R/t within 1e-3 of the oracle on all 32 proposals (deterministic completion) and of the
+    reference modules' own output on the >= 16 proposals whose reference pose is well defined."""
+    from sam6d_b200.pem import Net
+    gold = torch.load(os.path.join(golden_dir, "pem_b32.pt"), weights_only=False)
+    m = gold["meta"]
+    assert (m["B"], m["n"], m["coarse_npoint"]) == (32, 2048, 196)
+    net = Net(precision=precision).cuda().eval()
+    net.load_state_dict(po.make_state_dict(seed=m["seed"]), strict=True)
+    _end_to_end(net, gold, f"{precision} config #2", min_reference_defined=16)
 
 
 def test_net_matches_reference_golden_small(golden_dir):
@@ -162,7 +198,7 @@ def test_net_matches_reference_golden_small(golden_dir):
     cfg = dict(DEFAULT_MODEL_CFG, coarse_npoint=m["coarse_npoint"], fine_npoint=m["n"])
     net = Net(cfg).cuda().eval()
     net.load_state_dict(po.make_state_dict(seed=m["seed"]), strict=True)
-    _end_to_end(net, gold, gold["inputs"])
+    _end_to_end(net, gold, "fp32 small")
     ep = {k: gold["inputs"][k].cuda() for k in ("pts", "dense_fm", "dense_po", "dense_fo", "model")}
     # FPS indices are part of the fixture: bit-exact
     from sam6d_b200 import ops
@@ -198,23 +234,13 @@ def test_batch_32_properties():
 
 def test_bf16_tensor_core_mode_matches_reference_golden(golden_dir):
     """precision='bf16' (tcgen05 kernels: bf16 operands, fp32 accumulation, bf16 geometric embedding): same poses within the
-    north-star tolerance on the proposals whose reference pose is well defined."""
+    north-star tolerance on every proposal."""
     from sam6d_b200.pem import Net
     gold = torch.load(os.path.join(golden_dir, "pem_full.pt"), weights_only=False)
     m = gold["meta"]
     net = Net(precision="bf16").cuda().eval()
     net.load_state_dict(po.make_state_dict(seed=m["seed"]), strict=True)
-    inputs = po.make_inputs(B=m["B"], n=m["n"], seed=m["seed"])
-    torch.manual_seed(1)
-    rand = torch.rand(m["B"], po.N_PROPOSAL1 * 3)
-    out = net({k: inputs[k].cuda() for k in ("pts", "dense_fm", "dense_po", "dense_fo", "model")}, rand=rand.cuda())
-    well = ~gold["init_degenerate"]
-    report = {k: (out[k].cpu() - gold[k]).abs().reshape(m["B"], -1).amax(dim=1).tolist() for k in ("init_R", "pred_R", "pred_t")}
-    print("bf16 mode |gpu - reference| per proposal:", report, "well-defined:", well.tolist())
-    torch.testing.assert_close(out["pred_R"].cpu()[well], gold["pred_R"][well], atol=R_TOL, rtol=0)
-    torch.testing.assert_close(out["pred_t"].cpu()[well], gold["pred_t"][well], atol=T_TOL, rtol=0)
-    R = out["pred_R"].cpu()
-    torch.testing.assert_close(R @ R.transpose(1, 2), torch.eye(3).expand_as(R), atol=1e-5, rtol=0)
+    _end_to_end(net, gold, "bf16 full")
 
 
 @pytest.mark.parametrize("B", [1, 3, 32])
