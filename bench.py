@@ -132,6 +132,48 @@ def cpu_oracle_throughput(reps: int, threads: int, nprop: int = 0):
     return nprop / (sum(times) / len(times)), times
 
 
+def same_box_reference(dev, B):
+    """the reference formulation on the SAME B200 -- (i) the reference algorithm (oracle port: the
+    reference's own torch ops) on .cuda() with the reference's own pointnet2 CUDA kernels (oracle/_ref) underneath, as
+    `ref_gpu_poses_per_s`; (ii) the reference `_ext` FPS / ball-query kernels timed next to ours on the bench shapes.
+    Checker / baseline code only: nothing here is on the product path."""
+    out = {}
+    try:
+        from oracle import pem_oracle as po, pn2
+        from sam6d_b200 import ops
+        ref = pn2._ref()
+        x = po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=1)["dense_po"].to(dev)
+        x2 = torch.cat([x, x.flip(1)], dim=0).contiguous()                      # 2B clouds, the launch shape of the step
+
+        def t_us(fn, reps=5):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return 1e3 * e0.elapsed_time(e1) / reps
+        out["fps_2048_to_196_us"] = dict(clouds=2 * B, reference_ext=t_us(lambda: ref.furthest_point_sampling(x2, 196)),
+                                         ours=t_us(lambda: ops.furthest_point_sampling(x2, 196)))
+        out["ball_query_r0.1x32_r0.2x64_us"] = dict(
+            clouds=2 * B, reference_ext=t_us(lambda: (ref.ball_query(x2, x2, 0.1, 32), ref.ball_query(x2, x2, 0.2, 64))),
+            ours=t_us(lambda: ops.ball_query_pair(x2, x2, 0.1, 32, 0.2, 64)))
+        sd = {k: v.to(dev) for k, v in po.make_state_dict(seed=1).items()}
+        inp = {k: v.to(dev) for k, v in po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=1).items()}
+        torch.manual_seed(1)
+        rand = torch.rand(B, po.N_PROPOSAL1 * 3, device=dev)
+        run = lambda: po.pem_forward(sd, inp["pts"], inp["dense_fm"], inp["dense_po"], inp["dense_fo"], inp["model"], rand=rand)  # noqa: E731
+        with torch.no_grad():
+            us = t_us(run, reps=2)
+        out["ref_gpu_poses_per_s"] = B / (us * 1e-6)
+        out["ref_gpu_ms_per_step"] = us * 1e-3
+        out["ref_gpu_note"] = ("reference algorithm (oracle port = the reference's torch ops, fp32, stock cuBLAS / cuSOLVER / eager kernels of "
+                               f"torch {torch.__version__}) + the reference's own pointnet2 CUDA kernels, {B} proposals per step on this GPU")
+    except Exception as e:                                                        # reported, never fatal for the bench line
+        out["unavailable"] = f"{type(e).__name__}: {e}"[:300]
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -236,6 +278,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the same-box reference lines (oracle port + reference _ext kernels on this GPU)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core exact path")
@@ -336,8 +379,9 @@ def main():
 
     def timed(fn, steps, profile_kernel=None):
         barrier()
-        if profile_kernel:
-            _lib.time_kernel(profile_kernel, True)
+        names = [profile_kernel] if isinstance(profile_kernel, str) else list(profile_kernel or [])
+        for nm in names:
+            _lib.time_kernel(nm, True)
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -348,10 +392,11 @@ def main():
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - l0
         kernel_ms = None
-        if profile_kernel:
-            ev = _lib.timed_events(profile_kernel)
-            kernel_ms = [a.elapsed_time(b) for a, b in ev]
-            _lib.time_kernel(profile_kernel, False)
+        if names:
+            kernel_ms = {}
+            for nm in names:
+                kernel_ms[nm] = [a.elapsed_time(b) for a, b in _lib.timed_events(nm)]
+                _lib.time_kernel(nm, False)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -372,8 +417,12 @@ def main():
     if sampler:
         sampler.start()
     ms, launches, _ = timed(step_resident, args.steps)
-    # dominant-kernel roofline: same steps again with CUDA events around every rpe_scores launch
-    _, _, kms = timed(step_resident, args.steps, profile_kernel="sam6d_rpe_scores")
+    # dominant-kernel roofline: same steps again with CUDA events around every launch of the kernels the roofline report names
+    # (the stream over E; the attention kernel that consumes its scores; the geometric-embedding kernel that writes E)
+    from sam6d_b200 import pem as _pem
+    rpe_name = "sam6d_rpe_scores_tc" if (args.precision == "bf16" and _pem.RPE_TC) else "sam6d_rpe_scores"
+    _, _, kall = timed(step_resident, args.steps, profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_geo_embed_tc"])
+    kms = kall[rpe_name]
     for i in range(2):
         step_e2e(i)
     torch.cuda.synchronize()
@@ -391,9 +440,30 @@ def main():
         # batched, so a launch streams the embedding of `clouds` point clouds exactly once
         clouds = B * 12 * args.steps // len(kms)
         e_bytes = clouds * S * S * 256 * e_size
-        alg_bytes = e_bytes + clouds * S * 1024 * 4 + clouds * 4 * S * S * 4
+        # algorithmic bytes of an RPE self-attention call = the pair embedding E read once + the token matrix
+        # (636 MB + 3.2 MB per 32-cloud call in bf16).  The score tensor that rpe_scores hands to the attention kernel is NOT
+        # algorithmic (it exists only because scores and softmax are two kernels) and is not counted.
+        alg_bytes = e_bytes + clouds * S * 256 * e_size
         k_avg_ms = sum(kms) / len(kms)
         achieved = alg_bytes / (k_avg_ms * 1e-3) / 1e9
+        # whole RPE attention = score stream + the tensor-core attention launch that adds them as a dense bias (every third
+        # sam6d_attn_tc call of a block: self, cross, cross)
+        att = kall.get("sam6d_attn_tc") or []
+        att_bias = att[0::3] if len(att) == 3 * len(kms) else []
+        att_avg_ms = sum(att_bias) / len(att_bias) if att_bias else None
+        attention_frac = alg_bytes / ((k_avg_ms + att_avg_ms) * 1e-3) / 1e9 / pk["hbm"] if att_avg_ms else None
+        geo = kall.get("sam6d_geo_embed_tc") or []
+        roofline_tensor = None
+        if geo:
+            geo_ms = sum(geo) / len(geo)                 # one call per step = both launches (distance pass + angle pass)
+            # SURVEY.md 8(d) "min" count: proj_a on the 3 angle rows of every pair, 2*B clouds (the distance projection can be folded)
+            flops_min = 2.0 * (2 * B) * S * S * 3 * 256 * 256
+            flops_issued = 2.0 * (2 * B) * S * S * 5 * 256 * 256          # 4 angle rows (1 padding) + 1 distance row per pair
+            roofline_tensor = dict(kernel="geo_embed_tc_kernel<1> + <0> (GeometricStructureEmbedding: writes E)", bound="tensor",
+                                   achieved=flops_min / (geo_ms * 1e-3) / 1e12, peak=pk["tensor"], unit="TFLOP/s",
+                                   frac=flops_min / (geo_ms * 1e-3) / 1e12 / pk["tensor"], avg_call_ms=geo_ms,
+                                   flops_min_per_call=flops_min, flops_issued_per_call=flops_issued,
+                                   share_of_step=sum(geo) / ms)
         value = world * B * args.steps / (ms * 1e-3)
         e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
         traffic = None
@@ -413,11 +483,14 @@ def main():
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=world * B * sdist.POSE_FLOATS * 4,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=launches,
-            roofline=dict(kernel=f"rpe_scores_kernel<{'bf16' if args.precision == 'bf16' else 'float'}> (PEM RPE attention, streams the geometric embedding)", bound="hbm",
+            roofline=dict(kernel=f"{rpe_name[6:]} ({'bf16' if args.precision == 'bf16' else 'fp32'} E; PEM RPE attention, streams the geometric embedding)", bound="hbm",
                           achieved=achieved, peak=pk["hbm"], unit="GB/s", frac=achieved / pk["hbm"], traffic=traffic,
                           peak_source=pk["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if pk["source"] == "measured" else "fallback 6650 GB/s",
                           algorithmic_bytes_per_launch=alg_bytes, clouds_per_launch=clouds, launches_timed=len(kms), avg_launch_ms=k_avg_ms,
-                          share_of_step=sum(kms) / ms),
+                          share_of_step=sum(kms) / ms,
+                          attention_frac=attention_frac, attention_avg_ms=(k_avg_ms + att_avg_ms) if att_avg_ms else None,
+                          attention_note="score stream + the attn_tc launch that consumes it (softmax, PV), same algorithmic bytes"),
+            roofline_tensor=roofline_tensor,
             clocks=sampler.summary() if sampler else None,
         )
         if world == 1 and not args.no_cpu_baseline:
@@ -427,6 +500,8 @@ def main():
             line["cpu_baseline"] = dict(value=val, unit=UNIT, cores=threads, kind="port",
                                         sample=f"{CPU_SAMPLE_B} of the {B} proposals, 2 timed passes after a 1-proposal warm-up, "
                                                f"{sum(times):.1f} s of CPU work, torch fp32 on {threads} threads")
+        if world == 1 and not args.no_ref_gpu:
+            line["same_box_reference"] = same_box_reference(dev, B)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -123,6 +123,33 @@ int sam6d_geo_embed_f32(const float* T, long long npairs, const float* div_term,
 int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div_term, const void* Wa_bf16, const void* Wd_bf16,
                        const float* bias, void* E, int e_is_bf16, void* stream);
 
+/* ---- PEM input builder (PEM/run_inference_custom.py:165-253 get_test_data; PEM/utils/data_utils.py:73-160) ----------- */
+
+/* Stage A, all P detections of a frame: uncompressed COCO RLE (column-major runs; rle_cum = cumulative run ends of every
+ * detection concatenated, rle_off (P+1) offsets) -> mask AND depth > 0 (P,H,W) u8; stats (P,12) i32 = [0..3] raw extremes,
+ * [4] pixel count, [5..8] get_bbox y1,y2,x1,x2, [9] points that survive the radius filter ||p - mean|| < thr;
+ * choose2 (P,cap) i32 crop-linear pixel indices and cloud2 (P,cap,3) f32 camera-frame points of the survivors, in the
+ * reference's order.  depth (H,W) f32 metres; fx, fy, cx, cy float64 intrinsics; cap >= min(H,W)^2; choose1 scratch. */
+int sam6d_inputs_stage_a(const int* rle_cum, const int* rle_off, int P, int H, int W, const float* depth, double fx, double fy,
+                         double cx, double cy, double thr, unsigned char* mask, int* stats, int cap, int* choose1, int* choose2,
+                         float* cloud2, void* stream);
+/* Stage B, the Q kept detections keep[q]: choose_idx (Q,ns) i32 sample indices (drawn by the host like the reference's
+ * np.random.choice) -> pts (Q,ns,3) f32, rgb_choose (Q,ns) i64 (get_resize_rgb_choose), rgb (Q,3,S,S) f32 = crop, channel
+ * flip, mask, cv2.INTER_LINEAR resize (uint8 fixed point, bit exact), ToTensor + Normalize; rgb_u8 (Q,S,S,3) or NULL. */
+int sam6d_inputs_stage_b(const int* stats, const int* keep, int Q, int H, int W, int cap, const int* choose2, const float* cloud2,
+                         const int* choose_idx, int ns, int S, const unsigned char* image, const unsigned char* mask, int mask_flag,
+                         float* pts, long long* rgb_choose, float* rgb, unsigned char* rgb_u8, void* stream);
+
+/* ---- fused transformer-layer tail (bf16 token stream) -------------------------------------------------------------- */
+
+/* out = LN2(y + relu(y We^T + be) Ws^T + bs),  y = LN1(hid Wo^T + bo + x): AttentionLayer / RPEAttentionLayer tail and
+ * AttentionOutput of PEM/model/transformer.py:176-197, 435-438 (and LinearAttentionLayer / LinearTransformerLayer :575-608)
+ * as one persistent TMA + tcgen05 kernel.  hid, x, out (M,256) bf16 with row strides ld_* (multiples of 8); Wo (256,256),
+ * We (512,256), Ws (256,512) bf16 row-major; bo, g1, b1, bs, g2, b2 (256) and be (512) f32; 16-byte aligned pointers. */
+int sam6d_transformer_tail_bf16(const void* hid, long long ld_hid, const void* x, long long ld_x, const void* Wo, const float* bo,
+                                const float* g1, const float* b1, const void* We, const float* be, const void* Ws, const float* bs,
+                                const float* g2, const float* b2, void* out, long long ld_out, int M, float eps, void* stream);
+
 /* ---- attention ---------------------------------------------------------------------------------------------------- */
 
 /* relative-position score term of RPEMultiHeadAttention (PEM/model/transformer.py:389-394) with proj_p folded into

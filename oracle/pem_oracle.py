@@ -83,7 +83,7 @@ def pairwise_sqdist(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 def sinusoidal_embedding(idx: torch.Tensor, d_model: int) -> torch.Tensor:
     """Interleaved [sin(w0 x), cos(w0 x), sin(w1 x), ...]; transformer.py:262-283."""
-    div = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    div = torch.exp(torch.arange(0, d_model, 2, device=idx.device).float() * (-math.log(10000.0) / d_model))
     om = idx.reshape(-1, 1, 1) * div.view(1, -1, 1)
     emb = torch.cat([torch.sin(om), torch.cos(om)], dim=2)
     return emb.view(*idx.shape, d_model)
@@ -189,16 +189,16 @@ def rank1_rotation(H: torch.Tensor) -> torch.Tensor:
     u1, v1 = U[:, :, 0], Vh[:, 0, :]
     c = (u1 * v1).sum(1)
     w = torch.linalg.cross(u1, v1)
-    eye = torch.eye(3, dtype=H.dtype).expand_as(H)
+    eye = torch.eye(3, dtype=H.dtype, device=H.device).expand_as(H)
     K = torch.zeros_like(H)
     K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -w[:, 2], w[:, 1], w[:, 2], -w[:, 0], -w[:, 1], w[:, 0]
     R = c[:, None, None] * eye + K + w[:, :, None] * w[:, None, :] / (1.0 + c).clamp_min(1e-300)[:, None, None]
     flip = (1.0 + c) < 1e-9
     if flip.any():
         a = _any_orth(u1[flip])
-        R[flip] = 2.0 * a[:, :, None] * a[:, None, :] - torch.eye(3, dtype=H.dtype)
+        R[flip] = 2.0 * a[:, :, None] * a[:, None, :] - torch.eye(3, dtype=H.dtype, device=H.device)
     zero = ~(S[:, 0] > 0)
-    R[zero] = torch.eye(3, dtype=H.dtype)
+    R[zero] = torch.eye(3, dtype=H.dtype, device=H.device)
     return R
 
 
@@ -216,14 +216,14 @@ def weighted_procrustes(src, ref, weights=None, weight_thresh=0.0, eps=1e-5, ran
     H = (src - c_s).permute(0, 2, 1) @ (weights * (ref - c_r))
     U, _, V = torch.svd(H)
     Ut = U.transpose(1, 2)
-    eye = torch.eye(3).unsqueeze(0).repeat(bsz, 1, 1)
+    eye = torch.eye(3, device=src.device).unsqueeze(0).repeat(bsz, 1, 1)
     eye[:, -1, -1] = torch.sign(torch.det(V @ Ut))
     R = V @ eye @ Ut
     if rank1 is not None and rank1.any():
         H64 = (src[rank1] - c_s[rank1]).double().permute(0, 2, 1) @ (weights[rank1] * (ref[rank1] - c_r[rank1])).double()
         R[rank1] = rank1_rotation(H64).float()
     if rank0 is not None and rank0.any():
-        R[rank0] = torch.eye(3)
+        R[rank0] = torch.eye(3, device=src.device)
     t = (c_r.permute(0, 2, 1) - R @ c_s.permute(0, 2, 1)).squeeze(2)
     return R, t
 
@@ -480,7 +480,7 @@ def pem_forward(sd: SD, pts, dense_fm, dense_po, dense_fo, model,
     radius = torch.norm(dense_po, dim=2).max(1)[0]
     dense_pm = pts / (radius.reshape(-1, 1, 1) + 1e-6)
     dense_po = dense_po / (radius.reshape(-1, 1, 1) + 1e-6)
-    bg_point = torch.ones(B, 1, 3) * 100
+    bg_point = torch.ones(B, 1, 3, device=pts.device) * 100
     sp_m, sf_m, idx_m = sample_pts_feats(dense_pm, dense_fm, coarse_npoint)
     geo_m = geo_embedding(sd, torch.cat([bg_point, sp_m], dim=1))
     sp_o, sf_o, idx_o = sample_pts_feats(dense_po, dense_fo, coarse_npoint)

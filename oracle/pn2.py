@@ -37,6 +37,22 @@ def lib():
     return _lib
 
 
+_ref_mod = None
+
+
+def _ref():
+    """CUDA tensors go to the REFERENCE's own kernels (oracle/_ref/pointnet2_ref_ext.so, built from /root/reference by
+    oracle/build_ref_ext.py): the oracle port then runs on the GPU exactly as the reference would ("reference on the same
+    B200" line of bench.py)."""
+    global _ref_mod
+    if _ref_mod is None:
+        from . import build_ref_ext
+        _ref_mod = build_ref_ext.load_module()
+        if _ref_mod is None:
+            raise RuntimeError("oracle/_ref/pointnet2_ref_ext.so not present: CUDA inputs need the reference extension")
+    return _ref_mod
+
+
 def _f32(t: torch.Tensor) -> np.ndarray:
     return np.ascontiguousarray(t.detach().cpu().to(torch.float32).numpy())
 
@@ -51,6 +67,8 @@ def _p(a: np.ndarray):
 
 def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor:
     """points (B,N,3) f32 -> (B,nsamples) i32.  sampling_gpu.cu:75-178."""
+    if points.is_cuda:
+        return _ref().furthest_point_sampling(points.contiguous(), int(nsamples))
     x = _f32(points)
     b, n, _ = x.shape
     out = np.zeros((b, nsamples), dtype=np.int32)
@@ -60,6 +78,8 @@ def furthest_point_sampling(points: torch.Tensor, nsamples: int) -> torch.Tensor
 
 def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """points (B,C,N) f32, idx (B,M) i32 -> (B,C,M).  sampling_gpu.cu:13-25."""
+    if points.is_cuda:
+        return _ref().gather_points(points.contiguous(), idx.contiguous())
     x, i = _f32(points), _i32(idx)
     b, c, n = x.shape
     m = i.shape[1]
@@ -70,6 +90,8 @@ def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 def ball_query(new_xyz: torch.Tensor, xyz: torch.Tensor, radius: float, nsample: int) -> torch.Tensor:
     """new_xyz (B,M,3), xyz (B,N,3) -> (B,M,nsample) i32.  ball_query_gpu.cu:14-49."""
+    if new_xyz.is_cuda:
+        return _ref().ball_query(new_xyz.contiguous(), xyz.contiguous(), float(radius), int(nsample))
     q, x = _f32(new_xyz), _f32(xyz)
     b, m, _ = q.shape
     n = x.shape[1]
@@ -80,6 +102,8 @@ def ball_query(new_xyz: torch.Tensor, xyz: torch.Tensor, radius: float, nsample:
 
 def group_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     """points (B,C,N), idx (B,np,ns) i32 -> (B,C,np,ns).  group_points_gpu.cu:13-33."""
+    if points.is_cuda:
+        return _ref().group_points(points.contiguous(), idx.contiguous())
     x, i = _f32(points), _i32(idx)
     b, c, n = x.shape
     _, npnt, ns = i.shape

@@ -12,6 +12,7 @@ _CTYPES = {
     "int": ctypes.c_int,
     "long long": ctypes.c_longlong,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
 }
 
 

@@ -263,6 +263,25 @@ def layernorm_bf16io(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5, 
     return out
 
 
+def transformer_tail_bf16(hid: Tensor, x: Tensor, wo: Tensor, bo: Tensor, g1: Tensor, b1: Tensor, we: Tensor, be: Tensor, ws: Tensor,
+                          bs: Tensor, g2: Tensor, b2: Tensor, out: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
+    """LN2(y + relu(y We^T + be) Ws^T + bs) with y = LN1(hid Wo^T + bo + x): the attention-layer tail + AttentionOutput of
+    transformer.py:176-197 as one persistent TMA / tcgen05 kernel (csrc/tail_tc.cu).  hid, x (M,256) bf16 -> (M,256) bf16."""
+    _check(hid, torch.bfloat16, "hid", 2)
+    _check(x, torch.bfloat16, "x", 2)
+    M = hid.shape[0]
+    if hid.shape[1] != 256 or x.shape != hid.shape or wo.shape != (256, 256) or we.shape != (512, 256) or ws.shape != (256, 512):
+        raise RuntimeError("transformer_tail_bf16: d_model 256, hidden 512")
+    for w in (wo, we, ws):
+        _check(w, torch.bfloat16, "weight", 2)
+    if out is None:
+        out = torch.empty_like(hid)
+    _check(out, torch.bfloat16, "out", 2)
+    _lib.call("sam6d_transformer_tail_bf16", _p(hid), _ll(256), _p(x), _ll(256), _p(wo), _p(bo), _p(g1), _p(b1), _p(we), _p(be), _p(ws),
+              _p(bs), _p(g2), _p(b2), _p(out), _ll(256), int(M), _f(eps), _s())
+    return out
+
+
 def gather_rows_bf16_f32(src: Tensor, idx: Tensor) -> Tensor:
     """out[b,j,:] = float(src[b, idx[b,j], :]) for a bf16 (b,n,c) token matrix; negative index -> zero row"""
     _check(src, torch.bfloat16, "src", 3)

@@ -13,6 +13,7 @@ hand-written sm_100a kernels through the C ABI (sam6d_b200/ops.py); inference on
 losses, pose-noise augmentation -- are out of scope), and there is no CPU path.
 """
 import math
+import os
 from types import SimpleNamespace
 from typing import Dict, Optional
 
@@ -27,6 +28,11 @@ NUM_HEADS = 4  # hard-coded in the reference (coarse_point_matching.py:31, fine_
 # "bf16": tcgen05 tensor-core kernels -- operands rounded to bf16, fp32 accumulation in TMEM, geometric embedding stored
 # in bf16.  Index-valued results (FPS, ball query, labels) and the pose solvers are identical in both modes.
 PRECISIONS = ("fp32", "bf16")
+# bf16 path: linear + residual + LayerNorm + FFN + LayerNorm of every transformer layer as one kernel (csrc/tail_tc.cu);
+# False = the five-launch form (GEMM, LayerNorm, GEMM, GEMM, LayerNorm) kept as its comparator
+FUSED_TAIL = os.environ.get("SAM6D_FUSED_TAIL", "1") != "0"
+# the relative-position score stream over E on TMA + tcgen05 (csrc/rpe_tc.cu); False = the CUDA-core kernel (csrc/attn.cu)
+RPE_TC = os.environ.get("SAM6D_RPE_TC", "1") != "0"
 
 
 class _W:
@@ -234,6 +240,9 @@ class GeometricTransformer(nn.Module):
     # ---- bf16 token stream (precision="bf16", both clouds in one allocation): every Linear is the persistent TMA GEMM, the
     # residual stream, LayerNorm inputs/outputs and the attention output are bf16, accumulation and statistics fp32.
     def _tail_bf16(self, x2d, hid, lw, out=None):
+        if FUSED_TAIL:
+            return ops.transformer_tail_bf16(hid, x2d, lw["wo"].bf16, lw["bo"], lw["g1"], lw["b1"], lw["we"].bf16, lw["be"],
+                                             lw["ws"].bf16, lw["bs"], lw["g2"], lw["b2"], out=out)
         bf = torch.bfloat16
         y = ops.gemm_tma(hid, lw["wo"].bf16, lw["bo"], residual=x2d, out_dtype=bf)
         y = ops.layernorm_bf16io(y, lw["g1"], lw["b1"])
@@ -246,7 +255,7 @@ class GeometricTransformer(nn.Module):
         d = C // NUM_HEADS
         x2d = x.view(B * S, C)
         qk, vt = ops.gemm_tma_vt(x2d, w["w_qkv"].bf16, w["b_qkv"], 2 * C, S)                        # (B*S, q|k) and V^T
-        if S <= 200 and emb.dtype == torch.bfloat16:
+        if RPE_TC and S <= 200 and emb.dtype == torch.bfloat16:
             # the folded rel-pos queries as bf16 rows: B operand of the TMA / tcgen05 stream over E (csrc/rpe_tc.cu)
             u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"], out_dtype=torch.bfloat16)                # (B*S, 4*C) bf16
             sp = ops.rpe_scores_tc(emb, u)
@@ -659,11 +668,15 @@ class SparseToDenseTransformer(nn.Module):
         ops.linattn_tc_raw(q.data_ptr() + C * 2, C, N1 * C, blob, KS, w["sp_scale"], B, N, x_att.data_ptr() + C * 2, C, N1 * C)
         x_att.view(B, N1, C)[:, 0, :] = 0                                   # bg rows: defined input for the GEMMs below
         t = w["tail"]
-        y = ops.gemm_tma(x_att, t["wo"].bf16, t["bo"], residual=x2d, out_dtype=bf)
-        y = ops.layernorm_bf16io(y, t["g1"], t["b1"])
-        h = ops.gemm_tma(y, t["we"].bf16, t["be"], act=1, out_dtype=bf)
-        z = ops.gemm_tma(h, t["ws"].bf16, t["bs"], residual=y, out_dtype=bf)
-        out = ops.layernorm_bf16io(z, t["g2"], t["b2"]).view(B, N1, C)
+        if FUSED_TAIL:
+            out = ops.transformer_tail_bf16(x_att, x2d, t["wo"].bf16, t["bo"], t["g1"], t["b1"], t["we"].bf16, t["be"], t["ws"].bf16,
+                                            t["bs"], t["g2"], t["b2"]).view(B, N1, C)
+        else:
+            y = ops.gemm_tma(x_att, t["wo"].bf16, t["bo"], residual=x2d, out_dtype=bf)
+            y = ops.layernorm_bf16io(y, t["g1"], t["b1"])
+            h = ops.gemm_tma(y, t["we"].bf16, t["be"], act=1, out_dtype=bf)
+            z = ops.gemm_tma(h, t["ws"].bf16, t["bs"], residual=y, out_dtype=bf)
+            out = ops.layernorm_bf16io(z, t["g2"], t["b2"]).view(B, N1, C)
         out[:, 0, :] = sparse[:, 0, :].to(bf)                               # replaced bg token (transformer.py:660-668)
         return out
 
@@ -874,7 +887,11 @@ class Net(nn.Module):
         return dense_pm, dense_fm.contiguous(), dense_po, end_points['dense_fo'].contiguous(), radius
 
     @torch.no_grad()
-    def forward(self, end_points, rand=None):
+    def forward(self, end_points, rand=None, init_pose=None):
+        """rand: the (B, 3*nproposal1) uniforms of compute_coarse_Rt (default: drawn like the reference).  init_pose = (R, t):
+        the fine stage starts from this pose instead of the coarse stage's (the coarse stage still runs and reports init_R /
+        init_t); used by the parity tests to hold the fine stage to the 1e-3 bar independently of the coarse stage's discrete
+        hypothesis selection."""
         if self.training:
             raise NotImplementedError("sam6d_b200 implements the inference path: call model.eval()")
         dense_pm, dense_fm, dense_po, dense_fo, radius = self._features(end_points)
@@ -899,6 +916,11 @@ class Net(nn.Module):
             geo_embedding_o = self.geo_embedding(torch.cat([bg_point, sparse_po], dim=1))
         end_points = self.coarse_point_matching(sparse_pm, sparse_fm, geo_embedding_m, sparse_po, sparse_fo, geo_embedding_o,
                                                 radius, end_points, rand=rand)
+        if init_pose is not None:
+            coarse_R, coarse_t = end_points['init_R'], end_points['init_t']
+            end_points['init_R'], end_points['init_t'] = init_pose[0].contiguous(), init_pose[1].contiguous()
         end_points = self.fine_point_matching(dense_pm, dense_fm, geo_embedding_m, fps_idx_m, dense_po, dense_fo,
                                               geo_embedding_o, fps_idx_o, radius, end_points)
+        if init_pose is not None:
+            end_points['init_R'], end_points['init_t'] = coarse_R, coarse_t
         return end_points

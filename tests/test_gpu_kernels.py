@@ -225,6 +225,33 @@ def test_rpe_scores_tensor_core(ops, B, S):
     torch.testing.assert_close(got, old, atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("M", [100, 128, 1000, 12608, 40000])
+def test_transformer_tail_fused(ops, M):
+    """csrc/tail_tc.cu against the same math in fp64 on the bf16-rounded operands (y and h rounded to bf16 where the kernel
+    rounds them): 12608 rows = the sparse stream of the bench step (one tile per SM), 40000 = several tiles per CTA"""
+    g = G(M)
+    bf = torch.bfloat16
+    hid = torch.randn(M, 256, generator=g).to(bf)
+    x = torch.randn(M, 256, generator=g).to(bf)
+    wo = (torch.randn(256, 256, generator=g) / 16).to(bf)
+    we = (torch.randn(512, 256, generator=g) / 16).to(bf)
+    ws = (torch.randn(256, 512, generator=g) / 22).to(bf)
+    bo, be, bs = (torch.randn(n, generator=g) * 0.1 for n in (256, 512, 256))
+    g1, g2 = (1 + 0.1 * torch.randn(256, generator=g) for _ in range(2))
+    b1, b2 = (0.1 * torch.randn(256, generator=g) for _ in range(2))
+    dev = lambda t: t.cuda()      # noqa: E731
+    got = ops.transformer_tail_bf16(dev(hid), dev(x), dev(wo), dev(bo), dev(g1), dev(b1), dev(we), dev(be), dev(ws), dev(bs), dev(g2),
+                                    dev(b2))
+    d = lambda t: t.cuda().double()   # noqa: E731
+    ln = torch.nn.functional.layer_norm
+    y = ln(d(hid) @ d(wo).t() + d(bo) + d(x), (256,), d(g1), d(b1), 1e-5).to(bf).double()
+    h = torch.relu(y @ d(we).t() + d(be)).to(bf).double()
+    ref = ln(y + h @ d(ws).t() + d(bs), (256,), d(g2), d(b2), 1e-5)
+    err = (got.double() - ref).abs()
+    # one bf16 rounding of an O(1) output (2^-8 relative), plus the occasional flipped rounding of y / h
+    assert err.max().item() < 6e-2 and err.mean().item() < 4e-3, (err.max().item(), err.mean().item())
+
+
 def test_linear_attention(ops):
     sd = po.make_state_dict(seed=4)
     p = "fine_point_matching.transformers.0.dense_layer.attention.attention"

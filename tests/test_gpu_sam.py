@@ -61,6 +61,32 @@ def test_image_encoder_matches_reference_golden(golden_dir, precision, atol):
     assert abs(out.double().sum().item() - gold["out_sum"]) < atol * out.numel() * 0.05
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_vit_h_32_blocks_matches_reference_golden(golden_dir, precision):
+    """the full SAM ViT-H of build_sam.py:14-21 (32 blocks, 4 global) on one 1024 x 1024 frame against the vendored reference
+    module's CPU output (tests/golden/sam_vith.pt, tools/make_golden.py sam_vith).  Seeded random weights are a worst case for
+    error growth (no trained-in contraction): the bounds below are the measured drift plus margin, stated relative to the
+    output's standard deviation."""
+    gold = torch.load(os.path.join(golden_dir, "sam_vith.pt"), weights_only=False)
+    cfg = gold["meta"]["cfg"]
+    assert cfg["depth"] == 32
+    enc = _encoder(cfg, precision)
+    enc.load_state_dict(so.make_state_dict(seed=gold["meta"]["seed"], **cfg), strict=True)
+    img = so.make_images(B=1, seed=gold["meta"]["img_seed"])
+    out = enc(img.cuda()).cpu()
+    ref = gold["out_sub"]
+    err = (out[:, :, ::4, ::4] - ref).abs()
+    rel_rms = (err.pow(2).mean().sqrt() / gold["out_std"]).item()
+    cos = torch.nn.functional.cosine_similarity(out[:, :, ::4, ::4].flatten(), ref.flatten(), dim=0).item()
+    print(f"SAM ViT-H 32 blocks {precision}: max err {err.max().item():.3e}, rms err / output std {rel_rms:.3e}, cosine {cos:.6f}, "
+          f"|ref| max {gold['out_abs_max']:.2f} std {gold['out_std']:.3f}")
+    assert torch.isfinite(out).all()
+    if precision == "fp32":
+        assert rel_rms < 2e-3 and cos > 0.99999
+    else:
+        assert rel_rms < 0.12 and cos > 0.993
+
+
 def test_image_encoder_batch_and_independence():
     """two frames in one batch give the same embeddings as one at a time (no cross-image leakage through the window maps)"""
     cfg = dict(embed_dim=1280, depth=2, num_heads=16, global_attn_indexes=(1,))
