@@ -26,6 +26,8 @@ extern "C" {
  * xyz (b,n,3) -> idx (b,m); idx[:,0] = 0; ties resolved exactly like the reference kernel.
  * temp: scratch (b,n) f32, required only when n > 4096. */
 int sam6d_fps(const float* xyz, int b, int n, int m, float* temp, int* idx, void* stream);
+/* the single-CTA general-n FPS kernel on its own (comparator of the cluster kernel that sam6d_fps uses for 4096 < n <= 212 992) */
+int sam6d_fps_single_cta(const float* xyz, int b, int n, int m, float* temp, int* idx, void* stream);
 
 /* _ext.gather_points (PN2/_ext_src/src/sampling.cpp:18-41, sampling_gpu.cu:13-25): points (b,c,n), idx (b,m) -> (b,c,m) */
 int sam6d_gather_points(const float* points, const int* idx, int b, int c, int n, int m, float* out, void* stream);
@@ -140,6 +142,30 @@ int sam6d_inputs_stage_b(const int* stats, const int* keep, int Q, int H, int W,
                          const int* choose_idx, int ns, int S, const unsigned char* image, const unsigned char* mask, int mask_flag,
                          float* pts, long long* rgb_choose, float* rgb, unsigned char* rgb_u8, void* stream);
 
+/* crop, channel flip, mask, cv2.INTER_LINEAR resize (uint8 fixed point, bit exact), ToTensor + Normalize for Q images of their
+ * own (the template renderings of _get_template, run_inference_custom.py:117-136): images (Q,H,W,3) u8, masks (Q,H,W) u8,
+ * bbox (Q,4) i32 = y1,y2,x1,x2 (square) -> rgb (Q,3,S,S) f32, rgb_u8 (Q,S,S,3) or NULL */
+int sam6d_crop_resize_normalize(const unsigned char* images, const unsigned char* masks, const int* bbox, int Q, int H, int W, int S,
+                                int mask_flag, float* rgb, unsigned char* rgb_u8, void* stream);
+
+/* ---- ISM proposal descriptors around the DINOv2 trunk (ISM/model/dinov2.py:131-258, ISM/utils/bbox_utils.py:89-126,
+ *      ISM/model/loss.py:46-77) ---------------------------------------------------------------------------------------- */
+
+/* process_rgb_proposals / process_masks_proposals for all P proposals: image (H,W,3) u8 RGB, masks (P,H,W) f32, boxes (P,4) i32
+ * xyxy -> rgb (P,3,T,T) f32 (ToTensor + Normalize, x mask, box crop, nearest resize to longer side T, centre pad) and / or
+ * pmask (P,T,T) f32 (same geometry); either output may be NULL */
+int sam6d_crop_resize_pad(const unsigned char* image, const float* masks, const int* boxes, int P, int H, int W, int T, float* rgb,
+                          float* pmask, void* stream);
+/* compute_cls_and_patch_features tail: patch token (p,t) = tokens + p*tok_bs + t*tok_ld (C f32); kept when the mean of its
+ * patch x patch block of pmask (P, G*patch, G*patch) exceeds thresh, then L2-normalised, else zero -> out_f32 / out_bf16
+ * (P, G*G, C) (either NULL), valid (P, G*G) u8 or NULL */
+int sam6d_masked_patch_normalize(const float* tokens, long long tok_ld, long long tok_bs, const float* pmask, int P, int G, int patch,
+                                 int C, float thresh, float* out_f32, void* out_bf16, unsigned char* valid, void* stream);
+/* MaskedPatch_MatrixSimilarity.compute_straight + compute_visible_ratio on sim (P,N,N) f32 = query patches x best-template
+ * patches^T (row stride sim_ld, batch stride sim_bs, N <= 256); qvalid (P,N) u8 -> appe (P) f32, vis (P) f32 */
+int sam6d_appearance_reduce(const float* sim, long long sim_ld, long long sim_bs, int P, int N, const unsigned char* qvalid, float thred,
+                            float* appe, float* vis, void* stream);
+
 /* ---- fused transformer-layer tail (bf16 token stream) -------------------------------------------------------------- */
 
 /* out = LN2(y + relu(y We^T + be) Ws^T + bs),  y = LN1(hid Wo^T + bo + x): AttentionLayer / RPEAttentionLayer tail and
@@ -170,6 +196,16 @@ int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* K, long
                   long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
                   const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
                   int out_is_bf16, long long out_ld, void* stream);
+/* sam6d_attn_tc (no bias) over a window of keys: batch b's keys are rows [b*k_brows + k_row0, +Sk) of K and columns
+ * [v_col0, +Sk) of its V^T rows; lse (B,H,Sq) f32 or NULL receives the log-sum-exp of the scaled scores */
+int sam6d_attn_tc_ex(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                     long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, float scale, int k_brows, int k_row0, int v_col0,
+                     float* lse, void* out, int out_is_bf16, long long out_ld, void* stream);
+/* folds one more key (row key_row of every batch's K rows, column key_col of its V^T rows) into the bf16 result of
+ * sam6d_attn_tc_ex using its lse: the 257-token sequences of DINOv2 ViT-L/14 (ISM/model/layers/attention.py:47-69) */
+int sam6d_attn_merge_key(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, int k_brows,
+                         int key_row, const void* Vt, long long vt_ld, int key_col, const float* lse, int B, int H, int Sq,
+                         float scale, void* out, long long out_ld, void* stream);
 /* V (tokens x channels, bf16 column slice at col0 of a (nB*L, ld) matrix) -> V^T (nB*C rows, N1 >= L keys), zero padded */
 int sam6d_transpose_tokens_bf16(const void* src, long long ld, int col0, int C, int nB, int L, int N1, void* out, void* stream);
 /* LinearAttention kv-first branch (PEM/model/transformer.py:552-559) */

@@ -39,6 +39,11 @@ struct AttnArgs {
   int Hs, Ws;            // BIAS_MODE 2 window grid
   int k_col0;            // column of K inside its matrix (per head: + h*D)
   float scale;
+  // extended form (sam6d_attn_tc_ex): the keys of batch b are rows [b*k_brows + k_row0, +Sk) of the K matrix and columns
+  // [v_col0, v_col0 + Sk) of its V^T rows; lse (B,H,Sq) receives max + log(sum) of the scaled scores (natural log), so that a
+  // caller can merge further keys (the 257th token of a DINOv2 sequence) into the result
+  int k_brows, k_row0, v_col0;
+  float* lse;
 };
 
 // COMPACT (head dim 64, no / dense bias: the PEM layers): P and the bias staging alias the Q / K slabs (dead once the score MMA
@@ -101,9 +106,9 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
 #pragma unroll
       for (int s = 0; s < DS; ++s) {
         tc::tma_load_2d(&tmQ, &load_bar, q_s + s * Q_SLAB, a.q_col0 + h * D + s * 64, b * a.Sq + n0);
-        tc::tma_load_2d(&tmK, &load_bar, k_s + s * K_SLAB, a.k_col0 + h * D + s * 64, b * a.Sk);
+        tc::tma_load_2d(&tmK, &load_bar, k_s + s * K_SLAB, a.k_col0 + h * D + s * 64, b * a.k_brows + a.k_row0);
       }
-      for (int s = 0; s < nslab; ++s) tc::tma_load_2d(&tmVt, &load_bar, v_s + s * V_SLAB, s * 64, (b * a.H + h) * D);
+      for (int s = 0; s < nslab; ++s) tc::tma_load_2d(&tmVt, &load_bar, v_s + s * V_SLAB, a.v_col0 + s * 64, (b * a.H + h) * D);
       tc::mbar_wait(&load_bar, 0);
       tc::tc_fence_after_sync();
       // ---------------------------------------------------------------- S = Q K^T
@@ -263,6 +268,7 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
     tc::mbar_wait(&o_full, 0);
     tc::tc_fence_after_sync();
     const float inv = 1.f / sum;
+    if (a.lse && n < a.Sq) a.lse[((size_t)b * a.H + h) * a.Sq + n] = mx + __logf(sum);
     float* stage = reinterpret_cast<float*>(p_s) + warp * epi::WARP_STAGE_FLOATS;   // P slabs are free once O is complete
     const int HD = a.H * D;
     const int row0 = b * a.Sq + n0 + warp * 32;
@@ -374,27 +380,29 @@ namespace {
 // bias_mode 0 none | 1 dense fp32 (B,H,Sq,Sk) | 2 decomposed rel-pos, Sq = Sk = Hs*Ws, rel_h = the two tables pre-packed as
 // bf16 UMMA slabs (sam6d_b200.ops.pack_rel_pos: 2 x ceil(D/64) x [32 rows][64 ch], 128-byte swizzle), rel_w unused;
 // bv (H*D) fp32 or NULL; out (B*Sq, H*D) fp32 or bf16 with row stride out_ld.  head_dim 64 or 80, Sk <= 256.
-S6_API int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
-                         long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
-                         const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
-                         int out_is_bf16, long long out_ld, void* stream) {
+namespace {
+int attn_tc_launch(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                   long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
+                   const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
+                   int out_is_bf16, long long out_ld, int k_brows, int k_row0, int v_col0, float* lse, void* stream) {
   S6_REQUIRE(Q && K && Vt && out && B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= MAXK);
   S6_REQUIRE((head_dim == 64 || head_dim == 80) && bias_mode >= 0 && bias_mode <= 3);
   S6_REQUIRE((q_ld % 8) == 0 && (k_ld % 8) == 0 && (vt_ld % 8) == 0 && (q_col0 % 8) == 0 && (k_col0 % 8) == 0);
+  S6_REQUIRE(k_brows >= k_row0 + Sk && k_row0 >= 0 && v_col0 >= 0);
   if (bias_mode == 1 || bias_mode == 3) S6_REQUIRE(bias != nullptr);
   if (bias_mode == 2) S6_REQUIRE(rel_h && Hs > 0 && Ws > 0 && Hs <= 16 && Ws <= 16 && Hs * Ws == Sk && Sq == Sk && (reinterpret_cast<uintptr_t>(rel_h) & 15) == 0);
   if (B == 0) return 0;
   S6_REQUIRE(B <= 65535 && H <= 65535);
   const int N1 = (Sk + 15) & ~15;
-  S6_REQUIRE(vt_ld >= N1);
+  S6_REQUIRE(vt_ld >= v_col0 + N1);
   CUtensorMap tq, tk, tv;
   int rc = make_map(&tq, Q, (long long)B * Sq, q_ld, q_ld, 64, QT);
   if (rc) return rc;
-  rc = make_map(&tk, K, (long long)B * Sk, k_ld, k_ld, 64, N1);
+  rc = make_map(&tk, K, (long long)B * k_brows, k_ld, k_ld, 64, N1);
   if (rc) return rc;
   rc = make_map(&tv, Vt, (long long)B * H * head_dim, vt_ld, vt_ld, 64, head_dim);
   if (rc) return rc;
-  AttnArgs a{bias, rel_h, rel_w, Q, q_ld, q_col0, bv, out, out_ld, H, Sq, Sk, N1, Hs, Ws, k_col0, scale};   // mode 2: rel_h = packed blob
+  AttnArgs a{bias, rel_h, rel_w, Q, q_ld, q_col0, bv, out, out_ld, H, Sq, Sk, N1, Hs, Ws, k_col0, scale, k_brows, k_row0, v_col0, lse};   // mode 2: rel_h = packed blob
   cudaStream_t st = s6_stream(stream);
 #define ATT_LAUNCH(DD, MM) (out_is_bf16 ? launch<DD, MM, __nv_bfloat16>(tq, tk, tv, a, B, st) : launch<DD, MM, float>(tq, tk, tv, a, B, st))
   if (head_dim == 64) {
@@ -408,4 +416,69 @@ S6_API int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* 
   if (bias_mode == 3) return ATT_LAUNCH(80, 3);
   return ATT_LAUNCH(80, 2);
 #undef ATT_LAUNCH
+}
+
+// out[b,n,h,:] <- (w_p out[b,n,h,:] + w_c v_c) / (w_p + w_c), w_p = exp(lse - m), w_c = exp(s_c - m), s_c = scale q.k_c: one more
+// key (row key_row of every batch, V^T column key_col) folded into an attention result that came with its log-sum-exp.
+// one warp per (b, n, h), head dim 64: lane l owns channels 2l, 2l+1.
+__global__ void __launch_bounds__(256) attn_merge_key_kernel(const __nv_bfloat16* __restrict__ Q, long long q_ld, int q_col0,
+                                                             const __nv_bfloat16* __restrict__ K, long long k_ld, int k_col0, int k_brows,
+                                                             int key_row, const __nv_bfloat16* __restrict__ Vt, long long vt_ld, int key_col,
+                                                             const float* __restrict__ lse, int B, int H, int Sq, float scale,
+                                                             __nv_bfloat16* __restrict__ out, long long out_ld) {
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  s6_pdl_trigger();
+  s6_pdl_wait();
+  if (w >= (long long)B * Sq * H) return;
+  const int h = (int)(w % H);
+  const long long bn = w / H;
+  const int n = (int)(bn % Sq), b = (int)(bn / Sq);
+  const __nv_bfloat162 q2 = *reinterpret_cast<const __nv_bfloat162*>(Q + (size_t)bn * q_ld + q_col0 + h * 64 + lane * 2);
+  const __nv_bfloat162 k2 = *reinterpret_cast<const __nv_bfloat162*>(K + ((size_t)b * k_brows + key_row) * k_ld + k_col0 + h * 64 + lane * 2);
+  float s = __bfloat162float(q2.x) * __bfloat162float(k2.x) + __bfloat162float(q2.y) * __bfloat162float(k2.y);
+  s = warp_sum(s) * scale;
+  const float l = lse[((size_t)b * H + h) * Sq + n];
+  const float m = fmaxf(l, s), wp = __expf(l - m), wc = __expf(s - m), inv = 1.f / (wp + wc);
+  const __nv_bfloat16* vrow = Vt + ((size_t)(b * H + h) * 64 + lane * 2) * vt_ld + key_col;
+  const float v0 = __bfloat162float(vrow[0]), v1 = __bfloat162float(vrow[vt_ld]);
+  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + (size_t)bn * out_ld + h * 64 + lane * 2);
+  const __nv_bfloat162 o2 = *o;
+  *o = __floats2bfloat162_rn((wp * __bfloat162float(o2.x) + wc * v0) * inv, (wp * __bfloat162float(o2.y) + wc * v1) * inv);
+}
+}  // namespace
+
+S6_API int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                         long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
+                         const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
+                         int out_is_bf16, long long out_ld, void* stream) {
+  return attn_tc_launch(Q, q_ld, q_col0, K, k_ld, k_col0, Vt, vt_ld, B, H, Sq, Sk, head_dim, bias_mode, bias, rel_h, rel_w, Hs, Ws, bv,
+                        scale, out, out_is_bf16, out_ld, Sk, 0, 0, nullptr, stream);
+}
+
+// sam6d_attn_tc without bias over a WINDOW of keys: batch b's keys are rows [b*k_brows + k_row0, +Sk) of K and columns
+// [v_col0, +Sk) of its V^T rows; lse (B,H,Sq) f32 (or NULL) receives the log-sum-exp of the scaled scores.
+S6_API int sam6d_attn_tc_ex(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                            long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, float scale, int k_brows, int k_row0, int v_col0,
+                            float* lse, void* out, int out_is_bf16, long long out_ld, void* stream) {
+  return attn_tc_launch(Q, q_ld, q_col0, K, k_ld, k_col0, Vt, vt_ld, B, H, Sq, Sk, head_dim, 0, nullptr, nullptr, nullptr, 0, 0, nullptr,
+                        scale, out, out_is_bf16, out_ld, k_brows, k_row0, v_col0, lse, stream);
+}
+
+// folds ONE more key (row key_row of every batch's K rows, column key_col of its V^T rows) into a bf16 attention result `out`
+// (B*Sq, H*64) produced by sam6d_attn_tc_ex with its lse: the 257-token sequences of DINOv2 ViT-L/14 (256 patch keys on the
+// tensor cores + the class token here).  head dim 64.
+S6_API int sam6d_attn_merge_key(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, int k_brows,
+                                int key_row, const void* Vt, long long vt_ld, int key_col, const float* lse, int B, int H, int Sq,
+                                float scale, void* out, long long out_ld, void* stream) {
+  S6_REQUIRE(Q && K && Vt && lse && out && B >= 0 && H > 0 && Sq > 0 && (q_ld % 2) == 0 && (k_ld % 2) == 0 && (out_ld % 2) == 0 &&
+             (q_col0 % 2) == 0 && (k_col0 % 2) == 0);
+  if (B == 0) return 0;
+  const long long warps = (long long)B * Sq * H;
+  S6_CHECK(s6_launch_pdl(attn_merge_key_kernel, dim3(s6_cdiv(warps, 8)), dim3(256), 0, s6_stream(stream),
+                         reinterpret_cast<const __nv_bfloat16*>(Q), q_ld, q_col0, reinterpret_cast<const __nv_bfloat16*>(K), k_ld, k_col0,
+                         k_brows, key_row, reinterpret_cast<const __nv_bfloat16*>(Vt), vt_ld, key_col, lse, B, H, Sq, scale,
+                         reinterpret_cast<__nv_bfloat16*>(out), out_ld));
+  S6_LAUNCH_CHECK();
+  return 0;
 }

@@ -215,19 +215,21 @@ __device__ __forceinline__ void lin_coef(int d, int n_src, int n_dst, bool horiz
   a1 = __float2int_rn(f * 2048.f);
 }
 
-// grid (S, Q); block S threads (one output pixel column each); out (Q,3,S,S) float32, also the uint8 crop (Q,S,S,3) if u8 != null
-__global__ void inp_crop_resize_kernel(const unsigned char* __restrict__ image, const unsigned char* __restrict__ mask,
-                                       const int* __restrict__ stats, const int* __restrict__ keep, int H, int W, int S, int mask_flag,
-                                       float* __restrict__ out, unsigned char* __restrict__ u8) {
-  const int q = blockIdx.y, p = keep[q], dy = blockIdx.x, dx = threadIdx.x;
+// grid (S, Q); block S threads (one output pixel column each); out (Q,3,S,S) float32, also the uint8 crop (Q,S,S,3) if u8 != null.
+// Item q: bbox row bbox[q_or_keep * bbox_ld .. +4) = y1,y2,x1,x2; mask plane midx = keep ? keep[q] : q; image q * image_stride.
+__global__ void inp_crop_resize_kernel(const unsigned char* __restrict__ image, long long image_stride, const unsigned char* __restrict__ mask,
+                                       const int* __restrict__ bbox, int bbox_ld, const int* __restrict__ keep, int H, int W, int S,
+                                       int mask_flag, float* __restrict__ out, unsigned char* __restrict__ u8) {
+  const int q = blockIdx.y, p = keep ? keep[q] : q, dy = blockIdx.x, dx = threadIdx.x;
   if (dx >= S) return;
-  const int* s = stats + p * ST;
-  const int y1 = s[5], x1 = s[7], n = s[6] - s[5];            // square crop
+  const int* s = bbox + (size_t)p * bbox_ld;
+  const int y1 = s[0], x1 = s[2], n = s[1] - s[0];            // square crop
   const unsigned char* m = mask + (size_t)p * H * W;
+  const unsigned char* img = image + (size_t)q * image_stride;
   auto px = [&](int yy, int xx, int c) -> int {               // crop[yy][xx][c] after [:, :, ::-1] and masking
     const int gy = y1 + yy, gx = x1 + xx;
     if (mask_flag && !m[gy * W + gx]) return 0;
-    return image[((size_t)gy * W + gx) * 3 + (2 - c)];
+    return img[((size_t)gy * W + gx) * 3 + (2 - c)];
   };
   int v[3];
   if (n == 2 * S) {                                           // OpenCV switches INTER_LINEAR to the 2x2 area average
@@ -296,7 +298,19 @@ S6_API int sam6d_inputs_stage_b(const int* stats, const int* keep, int Q, int H,
   cudaStream_t st = s6_stream(stream);
   inp_gather_kernel<<<dim3(s6_cdiv(ns, 256), Q), 256, 0, st>>>(stats, keep, cap, choose2, cloud2, choose_idx, ns, S, pts, rgb_choose);
   S6_LAUNCH_CHECK();
-  inp_crop_resize_kernel<<<dim3(S, Q), ((S + 31) / 32) * 32, 0, st>>>(image, mask, stats, keep, H, W, S, mask_flag, rgb, rgb_u8);
+  inp_crop_resize_kernel<<<dim3(S, Q), ((S + 31) / 32) * 32, 0, st>>>(image, 0, mask, stats + 5, ST, keep, H, W, S, mask_flag, rgb, rgb_u8);
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// The crop / resize / normalise step alone for Q images of their own (the 42 template renderings of _get_template,
+// run_inference_custom.py:117-136): images (Q,H,W,3) u8, masks (Q,H,W) u8, bbox (Q,4) i32 = y1,y2,x1,x2 (square).
+S6_API int sam6d_crop_resize_normalize(const unsigned char* images, const unsigned char* masks, const int* bbox, int Q, int H, int W, int S,
+                                       int mask_flag, float* rgb, unsigned char* rgb_u8, void* stream) {
+  S6_REQUIRE(images && masks && bbox && rgb && Q >= 0 && H > 0 && W > 0 && S > 0 && S <= 1024);
+  if (Q == 0) return 0;
+  inp_crop_resize_kernel<<<dim3(S, Q), ((S + 31) / 32) * 32, 0, s6_stream(stream)>>>(images, (long long)H * W * 3, masks, bbox, 4, nullptr,
+                                                                                  H, W, S, mask_flag, rgb, rgb_u8);
   S6_LAUNCH_CHECK();
   return 0;
 }

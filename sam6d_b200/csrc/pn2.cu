@@ -146,6 +146,98 @@ __global__ void __launch_bounds__(THREADS) fps_big_kernel(const float* __restric
   }
 }
 
+// Large clouds (the 210 000-point template bank of get_obj_feats, PEM/model/feature_extraction.py:170-181): one thread-block
+// CLUSTER per cloud.  Each of the CS CTAs keeps its slice of the points and running min-distances in shared memory (SoA, up to
+// 13 312 points = 208 KB), finds its local arg-max with two redux.sync per level on packed keys, publishes (distance bits, tie
+// key) into every CTA's distributed shared memory, and one barrier.cluster per round later each CTA reduces the CS entries on its
+// own -- no global-memory round trip, no grid sync.  The slots are double-buffered by round parity, so one cluster barrier per
+// round suffices.  Tie order as above (bs_ref = 512 for these sizes): key = 2^27 - ((bit-reversed (k mod 512) << 18) | k), k < 2^18.
+constexpr int FPSC_THREADS = 1024, FPSC_MAX_PER_CTA = 13 * 1024;
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(const void* local_smem, unsigned cta, unsigned long long v) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_smem), ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(ra), "l"(v) : "memory");
+}
+
+template <int CS>
+__global__ void __launch_bounds__(FPSC_THREADS, 1) fps_cluster_kernel(const float* __restrict__ xyz, int n, int m, int* __restrict__ idx) {
+  extern __shared__ float sm[];
+  __shared__ unsigned red_hi[2][FPSC_THREADS / 32], red_lo[2][FPSC_THREADS / 32];
+  __shared__ unsigned long long slot[2][CS];          // written by every CTA of the cluster through DSMEM
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned rank = cluster_ctarank();
+  const int b = blockIdx.x / CS;
+  const int chunk = (n + CS - 1) / CS;                // points [rank*chunk, min(n, (rank+1)*chunk)) live in this CTA
+  const int k0 = rank * chunk, cnt = max(0, min(chunk, n - k0));
+  float* sx = sm;
+  float* sy = sm + chunk;
+  float* sz = sm + 2 * chunk;
+  float* st = sm + 3 * chunk;
+  const float* p = xyz + (size_t)b * n * 3;
+  int* out = idx + (size_t)b * m;
+  for (int i = tid; i < cnt; i += FPSC_THREADS) {
+    const float* q = p + (size_t)(k0 + i) * 3;
+    sx[i] = q[0]; sy[i] = q[1]; sz[i] = q[2]; st[i] = 1e10f;
+  }
+  __syncthreads();
+  cluster_sync_all();                                 // every CTA's shared memory exists before anyone writes into it
+  int old = 0;
+  if (rank == 0 && tid == 0) out[0] = 0;
+  for (int j = 1; j < m; ++j) {
+    const float x1 = __ldg(p + (size_t)old * 3), y1 = __ldg(p + (size_t)old * 3 + 1), z1 = __ldg(p + (size_t)old * 3 + 2);
+    unsigned bh = 0u, bl = 0u;
+    for (int i = tid; i < cnt; i += FPSC_THREADS) {
+      const float d = sqdist_ref(x1, y1, z1, sx[i], sy[i], sz[i]);
+      const float d2 = fminf(d, st[i]);
+      st[i] = d2;
+      const unsigned k = (unsigned)(k0 + i);
+      const unsigned key = (1u << 27) - (((__brev(k & 511u) >> 23) << 18) | k);
+      const unsigned h = __float_as_uint(d2);
+      if (h > bh || (h == bh && key > bl)) { bh = h; bl = key; }
+    }
+    unsigned wh = __reduce_max_sync(0xffffffffu, bh);
+    unsigned wl = __reduce_max_sync(0xffffffffu, bh == wh ? bl : 0u);
+    const int buf = j & 1;
+    if (lane == 0) { red_hi[buf][warp] = wh; red_lo[buf][warp] = wl; }
+    __syncthreads();
+    if (warp == 0) {
+      bh = red_hi[buf][lane]; bl = red_lo[buf][lane];
+      wh = __reduce_max_sync(0xffffffffu, bh);
+      wl = __reduce_max_sync(0xffffffffu, bh == wh ? bl : 0u);
+      if (lane < CS) st_cluster_u64(&slot[buf][rank], (unsigned)lane, ((unsigned long long)wh << 32) | wl);
+    }
+    cluster_sync_all();
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int c = 0; c < CS; ++c) best = max(best, slot[buf][c]);   // (distance bits, tie key) in one unsigned compare
+    old = (int)(((1u << 27) - (unsigned)(best & 0xffffffffull)) & 0x3ffffu);
+    if (rank == 0 && tid == 0) out[j] = old;
+  }
+  cluster_sync_all();                                 // no CTA exits while a peer may still write into its slots
+}
+
+template <int CS>
+static int launch_fps_cluster(const float* xyz, int b, int n, int m, int* idx, cudaStream_t st) {
+  const int chunk = (n + CS - 1) / CS;
+  const size_t smem = (size_t)chunk * 4 * sizeof(float);
+  auto kern = fps_cluster_kernel<CS>;
+  S6_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (CS > 8) S6_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(b * CS); cfg.blockDim = dim3(FPSC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  S6_CHECK(cudaLaunchKernelEx(&cfg, kern, xyz, n, m, idx));
+  return 0;
+}
+
 static int ref_block_size(int n) {  // cuda_utils.h:20-24
   int p = 1;
   while (p * 2 <= n && p * 2 <= 512) p *= 2;
@@ -169,10 +261,29 @@ S6_API int sam6d_fps(const float* xyz, int b, int n, int m, float* temp, int* id
       S6_CHECK(cudaFuncSetAttribute(fps_reg_kernel<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       fps_reg_kernel<512, 8><<<b, 512, smem, st>>>(xyz, n, m, bs_ref, idx);
     }
+  } else if (n <= 8 * FPSC_MAX_PER_CTA) {
+    int rc = launch_fps_cluster<8>(xyz, b, n, m, idx, st);        // 4097 .. 106 496 points: 8 CTAs (portable cluster size)
+    if (rc) return rc;
+  } else if (n <= 16 * FPSC_MAX_PER_CTA) {
+    int rc = launch_fps_cluster<16>(xyz, b, n, m, idx, st);       // .. 212 992 points (the 42 x 5000 template bank): 16 CTAs
+    if (rc) {                                                     // a 16-CTA cluster needs a GPC with 16 free SMs: else one CTA
+      (void)cudaGetLastError();
+      S6_REQUIRE(temp != nullptr);
+      fps_big_kernel<1024><<<b, 1024, 0, st>>>(xyz, n, m, bs_ref, temp, idx);
+    }
   } else {
     S6_REQUIRE(temp != nullptr);
     fps_big_kernel<1024><<<b, 1024, 0, st>>>(xyz, n, m, bs_ref, temp, idx);
   }
+  S6_LAUNCH_CHECK();
+  return 0;
+}
+
+// the single-CTA general-n kernel on its own (comparator of the cluster kernel in tests / profiles); temp (b,n) f32 scratch
+S6_API int sam6d_fps_single_cta(const float* xyz, int b, int n, int m, float* temp, int* idx, void* stream) {
+  S6_REQUIRE(xyz && idx && temp && b >= 0 && n > 0 && m >= 0);
+  if (b == 0 || m == 0) return 0;
+  fps_big_kernel<1024><<<b, 1024, 0, s6_stream(stream)>>>(xyz, n, m, ref_block_size(n), temp, idx);
   S6_LAUNCH_CHECK();
   return 0;
 }

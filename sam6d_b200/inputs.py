@@ -143,3 +143,61 @@ def get_test_data(dets: List[Dict], whole_image: np.ndarray, depth_raw: np.ndarr
                model=torch.from_numpy(model_points).to(dev).unsqueeze(0).repeat(n, 1, 1),
                K=torch.tensor(np.asarray(cam_K, dtype=np.float64).reshape(3, 3), dtype=torch.float32, device=dev).unsqueeze(0).repeat(n, 1, 1))
     return ret, whole_image, frame.whole_points(), model_points, [dets[i] for i in keep]
+
+
+def _square_bbox(mask: np.ndarray):
+    """get_bbox (PEM/utils/data_utils.py:127-160) on a host mask"""
+    H, W = mask.shape
+    rows, cols = np.flatnonzero(mask.any(axis=1)), np.flatnonzero(mask.any(axis=0))
+    rmin, rmax, cmin, cmax = int(rows[0]), int(rows[-1]) + 1, int(cols[0]), int(cols[-1]) + 1
+    b = min(max(rmax - rmin, cmax - cmin), min(H, W))
+    cy, cx, hb = (rmin + rmax) // 2, (cmin + cmax) // 2, b // 2
+    rmin, rmax, cmin, cmax = cy - hb, cy + hb, cx - hb, cx + hb
+    if rmin < 0:
+        rmax, rmin = rmax - rmin, 0
+    if cmin < 0:
+        cmax, cmin = cmax - cmin, 0
+    if rmax > H:
+        rmin, rmax = rmin - (rmax - H), H
+    if cmax > W:
+        cmin, cmax = cmin - (cmax - W), W
+    return [rmin, rmax, cmin, cmax]
+
+
+def get_templates_from_arrays(rgbs: Sequence[np.ndarray], masks: Sequence[np.ndarray], xyzs_mm: Sequence[np.ndarray],
+                              n_sample_template_point: int = 5000, img_size: int = 224, rgb_mask_flag: bool = True, choose_idx=None,
+                              rng=None, device=None):
+    """_get_template (PEM/run_inference_custom.py:117-146) for all template views after their file reads: rgb (H,W,3) uint8 as
+    loaded, mask (H,W) uint8 (255 = object), xyz (H,W,3) object coordinates in mm.
+    -> (all_tem, all_tem_pts, all_tem_choose): lists of (1,3,S,S) f32, (1,n,3) f32, (1,n) int64 like get_templates (:149-162)"""
+    dev = torch.device(device if device is not None else "cuda")
+    T = len(rgbs)
+    H, W = masks[0].shape
+    m = np.stack([np.ascontiguousarray(x == 255) for x in masks])
+    bbox = np.asarray([_square_bbox(mm) for mm in m], dtype=np.int32)
+    img_d = torch.from_numpy(np.ascontiguousarray(np.stack(rgbs), dtype=np.uint8)).to(dev)
+    mask_d = torch.from_numpy(m.astype(np.uint8)).to(dev)
+    bbox_d = torch.from_numpy(bbox).to(dev)
+    rgb = torch.empty(T, 3, img_size, img_size, dtype=torch.float32, device=dev)
+    _lib.call("sam6d_crop_resize_normalize", _p(img_d), _p(mask_d), _p(bbox_d), T, H, W, img_size, int(rgb_mask_flag), _p(rgb), None, _stream())
+    rng = rng if rng is not None else np.random
+    all_tem, all_pts, all_choose = [], [], []
+    for t in range(T):
+        y1, y2, x1, x2 = bbox[t].tolist()
+        crop = mask_d[t, y1:y2, x1:x2].reshape(-1)
+        choose = torch.nonzero(crop, as_tuple=False).reshape(-1)                      # row-major, ascending like numpy's nonzero
+        n = int(choose.numel())
+        if choose_idx is not None:
+            ci = np.asarray(choose_idx[t])
+        else:
+            ci = rng.choice(np.arange(n), n_sample_template_point) if n <= n_sample_template_point else \
+                rng.choice(np.arange(n), n_sample_template_point, replace=False)
+        choose = choose[torch.from_numpy(np.ascontiguousarray(ci, dtype=np.int64)).to(dev)]
+        xyz = torch.from_numpy(np.ascontiguousarray(xyzs_mm[t][y1:y2, x1:x2, :], dtype=np.float32)).to(dev).reshape(-1, 3) / 1000.0
+        cw = x2 - x1
+        ratio_h, ratio_w = img_size / (y2 - y1), img_size / cw
+        rc = (torch.floor((choose // cw).double() * ratio_h) * img_size + torch.floor((choose % cw).double() * ratio_w)).long()
+        all_tem.append(rgb[t:t + 1])
+        all_pts.append(xyz[choose].unsqueeze(0))
+        all_choose.append(rc.unsqueeze(0))
+    return all_tem, all_pts, all_choose

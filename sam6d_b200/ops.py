@@ -56,6 +56,16 @@ def furthest_point_sampling(xyz: Tensor, m: int) -> Tensor:
     return idx
 
 
+def furthest_point_sampling_single_cta(xyz: Tensor, m: int) -> Tensor:
+    """the one-CTA general-n kernel (comparator of the cluster kernel that furthest_point_sampling uses for large clouds)"""
+    _check(xyz, torch.float32, "points", 3)
+    b, n, _ = xyz.shape
+    idx = torch.zeros(b, m, dtype=torch.int32, device=xyz.device)
+    temp = torch.empty(b, n, dtype=torch.float32, device=xyz.device)
+    _lib.call("sam6d_fps_single_cta", _p(xyz), b, n, int(m), _p(temp), _p(idx), _s())
+    return idx
+
+
 def gather_points(points: Tensor, idx: Tensor) -> Tensor:
     """_ext.gather_points: (B,C,N) f32, (B,M) i32 -> (B,C,M)."""
     _check(points, torch.float32, "points", 3)

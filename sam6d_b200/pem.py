@@ -855,6 +855,11 @@ class Net(nn.Module):
         self.fine_npoint = cfg.fine_npoint
         if feature_extraction is not None:
             self.feature_extraction = feature_extraction
+        elif hasattr(cfg, "feature_extraction"):
+            # `Net(cfg.model)` of the reference (PEM/config/base.yaml:18-24): the ViT-B RGB branch under the reference's module
+            # name, so that sam-6d-pem-base.pth loads strict=True and model.feature_extraction.get_obj_feats exists
+            from .vit import ViTEncoder
+            self.feature_extraction = ViTEncoder(cfg.feature_extraction, cfg.fine_npoint, precision)
         self.geo_embedding = GeometricStructureEmbedding(cfg.geo_embedding)
         self.coarse_point_matching = CoarsePointMatching(cfg.coarse_point_matching)
         self.fine_point_matching = FinePointMatching(cfg.fine_point_matching)

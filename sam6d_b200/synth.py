@@ -222,3 +222,67 @@ def make_vit_state_dict(embed_dim=768, depth=12, out_dim=256, n_patches=196, num
         lin(v + "head", num_classes, embed_dim)
     lin(prefix + "output_upscaling", 16 * out_dim, 4 * embed_dim)
     return sd
+
+
+def make_dinov2_state_dict(embed_dim=1024, depth=24, num_heads=16, patch=14, img_size=518, seed=1) -> SD:
+    """seeded weights under the names of `dinov2_vitl14_pretrain.pth` (DinoVisionTransformer, ISM/model/vision_transformer.py):
+    linear weights ~ trunc-normal-like N(0, 0.02) as the reference initialises them, but NON-trivial biases, LayerNorm affines and
+    LayerScale gammas (the reference's zero / one initial values would hide those code paths)"""
+    g = torch.Generator().manual_seed(seed)
+    C = embed_dim
+    n = (img_size // patch) ** 2
+    sd: SD = {}
+    sd["cls_token"] = torch.randn(1, 1, C, generator=g) * 0.02
+    sd["pos_embed"] = torch.randn(1, n + 1, C, generator=g) * 0.02
+    sd["mask_token"] = torch.zeros(1, C)
+    sd["patch_embed.proj.weight"] = torch.randn(C, 3, patch, patch, generator=g) * 0.02
+    sd["patch_embed.proj.bias"] = torch.randn(C, generator=g) * 0.02
+
+    def lin(name, o, i):
+        sd[name + ".weight"] = torch.randn(o, i, generator=g) * 0.02
+        sd[name + ".bias"] = torch.randn(o, generator=g) * 0.02
+
+    def ln(name):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(C, generator=g)
+        sd[name + ".bias"] = 0.05 * torch.randn(C, generator=g)
+
+    for i in range(depth):
+        p = f"blocks.{i}."
+        ln(p + "norm1")
+        lin(p + "attn.qkv", 3 * C, C)
+        lin(p + "attn.proj", C, C)
+        sd[p + "ls1.gamma"] = 0.5 + torch.rand(C, generator=g)
+        ln(p + "norm2")
+        lin(p + "mlp.fc1", 4 * C, C)
+        lin(p + "mlp.fc2", C, 4 * C)
+        sd[p + "ls2.gamma"] = 0.5 + torch.rand(C, generator=g)
+    ln("norm")
+    return sd
+
+
+def make_proposals(P=6, H=480, W=640, seed=1):
+    """a synthetic frame with P mask proposals: image (H,W,3) uint8, masks (P,H,W) float32 0/1 (ellipses, boxes with holes, a
+    border-clipped one, an exactly square one), boxes (P,4) int64 xyxy = tight bounds of each mask (Detections convention)"""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    base = (torch.sin(xx / 23.0) + torch.cos(yy / 17.0) + 0.002 * (xx + yy)).unsqueeze(-1)
+    image = ((base * torch.tensor([40.0, 55.0, 35.0]) + 110 + 25 * torch.randn(H, W, 3, generator=g)).clamp(0, 255)).to(torch.uint8)
+    masks = torch.zeros(P, H, W)
+    for p in range(P):
+        cy, cx = int(torch.randint(60, H - 60, (1,), generator=g)), int(torch.randint(60, W - 60, (1,), generator=g))
+        ry, rx = int(torch.randint(12, 110, (1,), generator=g)), int(torch.randint(12, 110, (1,), generator=g))
+        kind = p % 4
+        if kind == 0:
+            m = ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+        elif kind == 1:
+            m = ((yy - cy).abs() < ry) & ((xx - cx).abs() < rx) & ~(((yy - cy).abs() < ry // 3) & ((xx - cx).abs() < rx // 3))
+        elif kind == 2:
+            m = (yy > H - 2 * ry) & (xx > W - 2 * rx)                      # clipped at the image border
+        else:
+            m = ((yy - cy).abs() < ry) & ((xx - cx).abs() < ry)            # square box
+        masks[p] = m.float()
+    boxes = torch.zeros(P, 4, dtype=torch.int64)
+    for p in range(P):
+        ys, xs = torch.nonzero(masks[p] > 0, as_tuple=True)
+        boxes[p] = torch.tensor([xs.min(), ys.min(), xs.max(), ys.max()])
+    return image, masks, boxes

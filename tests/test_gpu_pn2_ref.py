@@ -39,6 +39,34 @@ def test_fps_matches_reference_kernel(ref, b, n, m, dup):
     assert torch.equal(ops.furthest_point_sampling(x.cuda(), m).cpu(), want), "sam6d_b200 kernel != reference CUDA kernel"
 
 
+@pytest.mark.parametrize("b,n,m", [(1, 210000, 2048), (2, 50000, 512), (3, 4097, 100), (1, 106496, 300), (1, 106497, 300)])
+def test_fps_cluster_kernel_matches_reference_kernel(ref, b, n, m):
+    """large clouds: the thread-block-cluster FPS (8 / 16 CTAs per cloud, points in distributed shared memory) against the
+    reference's own kernel and the one-CTA kernel; 210 000 -> 2048 is the template bank of get_obj_feats
+    (PEM/model/feature_extraction.py:170-181).  Timings are written next to each other into gpurun_out/fps_big.json."""
+    import json
+    import os
+    from sam6d_b200 import ops
+    x = _clouds(b, n, n + m, dup=(n == 50000)).cuda()
+    want = ref.furthest_point_sampling(x, m)
+    got = ops.furthest_point_sampling(x, m)
+    assert torch.equal(got, want), "cluster FPS != reference CUDA kernel"
+    assert torch.equal(ops.furthest_point_sampling_single_cta(x, m), want)
+
+    def t_ms(fn):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    rec = dict(b=b, n=n, m=m, reference_ext_ms=t_ms(lambda: ref.furthest_point_sampling(x, m)),
+               cluster_ms=t_ms(lambda: ops.furthest_point_sampling(x, m)), single_cta_ms=t_ms(lambda: ops.furthest_point_sampling_single_cta(x, m)))
+    print("FPS", rec)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "fps_big.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    old = json.load(open(path)) if os.path.exists(path) else []
+    json.dump(old + [rec], open(path, "w"), indent=1)
+
+
 @pytest.mark.parametrize("n,r,ns", [(2048, 0.1, 32), (2048, 0.2, 64), (700, 0.3, 16)])
 def test_ball_query_matches_reference_kernel(ref, n, r, ns):
     from sam6d_b200 import ops

@@ -42,8 +42,7 @@ def import_reference_ism():
     if ISM not in sys.path:
         sys.path.insert(0, ISM)
     for n in ["ruamel", "ruamel.yaml", "pytorch_lightning", "hydra", "hydra.utils", "omegaconf", "trimesh", "pycocotools",
-              "pycocotools.mask", "distinctipy", "skimage", "skimage.feature", "skimage.morphology", "imageio", "xformers",
-              "xformers.ops"]:
+              "pycocotools.mask", "distinctipy", "skimage", "skimage.feature", "skimage.morphology", "imageio"]:   # (xformers is NOT stubbed: the reference falls back to eager attention on ImportError)
         try:
             importlib.import_module(n)
         except Exception:
