@@ -198,6 +198,125 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_scene(args):
+    """BASELINE configs #4 / #5 -- STRONG scaling of one fixed piece of work over the ranks:
+      --workload ycbv  (config #5): one frame, 200 proposals, 21 objects x 42 templates x 1024-d descriptors.  Template scoring
+                        is object-sharded (every rank scores all proposals against its objects with the fused CUDA kernel, one
+                        12-byte-per-proposal all-gather picks the winners), PEM matching is proposal-sharded (200 / N per rank,
+                        each proposal against the template bank of ITS object), one ragged all-gather of the poses.
+      --workload lmo   (config #4): 8 scenes x 16 proposals, 8 objects: scenes are sharded over the ranks; per scene the SAM ViT-H
+                        encoder (1024 x 1024), template scoring, PEM matching of its proposals; one all-gather of the poses.
+    value = poses of the whole job / max-over-ranks time."""
+    import torch.distributed as dist
+    from sam6d_b200 import _lib, dist as sdist, ism, synth
+    from sam6d_b200.pem import Net
+    world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ycbv = args.workload == "ycbv"
+    O, T, C = (21, 42, 1024) if ycbv else (8, 42, 1024)
+    scenes, P = (1, 200) if ycbv else (8, 16)
+    net = Net(precision=args.precision).to(dev).eval()
+    net.load_state_dict(synth.make_pem_state_dict(seed=1), strict=True)
+    # template banks of the O objects (dense_po / dense_fo, 2048 points each) and per-scene proposals
+    bank = synth.make_pem_inputs(B=O, n=N_PTS, n_model=N_MODEL, seed=50)
+    bank_po, bank_fo, bank_model = bank["dense_po"].to(dev), bank["dense_fo"].to(dev), bank["model"].to(dev)
+    sc = []
+    for s_ in range(scenes):
+        inp = synth.make_pem_inputs(B=P, n=N_PTS, n_model=N_MODEL, seed=200 + s_)
+        q, r = synth.make_descriptors(P=P, O=O, T=T, C=C, seed=300 + s_)
+        sc.append(dict(pts=inp["pts"].to(dev), dense_fm=inp["dense_fm"].to(dev), q=q.to(dev)))
+    _, refs = synth.make_descriptors(P=4, O=O, T=T, C=C, seed=300)
+    refs = refs.to(dev)
+    o_lo, o_hi = sdist.shard_range(O, rank, world)
+    refs_local = refs[o_lo:o_hi].contiguous()
+    enc, frames = None, None
+    if not ycbv:
+        from sam6d_b200.sam import build_image_encoder
+        enc = build_image_encoder("vit_h", precision=args.precision).to(dev).eval()
+        g = torch.Generator().manual_seed(1)
+        with torch.no_grad():
+            for prm in enc.parameters():
+                prm.copy_(torch.randn(prm.shape, generator=g) * (0.02 if prm.dim() > 1 else 0.05))
+        frames = [synth.make_images(B=1, seed=400 + s_).to(dev) for s_ in range(scenes)]
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+
+    def pem_on(scene, idx, obj):
+        """proposals idx of a scene, each against the bank of its assigned object"""
+        if idx.numel() == 0:
+            return torch.zeros(0, sdist.POSE_FLOATS, device=dev)
+        ep = dict(pts=scene["pts"][idx].contiguous(), dense_fm=scene["dense_fm"][idx].contiguous(), dense_po=bank_po[obj].contiguous(),
+                  dense_fo=bank_fo[obj].contiguous(), model=bank_model[obj].contiguous())
+        rand = torch.rand(idx.numel(), synth.N_PROPOSAL1 * 3, device=dev, generator=gen)
+        return sdist.pack_poses(net(ep, rand=rand))
+
+    def step(i):
+        if ycbv:
+            scene = sc[0]
+            # every proposal keeps its best object (threshold -1: the sweep times all 200 poses, as BASELINE config #5 states)
+            sel, obj, score, tmpl = sdist.sharded_semantic_score(scene["q"], refs_local, o_lo, confidence_thresh=-1.0)
+            lo, hi = sdist.shard_range(P, rank, world)
+            counts = [b - a for a, b in (sdist.shard_range(P, r_, world) for r_ in range(world))]
+            local = pem_on(scene, sel[lo:hi], obj[lo:hi])
+            return sdist.all_gather_poses(local, counts=counts)
+        mine = list(range(rank, scenes, world))
+        outs = []
+        for s_ in mine:
+            enc(frames[s_])
+            sel, obj, score, tmpl = ism.compute_semantic_score(sc[s_]["q"], refs, confidence_thresh=-1.0)
+            outs.append(pem_on(sc[s_], sel, obj))
+        local = torch.cat(outs, dim=0) if outs else torch.zeros(0, sdist.POSE_FLOATS, device=dev)
+        counts = [len(range(r_, scenes, world)) * P for r_ in range(world)]
+        return sdist.all_gather_poses(local, counts=counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+    if rank == 0:
+        total = scenes * P
+        assert out.shape[0] == total
+        line = dict(metric=METRIC, value=total * args.steps / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong", vs_baseline=None,
+                    dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
+                    config=dict(workload="ycbv_21obj_200proposals_template_parallel" if ycbv else "lmo_8scenes_x16proposals_ism_plus_pem",
+                                objects=O, templates=T, proposals_per_step=total, scenes_per_step=scenes,
+                                parallelism=(f"objects sharded x{world} for scoring (1 all-gather, 12 B/proposal/rank) + proposals sharded x{world} "
+                                             f"for matching ({total // world}-{-(-total // world)} per GPU) + 1 ragged all-gather of poses") if ycbv else
+                                            f"scenes sharded x{world} (SAM ViT-H encoder + scoring + matching per scene) + 1 all-gather of poses",
+                                cache="per-step working set exceeds L2"),
+                    gpu_launches=launches, clocks=sampler.summary() if sampler else None)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_ism(args):
     """BASELINE.json config #3: SAM ViT-H image encoder + 42-template cosine scoring on a batch of synthetic frames.
     Secondary line (the headline metric of the repo is the PEM poses/s line): python bench.py --workload ism"""
@@ -285,13 +404,16 @@ def main():
     ap.add_argument("--rgb", action="store_true",
                     help="PEM workload including the RGB branch (SURVEY 8f row N1): ViT-B/16 features of 224x224 crops + pixel "
                          "gather replace the given dense_fm; not the BASELINE configuration, reported as its own workload name")
-    ap.add_argument("--workload", default="pem", choices=["pem", "ism"],
-                    help="pem: BASELINE config #2 (headline); ism: config #3, SAM ViT-H encoder + template scoring")
+    ap.add_argument("--workload", default="pem", choices=["pem", "ism", "ycbv", "lmo"],
+                    help="pem: BASELINE config #2 (headline); ism: config #3, SAM ViT-H encoder + template scoring; ycbv / lmo: "
+                         "configs #5 / #4, strong scaling of one fixed frame set over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "ism":
         return run_ism(args)
+    if args.workload in ("ycbv", "lmo"):
+        return run_scene(args)
 
     import torch.distributed as dist
     from sam6d_b200 import synth                  # seeded weights + synthetic inputs (no oracle code on this arm)

@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
         bl[rr] = (col < Sk) ? __ldg(wbase + off) : 0.f;
       }
     };
+    // the first bias tile travels while the loads and the score MMA are in flight; every later tile is requested right after its
+    // predecessor has been staged, so its global-load latency hides behind that chunk's arithmetic instead of stalling the next
+    if (BIAS_MODE == 1 || BIAS_MODE == 3) fetch_bias(0);
     tc::mbar_wait(&s_full, 0);
     tc::tc_fence_after_sync();
     if (BIAS_MODE == 2) {
@@ -196,10 +199,10 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
       float v[32];
       tc::tmem_ld32(t_addr + c * 32, v);
       if (BIAS_MODE == 1 || BIAS_MODE == 3) {
-        fetch_bias(c);
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) my_stage[st_w(rr, lane)] = bl[rr];
         __syncwarp();
+        if (c + 1 < nchunk) fetch_bias(c + 1);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -388,7 +391,7 @@ int attn_tc_launch(const void* Q, long long q_ld, int q_col0, const void* K, lon
   S6_REQUIRE(Q && K && Vt && out && B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= MAXK);
   S6_REQUIRE((head_dim == 64 || head_dim == 80) && bias_mode >= 0 && bias_mode <= 3);
   S6_REQUIRE((q_ld % 8) == 0 && (k_ld % 8) == 0 && (vt_ld % 8) == 0 && (q_col0 % 8) == 0 && (k_col0 % 8) == 0);
-  S6_REQUIRE(k_brows >= k_row0 + Sk && k_row0 >= 0 && v_col0 >= 0);
+  S6_REQUIRE(k_brows >= k_row0 + Sk && k_row0 >= 0 && v_col0 >= 0 && (v_col0 % 8) == 0);   // TMA boxes start on 16-byte boundaries
   if (bias_mode == 1 || bias_mode == 3) S6_REQUIRE(bias != nullptr);
   if (bias_mode == 2) S6_REQUIRE(rel_h && Hs > 0 && Ws > 0 && Hs <= 16 && Ws <= 16 && Hs * Ws == Sk && Sq == Sk && (reinterpret_cast<uintptr_t>(rel_h) & 15) == 0);
   if (B == 0) return 0;

@@ -23,7 +23,8 @@ __global__ void crop_resize_pad_kernel(const unsigned char* __restrict__ image, 
   const int x1 = boxes[p * 4], y1 = boxes[p * 4 + 1], x2 = boxes[p * 4 + 2], y2 = boxes[p * 4 + 3];
   const int bw = x2 - x1, bh = y2 - y1;
   // scale_factor = target_max / max(box size) as a float32 tensor element, .item() -> double (bbox_utils.py:99-105)
-  const float scale_f = (float)T / (float)max(bw, bh);
+  // `target_max / tensor` is torch.Tensor.__rtruediv__ = tensor.reciprocal() * target_max: two float32 roundings
+  const float scale_f = __fmul_rn(__frcp_rn((float)max(bw, bh)), (float)T);
   const double scale = (double)scale_f;
   const int rh = (int)floor((double)bh * scale), rw = (int)floor((double)bw * scale);
   const float inv = (float)(1.0 / scale);                 // ATen: scale = 1 / scale_factor, computed in double, used as float

@@ -501,6 +501,32 @@ def attn_tc(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, Vt: Tensor, B: int, 
     return out
 
 
+def attn_tc_ex(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, Vt: Tensor, B: int, H: int, Sq: int, Sk: int, D: int, scale: float,
+               k_brows: int, k_row0: int = 0, v_col0: int = 0, want_lse: bool = False, out_dtype=torch.bfloat16):
+    """attn_tc (no bias) over a window of keys: batch b's keys are rows [b*k_brows + k_row0, +Sk) of K and columns [v_col0, +Sk) of
+    its V^T rows.  -> (out (B*Sq, H*D), lse (B,H,Sq) f32 or None)"""
+    _check(Q, torch.bfloat16, "Q", 2)
+    _check(K, torch.bfloat16, "K", 2)
+    _check(Vt, torch.bfloat16, "Vt", 2)
+    out = torch.empty(B * Sq, H * D, dtype=out_dtype, device=Q.device)
+    lse = torch.empty(B, H, Sq, dtype=torch.float32, device=Q.device) if want_lse else None
+    _lib.call("sam6d_attn_tc_ex", _p(Q), _ll(Q.shape[1]), int(q_col0), _p(K), _ll(K.shape[1]), int(k_col0), _p(Vt), _ll(Vt.shape[1]),
+              int(B), int(H), int(Sq), int(Sk), int(D), _f(scale), int(k_brows), int(k_row0), int(v_col0), _p(lse), _p(out),
+              int(out_dtype == torch.bfloat16), _ll(H * D), _s())
+    return out, lse
+
+
+def attn_merge_key(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, k_brows: int, key_row: int, Vt: Tensor, key_col: int, lse: Tensor,
+                   B: int, H: int, Sq: int, scale: float, out: Tensor) -> Tensor:
+    """folds one more key (row key_row of every batch's K rows, column key_col of its V^T rows) into the bf16 result `out` of
+    attn_tc_ex (head dim 64), in place"""
+    _check(out, torch.bfloat16, "out", 2)
+    _check(lse, torch.float32, "lse", 3)
+    _lib.call("sam6d_attn_merge_key", _p(Q), _ll(Q.shape[1]), int(q_col0), _p(K), _ll(K.shape[1]), int(k_col0), int(k_brows), int(key_row),
+              _p(Vt), _ll(Vt.shape[1]), int(key_col), _p(lse), int(B), int(H), int(Sq), _f(scale), _p(out), _ll(out.shape[1]), _s())
+    return out
+
+
 def transpose_tokens(src: Tensor, col0: int, C: int, nB: int, L: int) -> Tensor:
     """V^T for attn_tc: src bf16 (nB*L, ld) -> (nB*C, ceil16(L)) bf16, zero padded keys"""
     _check(src, torch.bfloat16, "src", 2)
