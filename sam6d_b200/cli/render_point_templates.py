@@ -62,8 +62,12 @@ def render_templates(verts_mm, faces, colors, size=256, n_points=400000, seed=0)
     focal = 2.2 * size                                        # object fills ~70 % of the frame at distance 3.2 radius
     dist = 3.2 * radius
     views = []
+    poses = []
     for cam_dir in icosphere_42():
         R = look_at(cam_dir * dist)
+        Tm = np.eye(4)
+        Tm[:3, :3], Tm[:3, 3] = R, [0, 0, dist / 1000.0]       # object -> camera (metres), the layout of the reference's template poses
+        poses.append(Tm)
         pc = pts @ R.T + np.array([0, 0, dist])
         uu = np.round(focal * pc[:, 0] / pc[:, 2] + size / 2).astype(np.int64)
         vv = np.round(focal * pc[:, 1] / pc[:, 2] + size / 2).astype(np.int64)
@@ -81,6 +85,7 @@ def render_templates(verts_mm, faces, colors, size=256, n_points=400000, seed=0)
         mask[lin_s] = 255
         xyz[lin_s] = pts[sel].astype(np.float16)
         views.append((rgb.reshape(size, size, 3), mask.reshape(size, size), xyz.reshape(size, size, 3)))
+    render_templates.last_poses = np.stack(poses)
     return views
 
 
@@ -92,6 +97,8 @@ def write_templates(views, out_dir):
         cv2.imwrite(os.path.join(tdir, f"rgb_{i}.png"), rgb[:, :, ::-1])       # files hold RGB as load_im reads it
         cv2.imwrite(os.path.join(tdir, f"mask_{i}.png"), mask)
         np.save(os.path.join(tdir, f"xyz_{i}.npy"), xyz)
+    if getattr(render_templates, "last_poses", None) is not None:
+        np.save(os.path.join(tdir, "template_poses.npy"), render_templates.last_poses)
     return tdir
 
 

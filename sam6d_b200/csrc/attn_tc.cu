@@ -168,9 +168,6 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
         bl[rr] = (col < Sk) ? __ldg(wbase + off) : 0.f;
       }
     };
-    // the first bias tile travels while the loads and the score MMA are in flight; every later tile is requested right after its
-    // predecessor has been staged, so its global-load latency hides behind that chunk's arithmetic instead of stalling the next
-    if (BIAS_MODE == 1 || BIAS_MODE == 3) fetch_bias(0);
     tc::mbar_wait(&s_full, 0);
     tc::tc_fence_after_sync();
     if (BIAS_MODE == 2) {
@@ -199,10 +196,12 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
       float v[32];
       tc::tmem_ld32(t_addr + c * 32, v);
       if (BIAS_MODE == 1 || BIAS_MODE == 3) {
+        // (requesting chunk c+1 here, one chunk ahead, was measured: the 32 extra live registers spill at the 168-register cap of
+        //  the two-CTAs-per-SM layout and the launch got slower, 54 -> 72 us)
+        fetch_bias(c);
 #pragma unroll
         for (int rr = 0; rr < 32; ++rr) my_stage[st_w(rr, lane)] = bl[rr];
         __syncwarp();
-        if (c + 1 < nchunk) fetch_bias(c + 1);
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) {

@@ -147,7 +147,9 @@ S6_API int sam6d_geo_indices(const float* pts, int b, int S, float sigma_d, floa
   S6_REQUIRE(pts && T && b >= 0 && S >= 4 && S <= 4096);
   if (b == 0) return 0;
   dim3 grid(S, b);
-  geo_indices_kernel<<<grid, 256, (size_t)S * 4 * sizeof(float), s6_stream(stream)>>>(pts, S, sigma_d, factor_a, T);
+  const size_t smem = (size_t)S * 4 * sizeof(float);          // 64 KB at S = 4096: above the 48 KB default, opt in on every call
+  S6_CHECK(cudaFuncSetAttribute(geo_indices_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // (per device, cheap)
+  geo_indices_kernel<<<grid, 256, smem, s6_stream(stream)>>>(pts, S, sigma_d, factor_a, T);
   S6_LAUNCH_CHECK();
   return 0;
 }
@@ -158,12 +160,9 @@ S6_API int sam6d_geo_embed_f32(const float* T, long long npairs, const float* di
                                const float* bias, float* E, void* stream) {
   S6_REQUIRE(T && div_term && WaT && WdT && bias && E && npairs >= 0);
   if (npairs == 0) return 0;
-  static bool attr_set = false;
   const size_t smem = 256 * TP * 4 * sizeof(float);
-  if (!attr_set) {
-    S6_CHECK(cudaFuncSetAttribute(geo_embed_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // unconditionally: the attribute is per device, a process-wide flag would leave a second GPU of the same process without it
+  S6_CHECK(cudaFuncSetAttribute(geo_embed_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   geo_embed_f32_kernel<<<s6_cdiv(npairs, TP), 256, smem, s6_stream(stream)>>>(T, npairs, div_term, WaT, WdT, bias, E);
   S6_LAUNCH_CHECK();
   return 0;

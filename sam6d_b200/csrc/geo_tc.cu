@@ -27,11 +27,15 @@ constexpr int NUM_PRODUCERS = 256;                  // warps 4-11
 constexpr int MMA_WARP = 12;
 constexpr int NUM_THREADS = 128 + NUM_PRODUCERS + 32 + 128;   // epilogue warps 0-3 and 13-16 (two per TMEM lane quadrant)
 // the distance pass stages its full-line stores through shared memory (8 warps x 4.5 KB) and runs a 3-deep A ring to fit
+// A ring stage holds kKps k-blocks (slabs).  The angle pass packs two per stage: its producers pay one fence.proxy.async + barrier
+// round trip per stage, and with one k-block per stage those four synchronisations per tile -- not MUFU, tensor or issue
+// throughput -- set its pace (profiles/r02_geo_notes.md).
 template <int MODE>
 struct Cfg {
-  static constexpr int kStages = (MODE == 0) ? 4 : 3;
+  static constexpr int kKps = (MODE == 0) ? 2 : 1;
+  static constexpr int kStages = 3;
   static constexpr int kEpiBytes = (MODE == 0) ? 0 : 8 * epi::WARP_STAGE_FLOATS * 4;
-  static constexpr int kSmem = KBLOCKS * W_SLAB + kStages * A_SLAB + kEpiBytes + 1024;
+  static constexpr int kSmem = KBLOCKS * W_SLAB + kStages * kKps * A_SLAB + kEpiBytes + 1024;
 };
 
 template <typename ET>
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
                                                                       const float* __restrict__ div_term,
                                                                       const __nv_bfloat16* __restrict__ Wb,   // (256 out, 256 in) bf16
                                                                       const float* __restrict__ bias, ET* __restrict__ E) {
-  constexpr int ASTAGES = Cfg<MODE>::kStages;
+  constexpr int ASTAGES = Cfg<MODE>::kStages, KPS = Cfg<MODE>::kKps, STAGE_BYTES = KPS * A_SLAB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* w_smem = smem;                              // 4 slabs [256][64] bf16
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
     const uint4 v = *reinterpret_cast<const uint4*>(Wb + (size_t)n * 256 + c);
     *reinterpret_cast<uint4*>(w_smem + (c >> 6) * W_SLAB + tc::sw128_offset(n, c & 63)) = v;
   }
-  for (int u = tid; u < ASTAGES * A_SLAB / 16; u += NUM_THREADS)       // rows the angle pass never writes must be finite
+  for (int u = tid; u < ASTAGES * STAGE_BYTES / 16; u += NUM_THREADS)   // rows the angle pass never writes must be finite
     reinterpret_cast<uint4*>(a_smem)[u] = make_uint4(0u, 0u, 0u, 0u);
   tc::fence_proxy_async_smem();
   if (warp == MMA_WARP) tc::tmem_alloc(&tmem_slot, 512);
@@ -132,20 +136,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
         }
       }
 #pragma unroll
-      for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
+      for (int kb0 = 0; kb0 < KBLOCKS; kb0 += KPS, ++g) {
         const int s = (int)(g % ASTAGES);
         tc::mbar_wait(&empty_bar[s], (uint32_t)(((g / ASTAGES) & 1) ^ 1));
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
-          uint32_t w[4];
+        for (int kk = 0; kk < KPS; ++kk) {
+          const int kb = kb0 + kk;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float sv, cv;
-            __sincosf(x[j] * om[kb][q], &sv, &cv);
-            w[q] = tc::pack_bf16(sv, cv);
+          for (int j = 0; j < NT; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float sv, cv;
+              __sincosf(x[j] * om[kb][q], &sv, &cv);
+              w[q] = tc::pack_bf16(sv, cv);
+            }
+            const uint32_t addr = a_base + s * STAGE_BYTES + kk * A_SLAB + row[j] * 128 + ((c ^ (row[j] & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
           }
-          const uint32_t addr = a_base + s * A_SLAB + row[j] * 128 + ((c ^ (row[j] & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
         tc::fence_proxy_async_smem();
         __syncwarp();
@@ -163,14 +171,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
         tc::mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc::tc_fence_after_sync();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
+        for (int kb0 = 0; kb0 < KBLOCKS; kb0 += KPS, ++g) {
           const int s = (int)(g % ASTAGES);
           tc::mbar_wait(&full_bar[s], (uint32_t)((g / ASTAGES) & 1));
           tc::tc_fence_after_sync();
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            tc::umma_bf16(d_addr, tc::umma_desc_sw128(a_addr0 + s * A_SLAB + k * 32), tc::umma_desc_sw128(w_addr + kb * W_SLAB + k * 32),
-                          idesc, (kb | k) ? 1u : 0u);
+          for (int kk = 0; kk < KPS; ++kk)
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              tc::umma_bf16(d_addr, tc::umma_desc_sw128(a_addr0 + s * STAGE_BYTES + kk * A_SLAB + k * 32),
+                            tc::umma_desc_sw128(w_addr + (kb0 + kk) * W_SLAB + k * 32), idesc, (kb0 | kk | k) ? 1u : 0u);
           tc::umma_commit(&empty_bar[s]);
         }
         tc::umma_commit(&tmem_full_bar[acc]);
@@ -196,15 +206,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
 #pragma unroll
             for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[(c0 + c) * (sizeof(ET) == 4 ? 8 : 4) + u];
         }
-      }
-      // distance pass: E already holds max_k proj_a(...) from the angle pass; fetch this warp's four 32 x 32 tiles of it (coalesced
-      // register layout of epilogue.cuh) before waiting for the accumulator, so the read-modify-write latency hides behind the MMAs
-      constexpr bool PRE = (MODE == 1) && (sizeof(ET) == 2);
-      uint4 pre[PRE ? 4 : 1][4];
-      if constexpr (PRE) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc)
-          epi::prefetch_res_bf16(reinterpret_cast<const __nv_bfloat16*>(E), 256, (int)(tile * 128 + quad * 32), (int)npairs, (c0 + cc) * 32, lane, pre[cc]);
       }
       tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
@@ -245,20 +246,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
           }
         }
       } else {
-        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * A_SLAB) +
+        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * STAGE_BYTES) +
                        (quad + c0) * epi::WARP_STAGE_FLOATS;
         const long long row0 = tile * 128 + quad * 32;
         (void)raw;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = c0 + cc;
+#pragma unroll 1
+        for (int c = c0; c < c0 + 4; ++c) {
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
-          // rows = pairs: E = E (max_k proj_a from the angle pass) + acc + (b_a + b_d), full-line loads and stores
-          if constexpr (PRE)
-            epi::process_chunk<ET, 0, true, true, ET>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, bias, E, 256, E, 256, pre[cc]);
-          else
-            epi::process_chunk<ET, 0, true, true, ET>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, bias, E, 256, E, 256);
+          // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch)
+          epi::process_chunk<ET, 0, true, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, bias, nullptr, 0, E, 256);
         }
       }
       tc::tc_fence_before_sync();
@@ -268,171 +265,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
-}
-
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Angle pass, swapped operands:   D^T[channel, (pair, k)] = W_a . sin_emb(a_{pair,k})^T
-//   A operand = the resident weight (two M tiles: output channels 0..127 and 128..255 of every 64-channel k-slab),
-//   B operand = the producers' embedding rows, N = 96 = 32 pairs x 3 neighbours (no padding row: the row-major version spent a
-//               quarter of its MMA work and of its MUFU-free slab rows on the unused 4th neighbour),
-//   accumulator = 2 x 96 TMEM columns per tile, two tiles in flight (384 columns).
-// A TMEM lane is an output channel and the three neighbours of a pair are three ADJACENT COLUMNS, so the max over k is a register
-// max (the row-major layout needed a 24-shuffle transpose per 32-column chunk); the epilogue thread (= channel) STORES its value
-// to E[pair, channel] (this pass runs first; the distance pass adds proj_d + biases): a warp's 32 lanes write 32 consecutive
-// channels of one pair (64 B) per instruction, no load sits on the path.
-constexpr int SW_PAIRS = 32, SW_N = SW_PAIRS * 3;                    // 96 embedding rows per tile
-constexpr int SW_SLAB = SW_N * 128;                                  // 12 KB per k-block
-constexpr int SW_STAGES = 4;
-constexpr int SW_SMEM = KBLOCKS * W_SLAB + SW_STAGES * SW_SLAB + 1024;
-constexpr int SW_THREADS = 256 + NUM_PRODUCERS + 32;                 // warps 0-7 epilogue, 8-15 producers, 16 MMA
-
-template <typename ET>
-__global__ void __launch_bounds__(SW_THREADS, 1) geo_angle_swapped_kernel(const float* __restrict__ T, long long npairs,
-                                                                          const float* __restrict__ div_term,
-                                                                          const __nv_bfloat16* __restrict__ Wb, ET* __restrict__ E) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* w_smem = smem;
-  uint8_t* b_smem = smem + KBLOCKS * W_SLAB;
-  __shared__ __align__(8) uint64_t full_bar[SW_STAGES], empty_bar[SW_STAGES], tmem_full_bar[2], tmem_empty_bar[2];
-  __shared__ uint32_t tmem_slot;
-  __shared__ float omega[128];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long ntiles = (npairs + SW_PAIRS - 1) / SW_PAIRS;
-  constexpr int MMA_W = 16;
-
-  if (tid == 0) {
-    for (int s = 0; s < SW_STAGES; ++s) { tc::mbar_init(&full_bar[s], NUM_PRODUCERS / 32); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 256); }
-    tc::mbar_fence_init();
-  }
-  if (tid < 128) omega[tid] = div_term[tid];
-  for (int u = tid; u < 256 * 32; u += SW_THREADS) {
-    const int n = u >> 5, c = (u & 31) << 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(Wb + (size_t)n * 256 + c);
-    *reinterpret_cast<uint4*>(w_smem + (c >> 6) * W_SLAB + tc::sw128_offset(n, c & 63)) = v;
-  }
-  tc::fence_proxy_async_smem();
-  if (warp == MMA_W) tc::tmem_alloc(&tmem_slot, 512);
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  tc::tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_slot;
-
-  if (warp >= 8 && warp < MMA_W) {
-    // ------------------------------------------------------------------ producers: thread <-> (16-byte chunk column, 3 rows)
-    const int pt = tid - 256;
-    const int c = pt & 7;
-    int row[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) row[j] = (j * NUM_PRODUCERS + pt) >> 3;      // 0..95 = 32 * k + pair  (neighbour-major)
-    float om[KBLOCKS][4];
-#pragma unroll
-    for (int kb = 0; kb < KBLOCKS; ++kb)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) om[kb][q] = omega[kb * 32 + c * 4 + q];
-    const uint32_t b_base = tc::smem_u32(b_smem);
-    long long g = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      float x[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const long long pair = tile * SW_PAIRS + (row[j] & 31);
-        x[j] = (pair < npairs) ? T[pair * 4 + (row[j] >> 5)] : 0.f;
-      }
-#pragma unroll
-      for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
-        const int s = (int)(g % SW_STAGES);
-        tc::mbar_wait(&empty_bar[s], (uint32_t)(((g / SW_STAGES) & 1) ^ 1));
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          uint32_t w[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float sv, cv;
-            __sincosf(x[j] * om[kb][q], &sv, &cv);
-            w[q] = tc::pack_bf16(sv, cv);
-          }
-          const uint32_t addr = b_base + s * SW_SLAB + row[j] * 128 + ((c ^ (row[j] & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        }
-        tc::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&full_bar[s]);
-      }
-    }
-  } else if (warp == MMA_W) {
-    // ------------------------------------------------------------------ MMA issuer: per k-step one MMA per channel half
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::umma_idesc_bf16(128, SW_N);
-      const uint32_t w_addr = tc::smem_u32(w_smem), b_addr0 = tc::smem_u32(b_smem);
-      long long g = 0, it = 0;
-      for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int acc = (int)(it & 1);
-        tc::mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc::tc_fence_after_sync();
-        const uint32_t d_addr = tmem_base + (uint32_t)(acc * 2 * SW_N);
-        for (int kb = 0; kb < KBLOCKS; ++kb, ++g) {
-          const int s = (int)(g % SW_STAGES);
-          tc::mbar_wait(&full_bar[s], (uint32_t)((g / SW_STAGES) & 1));
-          tc::tc_fence_after_sync();
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t bdesc = tc::umma_desc_sw128(b_addr0 + s * SW_SLAB + k * 32);
-#pragma unroll
-            for (int m = 0; m < 2; ++m)
-              tc::umma_bf16(d_addr + m * SW_N, tc::umma_desc_sw128(w_addr + kb * W_SLAB + m * (128 * 128) + k * 32), bdesc, idesc,
-                            (kb | k) ? 1u : 0u);
-          }
-          tc::umma_commit(&empty_bar[s]);
-        }
-        tc::umma_commit(&tmem_full_bar[acc]);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue: thread = output channel
-    const int quad = warp & 3, m = warp >> 2;                  // TMEM lane quadrant, channel half
-    const int ch = m * 128 + quad * 32 + lane;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int acc = (int)(it & 1);
-      const long long pair0 = tile * SW_PAIRS;
-      tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
-      tc::tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 2 * SW_N + m * SW_N);
-      // columns [32 k, 32 k + 32) hold neighbour k of the tile's 32 pairs: the max over k is an elementwise max of three chunks
-      float mx[32], v[32];
-      tc::tmem_ld32(t_addr, mx);
-      tc::tmem_ld32(t_addr + 32, v);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) mx[i] = fmaxf(mx[i], v[i]);
-      tc::tmem_ld32(t_addr + 64, v);
-      tc::tc_fence_before_sync();
-      tc::mbar_arrive(&tmem_empty_bar[acc]);                   // values are in registers
-#pragma unroll
-      for (int p = 0; p < SW_PAIRS; ++p) {
-        const long long pair = pair0 + p;
-        // this pass runs FIRST and only stores max_k proj_a (a warp writes 32 consecutive channels of one pair per instruction);
-        // the distance pass then adds proj_d + biases with its prefetched, full-line read-modify-write
-        if (pair < npairs) E[pair * 256 + ch] = (ET)fmaxf(mx[p], v[p]);
-      }
-    }
-  }
-  tc::tc_fence_before_sync();
-  __syncthreads();
-  if (warp == MMA_W) tc::tmem_dealloc(tmem_base, 512);
-}
-
-template <typename ET>
-int launch_angle_swapped(const float* T, long long npairs, const float* div_term, const __nv_bfloat16* W, ET* E, int sms, cudaStream_t st) {
-  auto kern = geo_angle_swapped_kernel<ET>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM);
-  if (e != cudaSuccess) return (int)e;
-  const long long ntiles = (npairs + SW_PAIRS - 1) / SW_PAIRS;
-  const int grid = (int)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, SW_THREADS, SW_SMEM, st>>>(T, npairs, div_term, W, E);
-  return (int)cudaGetLastError();
 }
 
 template <int MODE, typename ET>
@@ -464,13 +296,13 @@ S6_API int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div
   const __nv_bfloat16* Wd = reinterpret_cast<const __nv_bfloat16*>(Wd_bf16);
   int rc;
   if (e_is_bf16) {
-    rc = launch_angle_swapped<__nv_bfloat16>(T, npairs, div_term, Wa, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
-    if (rc) return rc;
     rc = launch_pass<1, __nv_bfloat16>(T, npairs, div_term, Wd, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
-  } else {
-    rc = launch_angle_swapped<float>(T, npairs, div_term, Wa, reinterpret_cast<float*>(E), sms, st);
     if (rc) return rc;
+    rc = launch_pass<0, __nv_bfloat16>(T, npairs, div_term, Wa, bias, reinterpret_cast<__nv_bfloat16*>(E), sms, st);
+  } else {
     rc = launch_pass<1, float>(T, npairs, div_term, Wd, bias, reinterpret_cast<float*>(E), sms, st);
+    if (rc) return rc;
+    rc = launch_pass<0, float>(T, npairs, div_term, Wa, bias, reinterpret_cast<float*>(E), sms, st);
   }
   return rc;
 }

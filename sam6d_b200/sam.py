@@ -251,9 +251,13 @@ ImageEncoderViT._block_bf16 = _block_bf16
 
 
 def build_image_encoder(name: str = "vit_h", precision: str = "bf16") -> ImageEncoderViT:
-    """the image_encoder argument of ISM/segment_anything/build_sam.py:55-80 for vit_h / vit_l / vit_b"""
+    """the image_encoder argument of ISM/segment_anything/build_sam.py:14-21,55-80 for vit_h -- the variant SAM-6D uses
+    (ISM/configs/model/segmentor_model/sam.yaml); the rel-pos attention kernels are built for its head dim 80, so vit_l / vit_b
+    (head dim 64) are rejected here rather than at the first forward"""
     from functools import partial
-    cfg = {"vit_h": (1280, 32, 16, (7, 15, 23, 31)), "vit_l": (1024, 24, 16, (5, 11, 17, 23)), "vit_b": (768, 12, 12, (2, 5, 8, 11))}[name]
+    if name != "vit_h":
+        raise ValueError("sam6d_b200 builds the SAM ViT-H image encoder (head dim 80); vit_l / vit_b are not supported")
+    cfg = {"vit_h": (1280, 32, 16, (7, 15, 23, 31))}[name]
     return ImageEncoderViT(depth=cfg[1], embed_dim=cfg[0], img_size=1024, mlp_ratio=4, norm_layer=partial(torch.nn.LayerNorm, eps=1e-6),
                            num_heads=cfg[2], patch_size=16, qkv_bias=True, use_rel_pos=True, global_attn_indexes=cfg[3],
                            window_size=14, out_chans=256, precision=precision)

@@ -286,3 +286,89 @@ def make_proposals(P=6, H=480, W=640, seed=1):
         ys, xs = torch.nonzero(masks[p] > 0, as_tuple=True)
         boxes[p] = torch.tensor([xs.min(), ys.min(), xs.max(), ys.max()])
     return image, masks, boxes
+
+
+def make_sam_decoder_state_dict(seed=1) -> SD:
+    """seeded weights under the names of `sam_vit_h_4b8939.pth` for `prompt_encoder.*` and `mask_decoder.*`
+    (ISM/segment_anything/modeling/{prompt_encoder,mask_decoder,transformer}.py).  Scales are chosen so that the automatic mask
+    generator's filters (predicted IoU > 0.88, stability >= 0.95) keep a useful share of the masks with random weights: the IoU
+    head's last bias is ~0.9 and the mask logits are a few units large."""
+    g = torch.Generator().manual_seed(seed)
+    sd: SD = {}
+
+    def lin(name, o, i, scale=None, bias_scale=0.02):
+        s = scale if scale is not None else 1.0 / math.sqrt(i)
+        sd[name + ".weight"] = torch.randn(o, i, generator=g) * s
+        sd[name + ".bias"] = torch.randn(o, generator=g) * bias_scale
+
+    def ln(name, c):
+        sd[name + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[name + ".bias"] = 0.05 * torch.randn(c, generator=g)
+
+    p = "prompt_encoder."
+    sd[p + "pe_layer.positional_encoding_gaussian_matrix"] = torch.randn(2, 128, generator=g)
+    for i in range(4):
+        sd[p + f"point_embeddings.{i}.weight"] = torch.randn(1, 256, generator=g) * 0.5
+    sd[p + "not_a_point_embed.weight"] = torch.randn(1, 256, generator=g) * 0.5
+    sd[p + "mask_downscaling.0.weight"] = torch.randn(4, 1, 2, 2, generator=g) * 0.5
+    sd[p + "mask_downscaling.0.bias"] = torch.randn(4, generator=g) * 0.02
+    ln(p + "mask_downscaling.1", 4)
+    sd[p + "mask_downscaling.3.weight"] = torch.randn(16, 4, 2, 2, generator=g) * 0.25
+    sd[p + "mask_downscaling.3.bias"] = torch.randn(16, generator=g) * 0.02
+    ln(p + "mask_downscaling.4", 16)
+    sd[p + "mask_downscaling.6.weight"] = torch.randn(256, 16, 1, 1, generator=g) * 0.25
+    sd[p + "mask_downscaling.6.bias"] = torch.randn(256, generator=g) * 0.02
+    sd[p + "no_mask_embed.weight"] = torch.randn(1, 256, generator=g) * 0.5
+    m = "mask_decoder."
+    t = m + "transformer."
+
+    def attn(name, internal):
+        for q in ("q_proj", "k_proj", "v_proj"):
+            lin(f"{name}.{q}", internal, 256)
+        lin(f"{name}.out_proj", 256, internal)
+
+    for i in range(2):
+        l = t + f"layers.{i}."
+        attn(l + "self_attn", 256)
+        ln(l + "norm1", 256)
+        attn(l + "cross_attn_token_to_image", 128)
+        ln(l + "norm2", 256)
+        lin(l + "mlp.lin1", 2048, 256)
+        lin(l + "mlp.lin2", 256, 2048)
+        ln(l + "norm3", 256)
+        ln(l + "norm4", 256)
+        attn(l + "cross_attn_image_to_token", 128)
+    attn(t + "final_attn_token_to_image", 128)
+    ln(t + "norm_final_attn", 256)
+    sd[m + "iou_token.weight"] = torch.randn(1, 256, generator=g) * 0.5
+    sd[m + "mask_tokens.weight"] = torch.randn(4, 256, generator=g) * 0.5
+    sd[m + "output_upscaling.0.weight"] = torch.randn(256, 64, 2, 2, generator=g) / 16.0
+    sd[m + "output_upscaling.0.bias"] = torch.randn(64, generator=g) * 0.02
+    ln(m + "output_upscaling.1", 64)
+    sd[m + "output_upscaling.3.weight"] = torch.randn(64, 32, 2, 2, generator=g) / 8.0
+    sd[m + "output_upscaling.3.bias"] = torch.randn(32, generator=g) * 0.02
+    for i in range(4):
+        h = m + f"output_hypernetworks_mlps.{i}.layers."
+        lin(h + "0", 256, 256)
+        lin(h + "1", 256, 256)
+        lin(h + "2", 32, 256, scale=40.0 / 16.0)
+    h = m + "iou_prediction_head.layers."
+    lin(h + "0", 256, 256)
+    lin(h + "1", 256, 256)
+    lin(h + "2", 4, 256, scale=0.05 / 16.0)
+    sd[h + "2.bias"] = torch.tensor([0.9, 0.9, 0.9, 0.9]) + 0.03 * torch.randn(4, generator=g)
+    return sd
+
+
+def make_image_embedding(seed=1, size=64) -> torch.Tensor:
+    """a smooth synthetic (1,256,size,size) image embedding: blobs of different feature directions (so that point prompts in
+    different places see different neighbourhoods) plus noise"""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, size), torch.linspace(0, 1, size), indexing="ij")
+    emb = 0.3 * torch.randn(256, size, size, generator=g)
+    for _ in range(12):
+        cy, cx, r = torch.rand(3, generator=g).tolist()
+        d = torch.randn(256, generator=g)
+        blob = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * (0.05 + 0.15 * r) ** 2))
+        emb += d[:, None, None] * blob[None]
+    return emb.unsqueeze(0)

@@ -65,3 +65,43 @@ def test_pem_cli_end_to_end(tmp_path, golden_dir):
     assert cli.main(argv) == 0
     res2 = json.load(open(os.path.join(out, "sam6d_results", "detection_pem.json")))
     assert [r["R"] for r in res] == [r["R"] for r in res2]
+
+
+def test_ism_cli_then_pem_cli(tmp_path, golden_dir):
+    """BASELINE config #1 as the reference's demo.sh chains it: templates -> ISM CLI (SAM automatic mask generation, DINOv2
+    descriptors, semantic / appearance / geometric scores -> detection_ism.json) -> PEM CLI consuming that file.  Seeded random
+    weights (no checkpoints ship): record format, validity and determinism are checked, not detection quality."""
+    import cv2
+    from scipy.spatial import ConvexHull
+    from sam6d_b200.cli import ism_run_inference_custom as ism_cli, pem_run_inference_custom as pem_cli, render_point_templates as rpt
+    gold = torch.load(os.path.join(golden_dir, "pem_input.pt"), weights_only=False)
+    out = str(tmp_path)
+    cv2.imwrite(os.path.join(out, "rgb.png"), gold["rgb"].numpy()[:, :, ::-1])
+    cv2.imwrite(os.path.join(out, "depth.png"), gold["depth"].numpy().astype(np.uint16))
+    json.dump(dict(cam_K=gold["cam_K"], depth_scale=gold["depth_scale"]), open(os.path.join(out, "camera.json"), "w"))
+    pts_mm = gold["model_points"].numpy().astype(np.float64) * 1000.0
+    hull = ConvexHull(pts_mm)
+    remap = {v: i for i, v in enumerate(hull.vertices)}
+    cad = os.path.join(out, "obj.ply")
+    _write_ply(cad, pts_mm[hull.vertices], np.array([[remap[a] for a in s] for s in hull.simplices]),
+               np.random.RandomState(0).randint(40, 255, (len(hull.vertices), 3)))
+    rpt.main(["--cad_path", cad, "--output_dir", out, "--size", "192"])
+    assert os.path.exists(os.path.join(out, "templates", "template_poses.npy"))
+    common = ["--output_dir", out, "--cad_path", cad, "--rgb_path", os.path.join(out, "rgb.png"), "--depth_path", os.path.join(out, "depth.png"),
+              "--cam_path", os.path.join(out, "camera.json")]
+    assert ism_cli.main(common + ["--random_weights", "--stability_score_thresh", "0.3", "--pred_iou_thresh", "0.5", "--points_per_side", "8"]) == 0
+    dets = json.load(open(os.path.join(out, "sam6d_results", "detection_ism.json")))
+    print(f"ISM CLI: {len(dets)} detections")
+    for d in dets:
+        assert set(["scene_id", "image_id", "category_id", "bbox", "score", "time", "segmentation"]) <= set(d)
+        assert d["segmentation"]["size"] == [480, 640] and sum(d["segmentation"]["counts"]) == 480 * 640
+        assert len(d["bbox"]) == 4 and np.isfinite(d["score"])
+    assert len(dets) >= 1
+    np.random.seed(0)
+    assert pem_cli.main(common + ["--seg_path", os.path.join(out, "sam6d_results", "detection_ism.json"), "--random_weights",
+                                  "--det_score_thresh", "-1"]) == 0
+    res = json.load(open(os.path.join(out, "sam6d_results", "detection_pem.json")))
+    assert len(res) <= len(dets)
+    for r in res:
+        R = np.array(r["R"])
+        assert np.allclose(R @ R.T, np.eye(3), atol=1e-4) and np.isfinite(np.array(r["t"])).all()
