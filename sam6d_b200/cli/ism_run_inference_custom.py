@@ -44,6 +44,7 @@ def get_parser():
     ap.add_argument("--template_poses", default=None, help="(T,4,4) .npy of the template camera poses (default: templates/template_poses.npy)")
     ap.add_argument("--points_per_side", default=32, type=int)
     ap.add_argument("--pred_iou_thresh", default=0.88, type=float)
+    ap.add_argument("--confidence_thresh", default=CONFIDENCE_THRESH, type=float, help="semantic-score threshold (ISM_sam.yaml: 0.2)")
     return ap
 
 
@@ -173,7 +174,7 @@ def main(argv=None):
         print("=> no mask proposal survived the filters")
         return 0
     q_cls, q_patch = desc(rgb, det)
-    idx_sel, pred_obj, sem, best_t = ism.compute_semantic_score(q_cls, ref_data["descriptors"], "avg_5", CONFIDENCE_THRESH)
+    idx_sel, pred_obj, sem, best_t = ism.compute_semantic_score(q_cls, ref_data["descriptors"], "avg_5", args.confidence_thresh)
     det.masks, det.boxes, q_patch = det.masks[idx_sel], det.boxes[idx_sel], q_patch[idx_sel]
     if idx_sel.numel() == 0:
         json.dump([], open(out_json, "w"))

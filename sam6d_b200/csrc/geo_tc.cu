@@ -27,13 +27,13 @@ constexpr int NUM_PRODUCERS = 256;                  // warps 4-11
 constexpr int MMA_WARP = 12;
 constexpr int NUM_THREADS = 128 + NUM_PRODUCERS + 32 + 128;   // epilogue warps 0-3 and 13-16 (two per TMEM lane quadrant)
 // the distance pass stages its full-line stores through shared memory (8 warps x 4.5 KB) and runs a 3-deep A ring to fit
-// A ring stage holds kKps k-blocks (slabs).  The angle pass packs two per stage: its producers pay one fence.proxy.async + barrier
-// round trip per stage, and with one k-block per stage those four synchronisations per tile -- not MUFU, tensor or issue
-// throughput -- set its pace (profiles/r02_geo_notes.md).
+// A ring stage holds kKps k-blocks (slabs).  Measured (profiles/r02_geo_notes.md): two k-blocks per stage (half the
+// fence.proxy.async + barrier round trips of the producers) made the angle pass 5 % SLOWER than one per stage with a 4-deep ring,
+// so the synchronisation count is not what bounds it; one k-block per stage stays.
 template <int MODE>
 struct Cfg {
-  static constexpr int kKps = (MODE == 0) ? 2 : 1;
-  static constexpr int kStages = 3;
+  static constexpr int kKps = 1;
+  static constexpr int kStages = (MODE == 0) ? 4 : 3;
   static constexpr int kEpiBytes = (MODE == 0) ? 0 : 8 * epi::WARP_STAGE_FLOATS * 4;
   static constexpr int kSmem = KBLOCKS * W_SLAB + kStages * kKps * A_SLAB + kEpiBytes + 1024;
 };

@@ -89,7 +89,8 @@ def test_ism_cli_then_pem_cli(tmp_path, golden_dir):
     assert os.path.exists(os.path.join(out, "templates", "template_poses.npy"))
     common = ["--output_dir", out, "--cad_path", cad, "--rgb_path", os.path.join(out, "rgb.png"), "--depth_path", os.path.join(out, "depth.png"),
               "--cam_path", os.path.join(out, "camera.json")]
-    assert ism_cli.main(common + ["--random_weights", "--stability_score_thresh", "0.3", "--pred_iou_thresh", "0.5", "--points_per_side", "8"]) == 0
+    assert ism_cli.main(common + ["--random_weights", "--stability_score_thresh", "0.0", "--pred_iou_thresh", "-10", "--confidence_thresh", "-1",
+                                  "--points_per_side", "8"]) == 0
     dets = json.load(open(os.path.join(out, "sam6d_results", "detection_ism.json")))
     print(f"ISM CLI: {len(dets)} detections")
     for d in dets:
