@@ -265,27 +265,34 @@ __global__ void __launch_bounds__(256) weighted_procrustes_kernel(const float* _
   }
 }
 
-// pose score (model_utils.py:275-281) and rescaled translation (fine_point_matching.py:80)
-__global__ void __launch_bounds__(1024) pose_score_kernel(const float* __restrict__ pts1, const int* __restrict__ lab1, int S,
-                                                          const float* __restrict__ R, const float* __restrict__ t,
-                                                          const float* __restrict__ model, int nm, float dis_thres,
-                                                          const float* __restrict__ radius, float* __restrict__ score,
-                                                          float* __restrict__ t_scaled) {
-  extern __shared__ float sm[];
-  float* mx = sm; float* my = mx + nm; float* mz = my + nm; float* m2 = mz + nm;
-  __shared__ double sh[32];
-  const int b = blockIdx.x, tid = threadIdx.x, N = S - 1;
-  for (int i = tid; i < nm; i += 1024) {
+// pose score (model_utils.py:275-281) and rescaled translation (fine_point_matching.py:80).
+// One thread-block CLUSTER of PS_CS CTAs per proposal (one CTA per proposal left 116 of the 148 SMs idle for the longest
+// kernel of the tail): each CTA scores a slice of the points against the CAD samples in its shared memory and publishes its
+// two counts (hits, valid points -- integers, so any summation order gives the same result) into CTA 0's distributed
+// shared memory; one cluster barrier later CTA 0 writes the score.
+constexpr int PS_CS = 8, PS_THREADS = 256;
+__device__ __forceinline__ unsigned ps_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__global__ void __launch_bounds__(PS_THREADS) pose_score_kernel(const float* __restrict__ pts1, const int* __restrict__ lab1, int S,
+                                                                const float* __restrict__ R, const float* __restrict__ t,
+                                                                const float* __restrict__ model, int nm, float dis_thres,
+                                                                const float* __restrict__ radius, float* __restrict__ score,
+                                                                float* __restrict__ t_scaled) {
+  extern __shared__ float4 smq4[];          // (x, y, z, |m|^2) per CAD sample
+  __shared__ int sh[2][PS_THREADS / 32];
+  __shared__ int slot[PS_CS][2];            // CTA 0's copy is written by every CTA of the cluster
+  const unsigned rank = ps_cluster_ctarank();
+  const int b = blockIdx.x / PS_CS, tid = threadIdx.x, N = S - 1;
+  for (int i = tid; i < nm; i += PS_THREADS) {
     const float* q = model + ((size_t)b * nm + i) * 3;
-    float x = q[0], y = q[1], z = q[2];
-    mx[i] = x; my[i] = y; mz[i] = z; m2[i] = x * x + y * y + z * z;
+    const float x = q[0], y = q[1], z = q[2];
+    smq4[i] = make_float4(x, y, z, x * x + y * y + z * z);
   }
   float Rb[9], tb[3];
   for (int a = 0; a < 9; ++a) Rb[a] = R[(size_t)b * 9 + a];
   for (int a = 0; a < 3; ++a) tb[a] = t[(size_t)b * 3 + a];
   __syncthreads();
-  double hits = 0.0, msum = 0.0;
-  for (int i = tid; i < N; i += 1024) {
+  int hits = 0, msum = 0;
+  for (int i = rank * PS_THREADS + tid; i < N; i += PS_CS * PS_THREADS) {
     const float* p = pts1 + ((size_t)b * N + i) * 3;
     float x = p[0] - tb[0], y = p[1] - tb[1], z = p[2] - tb[2];
     float tx = x * Rb[0] + y * Rb[3] + z * Rb[6];
@@ -293,18 +300,33 @@ __global__ void __launch_bounds__(1024) pose_score_kernel(const float* __restric
     float tz = x * Rb[2] + y * Rb[5] + z * Rb[8];
     float x2 = tx * tx + ty * ty + tz * tz;
     float best = INFINITY;
+#pragma unroll 4
     for (int m = 0; m < nm; ++m) {
-      float xy = tx * mx[m] + ty * my[m] + tz * mz[m];
-      best = fminf(best, fmaxf(x2 - 2.f * xy + m2[m], 0.f));
+      const float4 q = smq4[m];
+      float xy = tx * q.x + ty * q.y + tz * q.z;
+      best = fminf(best, fmaxf(x2 - 2.f * xy + q.w, 0.f));
     }
-    float mk = lab1[(size_t)b * S + i + 1] > 0 ? 1.f : 0.f;
+    const int mk = lab1[(size_t)b * S + i + 1] > 0 ? 1 : 0;
     if (sqrtf(best) < dis_thres) hits += mk;
     msum += mk;
   }
-  hits = block_sum_d(hits, sh);
-  msum = block_sum_d(msum, sh);
-  if (tid == 0) {
-    float h = (float)hits, ms = (float)msum;
+  hits = __reduce_add_sync(0xffffffffu, hits);
+  msum = __reduce_add_sync(0xffffffffu, msum);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = hits; sh[1][tid >> 5] = msum; }
+  __syncthreads();
+  if (tid < 2) {
+    int v = 0;
+    for (int w = 0; w < PS_THREADS / 32; ++w) v += sh[tid][w];
+    unsigned la = (unsigned)__cvta_generic_to_shared(&slot[rank][tid]), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(0u));
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(ra), "r"(v) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && tid == 0) {
+    int hsum = 0, ms_i = 0;
+    for (int c = 0; c < PS_CS; ++c) { hsum += slot[c][0]; ms_i += slot[c][1]; }
+    const float h = (float)hsum, ms = (float)ms_i;
     score[b] = (h / (ms + 1e-8f)) * (ms / (float)N);
     float rad = radius[b] + 1e-6f;
     for (int a = 0; a < 3; ++a) t_scaled[(size_t)b * 3 + a] = tb[a] * rad;
@@ -361,7 +383,12 @@ S6_API int sam6d_pose_score(const float* pts1, const int* lab1, int B, int N, co
   size_t smem = (size_t)nm * 4 * sizeof(float);
   S6_REQUIRE(smem <= 200 * 1024);
   S6_CHECK(cudaFuncSetAttribute(pose_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pose_score_kernel<<<B, 1024, smem, s6_stream(stream)>>>(pts1, lab1, N + 1, R, t, model, nm, dis_thres, radius, score, t_scaled);
-  S6_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * PS_CS); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s6_stream(stream);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = PS_CS; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  S6_CHECK(cudaLaunchKernelEx(&cfg, pose_score_kernel, pts1, (const int*)lab1, N + 1, R, t, model, nm, dis_thres, radius, score, t_scaled));
   return 0;
 }

@@ -38,6 +38,17 @@ struct Cfg {
   static constexpr int kSmem = KBLOCKS * W_SLAB + kStages * kKps * A_SLAB + kEpiBytes + 1024;
 };
 
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bf16x2_add(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
 template <typename ET>
 __device__ __forceinline__ void store8(ET* p, const float v[8]);
 template <>
@@ -79,6 +90,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
   __shared__ __align__(8) uint64_t full_bar[ASTAGES], empty_bar[ASTAGES], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float omega[128];
+  __shared__ __align__(16) float sbias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int PAIRS_PER_TILE = (MODE == 0) ? 32 : 128;
@@ -86,10 +98,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
 
   if (tid == 0) {
     for (int s = 0; s < ASTAGES; ++s) { tc::mbar_init(&full_bar[s], NUM_PRODUCERS / 32); tc::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 256); }
+    for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full_bar[a], 1); tc::mbar_init(&tmem_empty_bar[a], 8); }
     tc::mbar_fence_init();
   }
   if (tid < 128) omega[tid] = div_term[tid];
+  if (tid < 256) sbias[tid] = bias[tid];
   // resident weight: W (n, k) row-major bf16 -> slab kb holds columns [64 kb, 64 kb + 64) of every row, swizzled
   for (int u = tid; u < 256 * 32; u += NUM_THREADS) {      // 16-byte units: 256 rows x 32 units
     const int n = u >> 5, c = (u & 31) << 3;
@@ -123,18 +136,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
       for (int q = 0; q < 4; ++q) om[kb][q] = omega[kb * 32 + c * 4 + q];
     const uint32_t a_base = tc::smem_u32(a_smem);
     long long g = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      float x[NT];
+    // the indices of the NEXT tile are fetched before this tile's k-blocks are produced (the load latency would otherwise
+    // sit in front of every tile: the ring holds exactly one tile, so the producers cannot run further ahead than that)
+    auto fetch = [&](long long tile, float (&xx)[NT]) {
 #pragma unroll
       for (int j = 0; j < NT; ++j) {
         if (MODE == 0) {
           const long long pair = tile * 32 + (row[j] >> 2);
-          x[j] = (pair < npairs) ? T[pair * 4 + (row[j] & 3)] : 0.f;
+          xx[j] = (pair < npairs) ? __ldg(T + pair * 4 + (row[j] & 3)) : 0.f;
         } else {
           const long long pair = tile * 128 + row[j];
-          x[j] = (pair < npairs) ? T[pair * 4 + 3] : 0.f;
+          xx[j] = (pair < npairs) ? __ldg(T + pair * 4 + 3) : 0.f;
         }
       }
+    };
+    float xn[NT];
+    fetch(blockIdx.x, xn);
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      float x[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) x[j] = xn[j];
+      fetch(tile + gridDim.x, xn);
 #pragma unroll
       for (int kb0 = 0; kb0 < KBLOCKS; kb0 += KPS, ++g) {
         const int s = (int)(g % ASTAGES);
@@ -153,6 +175,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
             }
             const uint32_t addr = a_base + s * STAGE_BYTES + kk * A_SLAB + row[j] * 128 + ((c ^ (row[j] & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            if (MODE == 0 && (row[j] & 3) == 2) {
+              // the pair's 4th (padding) row repeats its 3rd neighbour: a maximum ignores duplicates, so the epilogue needs no mask
+              const uint32_t addr2 = a_base + s * STAGE_BYTES + kk * A_SLAB + (row[j] + 1) * 128 + ((c ^ ((row[j] + 1) & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr2), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
           }
         }
         tc::fence_proxy_async_smem();
@@ -168,12 +195,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
       long long g = 0, it = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int acc = (int)(it & 1);
-        tc::mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc::mbar_wait_suspend(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc::tc_fence_after_sync();
         const uint32_t d_addr = tmem_base + (uint32_t)(acc * BN);
         for (int kb0 = 0; kb0 < KBLOCKS; kb0 += KPS, ++g) {
           const int s = (int)(g % ASTAGES);
-          tc::mbar_wait(&full_bar[s], (uint32_t)((g / ASTAGES) & 1));
+          tc::mbar_wait_suspend(&full_bar[s], (uint32_t)((g / ASTAGES) & 1));
           tc::tc_fence_after_sync();
 #pragma unroll
           for (int kk = 0; kk < KPS; ++kk)
@@ -207,42 +234,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
             for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[(c0 + c) * (sizeof(ET) == 4 ? 8 : 4) + u];
         }
       }
-      tc::mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+      tc::mbar_wait_suspend(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       if (MODE == 0) {
         const long long pair = tile * 32 + (r >> 2);
         const int q = r & 3;
+        const bool up2 = (lane & 2) != 0, up1 = (lane & 1) != 0;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c = c0 + cc;
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
-          if (q == 3) {
+          // max over the 4 rows of the pair (row 3 repeats row 2), transposed so that lane q ends with columns [8q, 8q+8)
+          if constexpr (sizeof(ET) == 2) {
+            // packed: rounding to bf16 is monotone, so max(bf16(a), bf16(b)) = bf16(max(a, b)); half the selects / shuffles / maxima
+            uint32_t w[16];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = -INFINITY;
-          }
-          // max over the 4 rows of the pair, transposed so that lane q ends with columns [8q, 8q+8) of the chunk
-          float m[16];
-          const bool up2 = (lane & 2) != 0;
+            for (int i = 0; i < 16; ++i) w[i] = tc::pack_bf16(v[2 * i], v[2 * i + 1]);
+            uint32_t m[8];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float keep = up2 ? v[16 + i] : v[i], send = up2 ? v[i] : v[16 + i];
-            m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
-          }
-          float o[8];
-          const bool up1 = (lane & 1) != 0;
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t keep = up2 ? w[8 + i] : w[i], send = up2 ? w[i] : w[8 + i];
+              m[i] = bf16x2_max(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+            }
+            uint32_t o[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float keep = up1 ? m[8 + i] : m[i], send = up1 ? m[i] : m[8 + i];
-            o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
-          }
-          if (pair < npairs) {
-            float e[8];
-            load8<ET>(reinterpret_cast<const ET*>(&raw[cc][0]), e);
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t keep = up1 ? m[4 + i] : m[i], send = up1 ? m[i] : m[4 + i];
+              o[i] = bf16x2_max(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+            if (pair < npairs) {
+              const uint4 e = raw[cc][0];
+              *reinterpret_cast<uint4*>(E + pair * 256 + c * 32 + q * 8) =
+                  make_uint4(bf16x2_add(e.x, o[0]), bf16x2_add(e.y, o[1]), bf16x2_add(e.z, o[2]), bf16x2_add(e.w, o[3]));
+            }
+          } else {
+            float m[16];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) e[i] += o[i];
-            store8<ET>(E + pair * 256 + c * 32 + q * 8, e);
+            for (int i = 0; i < 16; ++i) {
+              float keep = up2 ? v[16 + i] : v[i], send = up2 ? v[i] : v[16 + i];
+              m[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+            }
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float keep = up1 ? m[8 + i] : m[i], send = up1 ? m[i] : m[8 + i];
+              o[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+            if (pair < npairs) {
+              float e[8];
+              load8<ET>(reinterpret_cast<const ET*>(&raw[cc][0]), e);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) e[i] += o[i];
+              store8<ET>(E + pair * 256 + c * 32 + q * 8, e);
+            }
           }
         }
       } else {
@@ -254,12 +300,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
         for (int c = c0; c < c0 + 4; ++c) {
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
-          // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch)
-          epi::process_chunk<ET, 0, true, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, bias, nullptr, 0, E, 256);
+          // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch).
+          // The bias comes from shared memory: as a global load per chunk it was the epilogue's long-scoreboard stall (ncu r02_geo).
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(&sbias[c * 32 + i * 4]);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+          epi::process_chunk<ET, 0, false, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, nullptr, nullptr, 0, E, 256);
         }
       }
       tc::tc_fence_before_sync();
-      tc::mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);      // one arrival per warp: 256 arrivals on one word serialise
     }
   }
   tc::tc_fence_before_sync();

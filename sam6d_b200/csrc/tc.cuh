@@ -38,6 +38,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// the same wait with a suspend-time hint: the warp sleeps in the barrier unit instead of re-issuing try_wait every ~25 cycles
+// (a lone MMA-issuer thread spinning took 22 % of its sub-partition's issue slots in the geometric embedding, ncu r02_geo)
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------------------- fences
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads)
