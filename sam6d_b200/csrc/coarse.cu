@@ -234,31 +234,20 @@ __global__ void __launch_bounds__(1024) topk_smallest_kernel(const float* __rest
 // (x, y, z, |m|^2) quadruples, so the inner loop is one 16-byte broadcast load and 4 instructions per (hypothesis, point, sample):
 // min_m (|x|^2 - 2 x.m + |m|^2) = |x|^2 + min_m (|m|^2 - 2 x.m), the clamp at 0 commutes with the minimum
 // (pairwise_distance, model_utils.py:98-111).
-constexpr int SEL_PP = 8, SEL_THREADS = 224;
-// packed fp32 pair FMA (FFMA2): each half is an IEEE fma, so the scores are those of the scalar chain bit for bit; it halves
-// the issue slots of the kernel's dominant instruction
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
-}
+// (a packed-fp32 FFMA2 variant with 8 hypotheses per CTA measured 550 us against 362 us for this one: FFMA2 issues at half rate)
+constexpr int SEL_PP = 4, SEL_THREADS = 224;
 __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const float* __restrict__ Rt, const int* __restrict__ top, int n1,
                                                                     int n2, const float* __restrict__ pts1, const float* __restrict__ w1,
                                                                     int n, const float* __restrict__ model, int nm,
                                                                     float* __restrict__ scores) {
-  extern __shared__ ulonglong2 smq[];   // per CAD sample two 16-byte words: {(x,x),(y,y)} and {(z,z),(|m|^2,|m|^2)}
+  extern __shared__ float4 smq[];   // nm quadruples
   __shared__ float red[2 * SEL_PP][SEL_THREADS / 32];
   __shared__ float rts[SEL_PP][12];
   const int pose0 = blockIdx.x * SEL_PP, b = blockIdx.y, tid = threadIdx.x;
   for (int i = tid; i < nm; i += SEL_THREADS) {
     const float* q = model + ((size_t)b * nm + i) * 3;
     const float x = q[0], y = q[1], z = q[2];
-    const float w = x * x + y * y + z * z;
-    smq[2 * i] = make_ulonglong2(pack2(x, x), pack2(y, y));
-    smq[2 * i + 1] = make_ulonglong2(pack2(z, z), pack2(w, w));
+    smq[i] = make_float4(x, y, z, x * x + y * y + z * z);
   }
   if (tid < SEL_PP * 12) {
     const int pp = tid / 12, e = tid - pp * 12;
@@ -272,33 +261,23 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const float*
   for (int i = tid; i < n; i += SEL_THREADS) {
     const float* p = pts1 + ((size_t)b * n + i) * 3;
     const float px = p[0], py = p[1], pz = p[2];
-    float x2[SEL_PP], best[SEL_PP];
-    unsigned long long ax[SEL_PP / 2], ay[SEL_PP / 2], az[SEL_PP / 2];
+    float ax[SEL_PP], ay[SEL_PP], az[SEL_PP], x2[SEL_PP], best[SEL_PP];
 #pragma unroll
-    for (int h = 0; h < SEL_PP / 2; ++h) {
-      float tx[2], ty[2], tz[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int pp = 2 * h + e;
-        const float* R = rts[pp];
-        const float x = px - R[9], y = py - R[10], z = pz - R[11];
-        tx[e] = x * R[0] + y * R[3] + z * R[6];
-        ty[e] = x * R[1] + y * R[4] + z * R[7];
-        tz[e] = x * R[2] + y * R[5] + z * R[8];
-        x2[pp] = tx[e] * tx[e] + ty[e] * ty[e] + tz[e] * tz[e];
-        best[pp] = INFINITY;
-      }
-      ax[h] = pack2(-2.f * tx[0], -2.f * tx[1]); ay[h] = pack2(-2.f * ty[0], -2.f * ty[1]); az[h] = pack2(-2.f * tz[0], -2.f * tz[1]);
+    for (int pp = 0; pp < SEL_PP; ++pp) {
+      const float* R = rts[pp];
+      const float x = px - R[9], y = py - R[10], z = pz - R[11];
+      const float tx = x * R[0] + y * R[3] + z * R[6];
+      const float ty = x * R[1] + y * R[4] + z * R[7];
+      const float tz = x * R[2] + y * R[5] + z * R[8];
+      x2[pp] = tx * tx + ty * ty + tz * tz;
+      ax[pp] = -2.f * tx; ay[pp] = -2.f * ty; az[pp] = -2.f * tz;
+      best[pp] = INFINITY;
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int m = 0; m < nm; ++m) {
-      const ulonglong2 qa = smq[2 * m], qb = smq[2 * m + 1];
+      const float4 q = smq[m];
 #pragma unroll
-      for (int h = 0; h < SEL_PP / 2; ++h) {
-        const unsigned long long d = ffma2(ax[h], qa.x, ffma2(ay[h], qa.y, ffma2(az[h], qb.x, qb.y)));
-        best[2 * h] = fminf(best[2 * h], __uint_as_float((unsigned)d));
-        best[2 * h + 1] = fminf(best[2 * h + 1], __uint_as_float((unsigned)(d >> 32)));
-      }
+      for (int pp = 0; pp < SEL_PP; ++pp) best[pp] = fminf(best[pp], fmaf(ax[pp], q.x, fmaf(ay[pp], q.y, fmaf(az[pp], q.z, q.w))));
     }
     const float wi = w1[(size_t)b * n + i];
     num += wi;
@@ -389,7 +368,7 @@ S6_API int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, i
                                const float* model, int nm, float* scores, float* R, float* t, void* stream) {
   S6_REQUIRE(Rt && top && pts1 && w1 && model && scores && R && t && B >= 0 && n > 0 && nm > 0 && n2 > 0);
   if (B == 0) return 0;
-  size_t smem = (size_t)nm * 8 * sizeof(float);
+  size_t smem = (size_t)nm * 4 * sizeof(float);
   S6_REQUIRE(smem <= 200 * 1024);
   S6_CHECK(cudaFuncSetAttribute(coarse_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(s6_cdiv(n2, SEL_PP), B);

@@ -15,6 +15,10 @@
 //                           transpose-reduce, each lane adds its 8-column share into E ; pass DIST (runs first): rows are
 //                           pairs, E = acc + bias with full-line stores (epilogue.cuh).
 // E is fp32 or bf16.  Accuracy: operands rounded to bf16 (sin/cos via MUFU), fp32 accumulation.
+#include <cuda.h>
+
+#include <cstring>
+
 #include "epilogue.cuh"
 #include "tc.cuh"
 
@@ -81,7 +85,8 @@ template <int MODE, typename ET>
 __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const float* __restrict__ T, long long npairs,
                                                                       const float* __restrict__ div_term,
                                                                       const __nv_bfloat16* __restrict__ Wb,   // (256 out, 256 in) bf16
-                                                                      const float* __restrict__ bias, ET* __restrict__ E) {
+                                                                      const float* __restrict__ bias, ET* __restrict__ E,
+                                                                      const __grid_constant__ CUtensorMap tmE) {
   constexpr int ASTAGES = Cfg<MODE>::kStages, KPS = Cfg<MODE>::kKps, STAGE_BYTES = KPS * A_SLAB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -156,7 +161,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
       float x[NT];
 #pragma unroll
       for (int j = 0; j < NT; ++j) x[j] = xn[j];
-      fetch(tile + gridDim.x, xn);
 #pragma unroll
       for (int kb0 = 0; kb0 < KBLOCKS; kb0 += KPS, ++g) {
         const int s = (int)(g % ASTAGES);
@@ -185,6 +189,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
         tc::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&full_bar[s]);
+        // next tile's indices: issued behind the first fence (a fence waits for the thread's outstanding loads, so a prefetch
+        // issued before it stalls the first k-block by the full load latency -- ncu r02_geo_v2); k-block 1 covers the latency
+        if (kb0 == 0) fetch(tile + gridDim.x, xn);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -216,24 +223,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
   } else {
     // ------------------------------------------------------------------ epilogue: warp w <-> TMEM lanes 32w .. 32w+31
     long long it = 0;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int acc = (int)(it & 1);
-      const int quad = warp & 3, c0 = (warp < 4) ? 0 : 4;      // this warp's TMEM lane quadrant and its 4 column chunks
-      const int r = quad * 32 + lane;
-      // angle pass: E already holds proj_d(...) + biases from the distance pass; fetch this lane's 8 x 8 columns of it before
-      // waiting for the accumulator so the read-modify-write latency hides behind the MMAs of the tile
-      constexpr int RAW = (MODE == 0) ? 4 : 1;
-      uint4 raw[RAW][sizeof(ET) == 4 ? 2 : 1];
+    const int quad = warp & 3, c0 = (warp < 4) ? 0 : 4;        // this warp's TMEM lane quadrant and its 4 column chunks
+    const int r = quad * 32 + lane;
+    // angle pass: E already holds proj_d(...) + biases from the distance pass.  This lane's 4 x 8 columns of the NEXT tile are
+    // fetched while the current tile is processed: issued only one accumulator wait ahead, the add stalled on DRAM latency
+    constexpr int RAW = (MODE == 0) ? 4 : 1;
+    constexpr int RU = sizeof(ET) == 4 ? 2 : 1;
+    uint4 raw[RAW][RU], rawn[RAW][RU];
+    auto fetch_e = [&](long long tile, uint4 (&dst)[RAW][RU]) {
       if (MODE == 0) {
         const long long pair = tile * 32 + (r >> 2);
-        if (pair < npairs) {
+        if (tile < ntiles && pair < npairs) {
           const uint4* src = reinterpret_cast<const uint4*>(E + pair * 256 + (r & 3) * 8);
 #pragma unroll
-          for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < RAW; ++c)
 #pragma unroll
-            for (int u = 0; u < (int)(sizeof(ET) == 4 ? 2 : 1); ++u) raw[c][u] = src[(c0 + c) * (sizeof(ET) == 4 ? 8 : 4) + u];
+            for (int u = 0; u < RU; ++u) dst[c][u] = src[(c0 + c) * (sizeof(ET) == 4 ? 8 : 4) + u];
         }
       }
+    };
+    fetch_e(blockIdx.x, rawn);
+    uint32_t st_pending = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+#pragma unroll
+      for (int c = 0; c < RAW; ++c)
+#pragma unroll
+        for (int u = 0; u < RU; ++u) raw[c][u] = rawn[c][u];
+      fetch_e(tile + gridDim.x, rawn);
       tc::mbar_wait_suspend(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
       tc::tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
@@ -292,32 +309,95 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) geo_embed_tc_kernel(const floa
           }
         }
       } else {
-        float* stage = reinterpret_cast<float*>(smem + KBLOCKS * W_SLAB + ASTAGES * STAGE_BYTES) +
-                       (quad + c0) * epi::WARP_STAGE_FLOATS;
+        uint8_t* stage_b = smem + KBLOCKS * W_SLAB + ASTAGES * STAGE_BYTES;
         const long long row0 = tile * 128 + quad * 32;
         (void)raw;
+        if constexpr (sizeof(ET) == 2) {
+          // rows = pairs: E = acc + (b_a + b_d).  The warp packs two chunks (64 columns) of its 32 rows into a SWIZZLE_128B
+          // 4 KB stage and one lane hands it to the TMA unit: no read-back, no per-lane global stores, rows past npairs are
+          // clipped by the tensor map.  The stage is reused once the previous store has been read out of it.
+          uint8_t* stage = stage_b + (quad + c0) * 4096;
 #pragma unroll 1
-        for (int c = c0; c < c0 + 4; ++c) {
-          float v[32];
-          tc::tmem_ld32(t_addr + c * 32, v);
-          // rows = pairs: E = acc + (b_a + b_d), written with full-line stores (npairs fits an int for any realistic batch).
-          // The bias comes from shared memory: as a global load per chunk it was the epilogue's long-scoreboard stall (ncu r02_geo).
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int c = c0 + 2 * h + cc;
+              float v[32];
+              tc::tmem_ld32(t_addr + c * 32, v);
+              uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(&sbias[c * 32 + i * 4]);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+              for (int i = 0; i < 8; ++i) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&sbias[c * 32 + i * 4]);
+                w[2 * i] = tc::pack_bf16(v[4 * i] + b4.x, v[4 * i + 1] + b4.y);
+                w[2 * i + 1] = tc::pack_bf16(v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+              }
+              if (cc == 0 && st_pending) {
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<uint4*>(stage + lane * 128 + (((cc * 4 + j) ^ (lane & 7)) << 4)) =
+                    make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmE)),
+                           "r"(tc::smem_u32(stage)), "r"((c0 + 2 * h) * 32), "r"((int)row0)
+                           : "memory");
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            st_pending = 1;
           }
-          epi::process_chunk<ET, 0, false, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, nullptr, nullptr, 0, E, 256);
+        } else {
+          float* stage = reinterpret_cast<float*>(stage_b) + (quad + c0) * epi::WARP_STAGE_FLOATS;
+#pragma unroll 1
+          for (int c = c0; c < c0 + 4; ++c) {
+            float v[32];
+            tc::tmem_ld32(t_addr + c * 32, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&sbias[c * 32 + i * 4]);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+            epi::process_chunk<ET, 0, false, false>(v, stage, lane, (int)row0, (int)npairs, c * 32, 256, 1.f, nullptr, nullptr, 0, E, 256);
+          }
         }
       }
       tc::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&tmem_empty_bar[acc]);      // one arrival per warp: 256 arrivals on one word serialise
     }
+    if (st_pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc::tc_fence_before_sync();
   __syncthreads();
   if (warp == MMA_WARP) tc::tmem_dealloc(tmem_base, 512);
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// E (npairs, 256) bf16 as a 2-D tensor, box = 64 columns x 32 rows, SWIZZLE_128B (the epilogue's stage layout)
+int make_e_map(CUtensorMap* map, const void* E, long long npairs) {
+  static EncodeFn enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      return 999;
+    enc = reinterpret_cast<EncodeFn>(p);
+  }
+  cuuint64_t gdim[2] = {256, (cuuint64_t)npairs};
+  cuuint64_t gstride[1] = {512};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(E), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + (int)r;
 }
 
 template <int MODE, typename ET>
@@ -329,7 +409,13 @@ int launch_pass(const float* T, long long npairs, const float* div_term, const _
   const long long per = (MODE == 0) ? 32 : 128;
   const long long ntiles = (npairs + per - 1) / per;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, NUM_THREADS, Cfg<MODE>::kSmem, st>>>(T, npairs, div_term, W, bias, E);
+  CUtensorMap tmE;
+  memset(&tmE, 0, sizeof(tmE));
+  if (MODE == 1 && sizeof(ET) == 2) {
+    const int rc = make_e_map(&tmE, E, npairs);
+    if (rc) return rc;
+  }
+  kern<<<grid, NUM_THREADS, Cfg<MODE>::kSmem, st>>>(T, npairs, div_term, W, bias, E, tmE);
   return (int)cudaGetLastError();
 }
 

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
   uint8_t* w2s = a2 + SLAB;
   uint8_t* w3s = w2s + W2_SLAB;
   __shared__ __align__(16) float w1s[32 * 8];
-  __shared__ float b1s[32], b2s[64], b3s[128];
+  __shared__ __align__(16) float b1s[32], b2s[64], b3s[128];
   __shared__ __align__(8) uint64_t a1_full, d2_full, a2_full, d3_full;
   __shared__ uint32_t tmem_slot;
 
@@ -100,20 +100,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
     const int r = tid;
     const uint32_t t_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t ph = 0;
+    // gather pipeline: the neighbour index of tile t+2 and the coordinates of tile t+1 are in flight while tile t is computed.
+    // They are issued behind the tile's LAST fence.proxy.async (a fence waits for the thread's outstanding loads).
+    auto load_idx = [&](long long tile) -> int {
+      const long long gp = tile * PPT + r / NS;
+      return (tile < ntiles && gp < total_points) ? __ldg(idx + gp * NS + (r % NS)) : -1;
+    };
+    auto load_x = [&](long long tile, int j, float (&xx)[6]) {
+      const long long gp = tile * PPT + r / NS;
+      if (j >= 0) {
+        const long long b = gp / N;
+        const float* pi = pts + gp * 3;
+        const float* pj = pts + (b * N + j) * 3;
+        const float jx = __ldg(pj), jy = __ldg(pj + 1), jz = __ldg(pj + 2);
+        xx[0] = jx - __ldg(pi); xx[1] = jy - __ldg(pi + 1); xx[2] = jz - __ldg(pi + 2); xx[3] = jx; xx[4] = jy; xx[5] = jz;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 6; ++e) xx[e] = 0.f;
+      }
+    };
+    float xn[6];
+    load_x(blockIdx.x, load_idx(blockIdx.x), xn);
+    int jn = load_idx((long long)blockIdx.x + gridDim.x);
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-      const long long gp = tile * PPT + r / NS;                 // global point index b*N + i
-      const bool valid = gp < total_points;
       // ---- layer 1
       {
-        float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid) {
-          const long long b = gp / N;
-          const int j = idx[gp * NS + (r % NS)];
-          const float* pi = pts + gp * 3;
-          const float* pj = pts + (b * N + j) * 3;
-          const float jx = pj[0], jy = pj[1], jz = pj[2];
-          x[0] = jx - pi[0]; x[1] = jy - pi[1]; x[2] = jz - pi[2]; x[3] = jx; x[4] = jy; x[5] = jz;
-        }
+        float x[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[e] = xn[e];
         uint8_t* row_ptr = a1 + r * 128;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -150,10 +164,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t w[4];
+            const float4 ba = *reinterpret_cast<const float4*>(&b2s[half * 32 + c * 8]);
+            const float4 bb = *reinterpret_cast<const float4*>(&b2s[half * 32 + c * 8 + 4]);
+            const float bq[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int o = c * 8 + q * 2;
-              w[q] = tc::pack_bf16(fmaxf(v[o] + b2s[half * 32 + o], 0.f), fmaxf(v[o + 1] + b2s[half * 32 + o + 1], 0.f));
+              w[q] = tc::pack_bf16(fmaxf(v[o] + bq[q * 2], 0.f), fmaxf(v[o + 1] + bq[q * 2 + 1], 0.f));
             }
             *reinterpret_cast<uint4*>(row_ptr + (((half * 4 + c) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -162,6 +179,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
         tc::fence_proxy_async_smem();
         tc::mbar_arrive(&a2_full);
       }
+      load_x(tile + gridDim.x, jn, xn);
+      jn = load_idx(tile + 2LL * gridDim.x);
       // ---- layer 3 epilogue: this thread is output channel `tid`; columns [32 c, 32 c + 32) are rows of the tile
       tc::mbar_wait(&d3_full, ph);
       tc::tc_fence_after_sync();

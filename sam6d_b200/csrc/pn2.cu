@@ -445,78 +445,77 @@ S6_API int sam6d_ball_query(const float* new_xyz, const float* xyz, int b, int n
 }
 
 // Two concentric ball queries over the same clouds in one sweep (PositionalEncoding groups every point at r1/ns1 and r2/ns2,
-// fine_point_matching.py:104-109): the distance is computed once, each list keeps its own counter and first hit.
-__global__ void __launch_bounds__(256) ball_query_pair_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n,
-                                                              int m, float ra2, int nsa, float rb2, int nsb, int* __restrict__ idxa,
-                                                              int* __restrict__ idxb, int* __restrict__ cnta_out,
-                                                              int* __restrict__ cntb_out) {
-  extern __shared__ float sp[];
-  const int TILE = 1024;
-  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * 8 + warp;
+// fine_point_matching.py:104-109).  THREAD per query, candidates broadcast from shared memory as (x, y, z, -) quadruples: one
+// LDS.128 serves 32 queries and a candidate costs ~9 issue slots per warp (3 subtractions, the reference's mul/fma/fma chain,
+// two compares) against ~25 per 32 candidates for the warp-per-query ballot scan it replaces (ncu: that one was issue-bound at
+// 0.47 ms for 131 072 queries x 2048 candidates).  Hits are rare (a few per cent), so the list bookkeeping sits behind a branch.
+// The order of a list is the scan order, i.e. ascending index, as in ball_query_gpu.cu:17-49.
+constexpr int BQP_THREADS = 256, BQP_TILE = 2048;
+__global__ void __launch_bounds__(BQP_THREADS) ball_query_pair_kernel(const float* __restrict__ new_xyz, const float* __restrict__ xyz, int n,
+                                                                      int m, float ra2, int nsa, float rb2, int nsb, int* __restrict__ idxa,
+                                                                      int* __restrict__ idxb, int* __restrict__ cnta_out,
+                                                                      int* __restrict__ cntb_out) {
+  __shared__ float4 sp[BQP_TILE];
+  const int b = blockIdx.y, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * BQP_THREADS + threadIdx.x;
+  const bool live = j < m;
   const float* p = xyz + (size_t)b * n * 3;
   float nx = 0.f, ny = 0.f, nz = 0.f;
-  if (j < m) {
+  if (live) {
     const float* q = new_xyz + ((size_t)b * m + j) * 3;
     nx = q[0]; ny = q[1]; nz = q[2];
   }
-  int* oa = (j < m) ? idxa + ((size_t)b * m + j) * nsa : nullptr;
-  int* ob = (j < m) ? idxb + ((size_t)b * m + j) * nsb : nullptr;
+  int* oa = idxa + ((size_t)b * m + (live ? j : 0)) * nsa;
+  int* ob = idxb + ((size_t)b * m + (live ? j : 0)) * nsb;
   int ca = 0, cb = 0, fa = 0, fb = 0;
-  const unsigned below = (1u << lane) - 1u;
-  for (int base = 0; base < n; base += TILE) {
-    int tn = min(TILE, n - base);
+  for (int base = 0; base < n; base += BQP_TILE) {
+    const int tn = min(BQP_TILE, n - base);
     __syncthreads();
-    for (int i = threadIdx.x; i < tn * 3; i += blockDim.x) sp[i] = p[(size_t)base * 3 + i];
+    for (int i = threadIdx.x; i < tn; i += BQP_THREADS) {
+      const float* q = p + (size_t)(base + i) * 3;
+      sp[i] = make_float4(q[0], q[1], q[2], 0.f);
+    }
     __syncthreads();
-    if (j < m && (ca < nsa || cb < nsb)) {
-      // two groups of 32 candidates per step: both distances and all four ballots are issued before the (serial) list
-      // bookkeeping, which halves the dependent-latency chain of the scan
-      for (int k0 = 0; k0 < tn && (ca < nsa || cb < nsb); k0 += 64) {
-        float d2[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int k = k0 + u * 32 + lane;
-          d2[u] = INFINITY;
-          if (k < tn) {
-            float dx = nx - sp[k * 3 + 0], dy = ny - sp[k * 3 + 1], dz = nz - sp[k * 3 + 2];
-            float d = __fmul_rn(dx, dx);
-            d = __fmaf_rn(dy, dy, d);
-            d2[u] = __fmaf_rn(dz, dz, d);
+    if (live) {
+#pragma unroll 4
+      for (int k = 0; k < tn; ++k) {
+        const float4 c = sp[k];
+        const float dx = nx - c.x, dy = ny - c.y, dz = nz - c.z;
+        float d = __fmul_rn(dx, dx);
+        d = __fmaf_rn(dy, dy, d);
+        d = __fmaf_rn(dz, dz, d);
+        if (d < rb2) {
+          if (cb < nsb) {
+            if (cb == 0) fb = base + k;
+            ob[cb] = base + k;
           }
-        }
-        unsigned mb[2], ma[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          mb[u] = __ballot_sync(0xffffffffu, d2[u] < rb2);
-          ma[u] = __ballot_sync(0xffffffffu, d2[u] < ra2);
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int k = k0 + u * 32 + lane;
-          if (mb[u] && cb < nsb) {
-            if (cb == 0) fb = base + k0 + u * 32 + __ffs(mb[u]) - 1;
-            int pos = cb + __popc(mb[u] & below);
-            if (d2[u] < rb2 && pos < nsb) ob[pos] = base + k;
-            cb += __popc(mb[u]);
-          }
-          if (ma[u] && ca < nsa) {
-            if (ca == 0) fa = base + k0 + u * 32 + __ffs(ma[u]) - 1;
-            int pos = ca + __popc(ma[u] & below);
-            if (d2[u] < ra2 && pos < nsa) oa[pos] = base + k;
-            ca += __popc(ma[u]);
+          ++cb;
+          if (d < ra2) {
+            if (ca < nsa) {
+              if (ca == 0) fa = base + k;
+              oa[ca] = base + k;
+            }
+            ++ca;
           }
         }
       }
     }
   }
-  if (j < m) {
-    int c = min(ca, nsa);
-    for (int l = c + lane; l < nsa; l += 32) oa[l] = (ca > 0) ? fa : 0;
-    if (cnta_out && lane == 0) cnta_out[(size_t)b * m + j] = c;
-    c = min(cb, nsb);
-    for (int l = c + lane; l < nsb; l += 32) ob[l] = (cb > 0) ? fb : 0;
-    if (cntb_out && lane == 0) cntb_out[(size_t)b * m + j] = c;
+  // pad the lists with their first entry (0 when empty), warp-cooperatively so that the stores are contiguous
+  ca = min(ca, nsa); cb = min(cb, nsb);
+  if (live) {
+    if (cnta_out) cnta_out[(size_t)b * m + j] = ca;
+    if (cntb_out) cntb_out[(size_t)b * m + j] = cb;
+  }
+  const int j0 = j - lane;
+  for (int q = 0; q < 32; ++q) {
+    if (j0 + q >= m) break;
+    const int qa = __shfl_sync(0xffffffffu, ca, q), qfa = __shfl_sync(0xffffffffu, fa, q);
+    const int qb = __shfl_sync(0xffffffffu, cb, q), qfb = __shfl_sync(0xffffffffu, fb, q);
+    int* la = idxa + ((size_t)b * m + j0 + q) * nsa;
+    int* lb = idxb + ((size_t)b * m + j0 + q) * nsb;
+    for (int l = qa + lane; l < nsa; l += 32) la[l] = qfa;
+    for (int l = qb + lane; l < nsb; l += 32) lb[l] = qfb;
   }
 }
 
@@ -526,8 +525,8 @@ S6_API int sam6d_ball_query_pair(const float* new_xyz, const float* xyz, int b, 
   S6_REQUIRE(new_xyz && xyz && idx_a && idx_b && b >= 0 && n > 0 && m >= 0 && nsample_a > 0 && nsample_b > 0 &&
              radius_a <= radius_b);
   if (b == 0 || m == 0) return 0;
-  dim3 grid(s6_cdiv(m, 8), b);
-  ball_query_pair_kernel<<<grid, 256, 1024 * 3 * sizeof(float), s6_stream(stream)>>>(
+  dim3 grid(s6_cdiv(m, BQP_THREADS), b);
+  ball_query_pair_kernel<<<grid, BQP_THREADS, 0, s6_stream(stream)>>>(
       new_xyz, xyz, n, m, radius_a * radius_a, nsample_a, radius_b * radius_b, nsample_b, idx_a, idx_b, cnt_a, cnt_b);
   S6_LAUNCH_CHECK();
   return 0;
