@@ -543,7 +543,11 @@ def main():
     # (the stream over E; the attention kernel that consumes its scores; the geometric-embedding kernel that writes E)
     from sam6d_b200 import pem as _pem
     rpe_name = "sam6d_rpe_scores_tc" if (args.precision == "bf16" and _pem.RPE_TC) else "sam6d_rpe_scores"
-    _, _, kall = timed(step_resident, args.steps, profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_geo_embed_tc"])
+    padded = rpe_name == "sam6d_rpe_scores_tc" and _pem.PADDED_BIAS
+    if padded:
+        rpe_name = "sam6d_rpe_scores_tc_ld"              # score planes with padded rows, consumed by sam6d_attn_tc_bias_ld
+    _, _, kall = timed(step_resident, args.steps,
+                       profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_attn_tc_bias_ld", "sam6d_geo_embed_tc"])
     kms = kall[rpe_name]
     for i in range(2):
         step_e2e(i)
@@ -572,6 +576,8 @@ def main():
         # sam6d_attn_tc call of a block: self, cross, cross)
         att = kall.get("sam6d_attn_tc") or []
         att_bias = att[0::3] if len(att) == 3 * len(kms) else []
+        if padded:
+            att_bias = kall.get("sam6d_attn_tc_bias_ld") or []
         att_avg_ms = sum(att_bias) / len(att_bias) if att_bias else None
         attention_frac = alg_bytes / ((k_avg_ms + att_avg_ms) * 1e-3) / 1e9 / pk["hbm"] if att_avg_ms else None
         geo = kall.get("sam6d_geo_embed_tc") or []

@@ -211,6 +211,8 @@ int sam6d_rpe_scores(const void* E, int e_is_bf16, const float* U, long long u_l
 /* the same term on TMA + tcgen05 (bf16 path, the HBM-bound stream over E): E (B,S,S,256) bf16, U (B*S, 4*256) bf16
  * contiguous, S <= 200  ->  SP (B,4,S,S) f32 */
 int sam6d_rpe_scores_tc(const void* E, const void* U, int B, int S, float* SP, void* stream);
+/* the same with padded score rows: SP (B,4,S,sp_ld), sp_ld >= S; with sp_ld a multiple of 4 sam6d_attn_tc_bias_ld streams it */
+int sam6d_rpe_scores_tc_ld(const void* E, const void* U, int B, int S, float* SP, int sp_ld, void* stream);
 /* softmax((Q K^T + bias) * scale) V, head dim 64, Sk <= 256 (MultiHeadAttention :109-148, RPEMultiHeadAttention :369-406) */
 int sam6d_mha(const float* Q, long long q_ld, long long q_bs, const float* K, long long k_ld, long long k_bs, const float* V,
               long long v_ld, long long v_bs, const float* bias, int B, int H, int Sq, int Sk, float scale, float* O,
@@ -223,6 +225,12 @@ int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* K, long
                   long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
                   const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
                   int out_is_bf16, long long out_ld, void* stream);
+/* sam6d_attn_tc (head dim 64) with a dense fp32 bias in padded planes (B,H,Sq,bias_ld), bias_ld >= Sk a multiple of 4 floats,
+ * 16-byte aligned base: the bias tiles stream through cp.async four chunks ahead of the softmax (RPEMultiHeadAttention,
+ * PEM/model/transformer.py:395-399) */
+int sam6d_attn_tc_bias_ld(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                          long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, const float* bias, long long bias_ld,
+                          float scale, void* out, int out_is_bf16, long long out_ld, void* stream);
 /* sam6d_attn_tc (no bias) over a window of keys: batch b's keys are rows [b*k_brows + k_row0, +Sk) of K and columns
  * [v_col0, +Sk) of its V^T rows; lse (B,H,Sq) f32 or NULL receives the log-sum-exp of the scaled scores */
 int sam6d_attn_tc_ex(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,

@@ -44,6 +44,7 @@ struct AttnArgs {
   // caller can merge further keys (the 257th token of a DINOv2 sequence) into the result
   int k_brows, k_row0, v_col0;
   float* lse;
+  long long bias_ld;     // BIAS_MODE 4: row stride of the bias planes (B,H,Sq,bias_ld), a multiple of 4 floats, >= Sk
 };
 
 // COMPACT (head dim 64, no / dense bias: the PEM layers): P and the bias staging alias the Q / K slabs (dead once the score MMA
@@ -51,7 +52,7 @@ struct AttnArgs {
 // and 256 TMEM columns and two CTAs share an SM -- one CTA's serial load -> MMA -> softmax -> MMA -> store chain hides behind
 // the other's.
 template <int D, int BIAS_MODE>
-constexpr bool kCompact = (D == 64) && (BIAS_MODE == 0 || BIAS_MODE == 1);
+constexpr bool kCompact = (D == 64) && (BIAS_MODE == 0 || BIAS_MODE == 1 || BIAS_MODE == 4);
 
 template <int D, int BIAS_MODE, typename OT>
 __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -192,6 +193,55 @@ __global__ void __launch_bounds__(NUM_THREADS, kCompact<D, BIAS_MODE> ? 2 : 1) a
     float* my_stage = COMPACT ? reinterpret_cast<float*>(p_s + warp * 32 * 128) : bstage + warp * (32 * 33);
     auto st_w = [&](int rr, int col) { return COMPACT ? rr * 32 + (col ^ rr) : rr * 33 + col; };
     int kh_run = 0, kw_run = 0;                                            // (kh, kw) of the running key column, no div / mod
+    if constexpr (BIAS_MODE == 4) {
+      // Padded bias planes (row stride a multiple of 16 bytes): the warp's 32 x 32 tile of a chunk is copied with 8 cp.async of 16
+      // bytes per lane straight into shared memory -- no registers, so FOUR chunks are in flight while one is consumed (a register
+      // prefetch of one chunk spilled; fetching chunk by chunk left a full L2 round trip in front of each of the 7 chunks).
+      // Buffer i = this warp's 32 rows of P slab i (only this warp ever writes them); 16-byte pieces XOR-swizzled by row so that
+      // the thread-per-row read-back is conflict-free per quarter warp.
+      const long long ld = a.bias_ld;
+      const float* wb4 = a.bias + (((size_t)b * a.H + h) * a.Sq + wrow0) * ld;
+      auto issue = [&](int c) {
+        if (c < nchunk) {
+          const uint32_t dst0 = tc::smem_u32(p_s + (c & 3) * P_SLAB + warp * 4096);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int id = i * 32 + lane, rr = id >> 3, pc = id & 7;
+            const int col = c * 32 + pc * 4;
+            if (col < ld) {
+              const float* src = wb4 + (long long)min(rr, rows_ok - 1) * ld + col;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + rr * 128 + ((pc ^ (rr & 7)) << 4)), "l"(src) : "memory");
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+#pragma unroll
+      for (int c = 0; c < 4; ++c) issue(c);
+      for (int c = 0; c < nchunk; ++c) {
+        float v[32];
+        tc::tmem_ld32(t_addr + c * 32, v);
+        asm volatile("cp.async.wait_group 3;" ::: "memory");
+        __syncwarp();
+        const uint8_t* rowp = p_s + (c & 3) * P_SLAB + warp * 4096 + lane * 128;
+#pragma unroll
+        for (int pc = 0; pc < 8; ++pc) {
+          const float4 b4 = *reinterpret_cast<const float4*>(rowp + ((pc ^ (lane & 7)) << 4));
+          const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = pc * 4 + e, col = c * 32 + j;
+            float x = -INFINITY;
+            if (col < Sk) { x = (v[j] + bq[e]) * a.scale; mx = fmaxf(mx, x); }
+            v[j] = x;
+          }
+        }
+        tc::tmem_st32(t_addr + c * 32, v);
+        __syncwarp();                                     // every lane has read the buffer before it is refilled
+        issue(c + 4);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else
     for (int c = 0; c < nchunk; ++c) {
       float v[32];
       tc::tmem_ld32(t_addr + c * 32, v);
@@ -386,9 +436,12 @@ namespace {
 int attn_tc_launch(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
                    long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, int bias_mode, const float* bias,
                    const void* rel_h, const float* rel_w, int Hs, int Ws, const float* bv, float scale, void* out,
-                   int out_is_bf16, long long out_ld, int k_brows, int k_row0, int v_col0, float* lse, void* stream) {
+                   int out_is_bf16, long long out_ld, int k_brows, int k_row0, int v_col0, float* lse, void* stream,
+                   long long bias_ld = 0) {
   S6_REQUIRE(Q && K && Vt && out && B >= 0 && H > 0 && Sq > 0 && Sk > 0 && Sk <= MAXK);
-  S6_REQUIRE((head_dim == 64 || head_dim == 80) && bias_mode >= 0 && bias_mode <= 3);
+  S6_REQUIRE((head_dim == 64 || head_dim == 80) && bias_mode >= 0 && bias_mode <= 4);
+  if (bias_mode == 4)
+    S6_REQUIRE(bias && head_dim == 64 && bias_ld >= Sk && (bias_ld % 4) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
   S6_REQUIRE((q_ld % 8) == 0 && (k_ld % 8) == 0 && (vt_ld % 8) == 0 && (q_col0 % 8) == 0 && (k_col0 % 8) == 0);
   S6_REQUIRE(k_brows >= k_row0 + Sk && k_row0 >= 0 && v_col0 >= 0 && (v_col0 % 8) == 0);   // TMA boxes start on 16-byte boundaries
   if (bias_mode == 1 || bias_mode == 3) S6_REQUIRE(bias != nullptr);
@@ -404,13 +457,14 @@ int attn_tc_launch(const void* Q, long long q_ld, int q_col0, const void* K, lon
   if (rc) return rc;
   rc = make_map(&tv, Vt, (long long)B * H * head_dim, vt_ld, vt_ld, 64, head_dim);
   if (rc) return rc;
-  AttnArgs a{bias, rel_h, rel_w, Q, q_ld, q_col0, bv, out, out_ld, H, Sq, Sk, N1, Hs, Ws, k_col0, scale, k_brows, k_row0, v_col0, lse};   // mode 2: rel_h = packed blob
+  AttnArgs a{bias, rel_h, rel_w, Q, q_ld, q_col0, bv, out, out_ld, H, Sq, Sk, N1, Hs, Ws, k_col0, scale, k_brows, k_row0, v_col0, lse, bias_ld};   // mode 2: rel_h = packed blob
   cudaStream_t st = s6_stream(stream);
 #define ATT_LAUNCH(DD, MM) (out_is_bf16 ? launch<DD, MM, __nv_bfloat16>(tq, tk, tv, a, B, st) : launch<DD, MM, float>(tq, tk, tv, a, B, st))
   if (head_dim == 64) {
     if (bias_mode == 0) return ATT_LAUNCH(64, 0);
     if (bias_mode == 1) return ATT_LAUNCH(64, 1);
     if (bias_mode == 3) return ATT_LAUNCH(64, 3);
+    if (bias_mode == 4) return ATT_LAUNCH(64, 4);
     return ATT_LAUNCH(64, 2);
   }
   if (bias_mode == 0) return ATT_LAUNCH(80, 0);
@@ -456,6 +510,16 @@ S6_API int sam6d_attn_tc(const void* Q, long long q_ld, int q_col0, const void* 
                          int out_is_bf16, long long out_ld, void* stream) {
   return attn_tc_launch(Q, q_ld, q_col0, K, k_ld, k_col0, Vt, vt_ld, B, H, Sq, Sk, head_dim, bias_mode, bias, rel_h, rel_w, Hs, Ws, bv,
                         scale, out, out_is_bf16, out_ld, Sk, 0, 0, nullptr, stream);
+}
+
+// sam6d_attn_tc with a dense fp32 bias whose planes are PADDED: (B,H,Sq,bias_ld), bias_ld >= Sk a multiple of 4 floats, base
+// 16-byte aligned (what sam6d_rpe_scores_tc_ld writes).  Head dim 64.  The bias tiles then stream through cp.async, four chunks
+// ahead of the softmax.
+S6_API int sam6d_attn_tc_bias_ld(const void* Q, long long q_ld, int q_col0, const void* K, long long k_ld, int k_col0, const void* Vt,
+                                 long long vt_ld, int B, int H, int Sq, int Sk, int head_dim, const float* bias, long long bias_ld,
+                                 float scale, void* out, int out_is_bf16, long long out_ld, void* stream) {
+  return attn_tc_launch(Q, q_ld, q_col0, K, k_ld, k_col0, Vt, vt_ld, B, H, Sq, Sk, head_dim, 4, bias, nullptr, nullptr, 0, 0, nullptr,
+                        scale, out, out_is_bf16, out_ld, Sk, 0, 0, nullptr, stream, bias_ld);
 }
 
 // sam6d_attn_tc without bias over a WINDOW of keys: batch b's keys are rows [b*k_brows + k_row0, +Sk) of K and columns

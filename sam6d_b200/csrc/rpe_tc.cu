@@ -36,7 +36,7 @@ constexpr int SMEM = STAGES * STAGE_BYTES + 1024;
 
 __global__ void __launch_bounds__(THREADS, 1) rpe_scores_tc_kernel(const __grid_constant__ CUtensorMap tmE,
                                                                    const __grid_constant__ CUtensorMap tmU, int S, int total_rows,
-                                                                   float* __restrict__ SP) {
+                                                                   float* __restrict__ SP, int sp_ld) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar[2], tmem_empty_bar[2];
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_scores_tc_kernel(const __grid_
     const int ew = warp - 2, quad = warp & 3, t = ew >> 2;
     const int m = t * 128 + quad * 32 + lane;
     const bool tile_on = t < ntile;
-    const size_t SS = (size_t)S * S;
+    const size_t SS = (size_t)S * sp_ld;
     int g = 0;
     for (int i0 = 0; i0 < nrows; i0 += GROUP, ++g) {
       const int buf = g & 1, cnt = min(GROUP, nrows - i0);
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 1) rpe_scores_tc_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < GROUP; ++j) {
             if (j < cnt) {
-              float* o = SP + ((size_t)b * 4 * S + n) * S + m;
+              float* o = SP + ((size_t)b * 4 * S + n) * sp_ld + m;
 #pragma unroll
               for (int h = 0; h < 4; ++h) o[h * SS] = __uint_as_float(v[j][h]);
               if (++n == S) { n = 0; ++b; }
@@ -195,8 +195,9 @@ int make_map(CUtensorMap* map, const void* ptr, long long rows, int box_rows) {
 
 // E (B,S,S,256) bf16 contiguous, U (B*S, 4*256) bf16 contiguous (row = the four folded per-head queries of a token)
 // -> SP (B,4,S,S) fp32.  S <= 200.  The tcgen05 / TMA form of sam6d_rpe_scores (PEM/model/transformer.py:369-399).
-S6_API int sam6d_rpe_scores_tc(const void* E, const void* U, int B, int S, float* SP, void* stream) {
-  S6_REQUIRE(E && U && SP && B >= 0 && S > 0 && S <= SLAB_ROWS);
+namespace {
+int rpe_scores_tc_launch(const void* E, const void* U, int B, int S, float* SP, int sp_ld, void* stream) {
+  S6_REQUIRE(E && U && SP && B >= 0 && S > 0 && S <= SLAB_ROWS && sp_ld >= S);
   S6_REQUIRE((reinterpret_cast<uintptr_t>(E) & 15) == 0 && (reinterpret_cast<uintptr_t>(U) & 15) == 0);
   S6_REQUIRE((long long)B * S * S < 2000000000LL);
   if (B == 0) return 0;
@@ -210,7 +211,17 @@ S6_API int sam6d_rpe_scores_tc(const void* E, const void* U, int B, int S, float
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int total = B * S, grid = total < sms ? total : sms;
   S6_CHECK(cudaFuncSetAttribute(rpe_scores_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  S6_CHECK(s6_launch_pdl(rpe_scores_tc_kernel, dim3(grid), dim3(THREADS), SMEM, s6_stream(stream), tmE, tmU, S, total, SP));
+  S6_CHECK(s6_launch_pdl(rpe_scores_tc_kernel, dim3(grid), dim3(THREADS), SMEM, s6_stream(stream), tmE, tmU, S, total, SP, sp_ld));
   S6_LAUNCH_CHECK();
   return 0;
+}
+}  // namespace
+
+S6_API int sam6d_rpe_scores_tc(const void* E, const void* U, int B, int S, float* SP, void* stream) {
+  return rpe_scores_tc_launch(E, U, B, S, SP, S, stream);
+}
+// the same with padded score rows: SP (B,4,S,sp_ld), sp_ld >= S (columns [S, sp_ld) are left untouched); with sp_ld a multiple
+// of 4 the attention kernel can stream the planes with 16-byte copies (sam6d_attn_tc_bias_ld)
+S6_API int sam6d_rpe_scores_tc_ld(const void* E, const void* U, int B, int S, float* SP, int sp_ld, void* stream) {
+  return rpe_scores_tc_launch(E, U, B, S, SP, sp_ld, stream);
 }

@@ -440,6 +440,36 @@ def rpe_scores_tc(E: Tensor, U: Tensor) -> Tensor:
     return SP
 
 
+def rpe_scores_tc_padded(E: Tensor, U: Tensor) -> Tensor:
+    """rpe_scores_tc into planes whose rows are padded to a multiple of 16 keys: returns the (B,4,S,ld) f32 buffer (columns
+    [S, ld) are not written); attn_tc_padded_bias consumes it with 16-byte copies"""
+    _check(E, torch.bfloat16, "E", 4)
+    _check(U, torch.bfloat16, "U", 2)
+    B, S = E.shape[0], E.shape[1]
+    if U.shape != (B * S, 1024) or E.shape[3] != 256 or E.shape[2] != S:
+        raise RuntimeError("rpe_scores_tc: E (B,S,S,256), U (B*S,1024)")
+    ld = (S + 15) // 16 * 16
+    SP = torch.empty(B, 4, S, ld, dtype=torch.float32, device=E.device)
+    _lib.call("sam6d_rpe_scores_tc_ld", _p(E), _p(U), B, S, _p(SP), int(ld), _s())
+    return SP
+
+
+def attn_tc_padded_bias(Q: Tensor, q_col0: int, K: Tensor, k_col0: int, Vt: Tensor, B: int, H: int, Sq: int, Sk: int, D: int,
+                        scale: float, bias: Tensor, out_dtype=torch.bfloat16) -> Tensor:
+    """attn_tc with the dense bias in padded planes (B,H,Sq,ld) f32 (from rpe_scores_tc_padded); head dim 64"""
+    _check(Q, torch.bfloat16, "Q", 2)
+    _check(K, torch.bfloat16, "K", 2)
+    _check(Vt, torch.bfloat16, "Vt", 2)
+    _check(bias, torch.float32, "bias", 4)
+    if bias.shape[:3] != (B, H, Sq) or bias.shape[3] < Sk or bias.shape[3] % 4:
+        raise RuntimeError("attn_tc_padded_bias: bias (B,H,Sq,ld), ld >= Sk, ld % 4 == 0")
+    out = torch.empty(B * Sq, H * D, dtype=out_dtype, device=Q.device)
+    _lib.call("sam6d_attn_tc_bias_ld", _p(Q), _ll(Q.shape[1]), int(q_col0), _p(K), _ll(K.shape[1]), int(k_col0), _p(Vt), _ll(Vt.shape[1]),
+              int(B), int(H), int(Sq), int(Sk), int(D), _p(bias), _ll(bias.shape[3]), _f(scale), _p(out),
+              int(out_dtype == torch.bfloat16), _ll(H * D), _s())
+    return out
+
+
 def mha_raw(q_ptr, q_ld, q_bs, k_ptr, k_ld, k_bs, v_ptr, v_ld, v_bs, bias: Optional[Tensor], B, H, Sq, Sk, scale,
             o_ptr, o_ld, o_bs):
     _lib.call("sam6d_mha", ctypes.c_void_p(q_ptr), _ll(q_ld), _ll(q_bs), ctypes.c_void_p(k_ptr), _ll(k_ld), _ll(k_bs),

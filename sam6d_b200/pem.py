@@ -32,6 +32,7 @@ PRECISIONS = ("fp32", "bf16")
 # False = the five-launch form (GEMM, LayerNorm, GEMM, GEMM, LayerNorm) kept as its comparator
 FUSED_TAIL = os.environ.get("SAM6D_FUSED_TAIL", "1") != "0"
 # the relative-position score stream over E on TMA + tcgen05 (csrc/rpe_tc.cu); False = the CUDA-core kernel (csrc/attn.cu)
+PADDED_BIAS = os.environ.get("SAM6D_PADDED_BIAS", "1") != "0"
 RPE_TC = os.environ.get("SAM6D_RPE_TC", "1") != "0"
 
 
@@ -258,6 +259,11 @@ class GeometricTransformer(nn.Module):
         if RPE_TC and S <= 200 and emb.dtype == torch.bfloat16:
             # the folded rel-pos queries as bf16 rows: B operand of the TMA / tcgen05 stream over E (csrc/rpe_tc.cu)
             u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"], out_dtype=torch.bfloat16)                # (B*S, 4*C) bf16
+            if PADDED_BIAS:
+                # score planes with 16-key padded rows: the attention kernel streams them with 16-byte cp.async copies
+                sp = ops.rpe_scores_tc_padded(emb, u)
+                hid = ops.attn_tc_padded_bias(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), sp)
+                return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
             sp = ops.rpe_scores_tc(emb, u)
         else:
             u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                          # (B*S, 4*C) fp32

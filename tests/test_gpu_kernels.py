@@ -225,6 +225,29 @@ def test_rpe_scores_tensor_core(ops, B, S):
     torch.testing.assert_close(got, old, atol=2e-3, rtol=1e-4)
 
 
+@pytest.mark.parametrize("B,S", [(2, 197), (3, 65), (2, 130), (1, 200)])
+def test_padded_bias_attention_equals_dense_bias(ops, B, S):
+    """score planes with 16-key padded rows (sam6d_rpe_scores_tc_ld) + the cp.async-streamed bias of sam6d_attn_tc_bias_ld:
+    same scores bit for bit, same attention output bit for bit as the dense-bias kernel (identical arithmetic, other data path)"""
+    H, D = 4, 64
+    E = (torch.randn(B, S, S, 256, generator=G(1)) * 0.7).bfloat16().cuda()
+    U = torch.randn(B * S, 1024, generator=G(2)).bfloat16().cuda()
+    sp = ops.rpe_scores_tc(E, U)
+    spp = ops.rpe_scores_tc_padded(E, U)
+    assert spp.shape[3] % 16 == 0 and spp.shape[3] >= S
+    assert torch.equal(spp[..., :S], sp)
+    qk = torch.randn(B * S, 2 * H * D, generator=G(3)).bfloat16().cuda()
+    v = torch.randn(B * S, H * D, generator=G(4)).bfloat16().cuda()
+    # V^T per (batch, head): (B*H*D, ceil16(S))
+    N1 = (S + 15) // 16 * 16
+    vt = torch.zeros(B * H * D, N1, dtype=torch.bfloat16, device="cuda")
+    vt[:, :S] = v.view(B, S, H * D).permute(0, 2, 1).reshape(B * H * D, S)
+    want = ops.attn_tc(qk, 0, qk, H * D, vt, B, H, S, S, D, 0.125, bias=sp, out_dtype=torch.bfloat16)
+    spp[..., S:] = float("nan")                               # the padding must never be read into a result
+    got = ops.attn_tc_padded_bias(qk, 0, qk, H * D, vt, B, H, S, S, D, 0.125, spp)
+    assert torch.equal(got, want)
+
+
 @pytest.mark.parametrize("M", [100, 128, 1000, 12608, 40000])
 def test_transformer_tail_fused(ops, M):
     """csrc/tail_tc.cu against the same math in fp64 on the bf16-rounded operands (y and h rounded to bf16 where the kernel
