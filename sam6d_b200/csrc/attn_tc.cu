@@ -386,6 +386,8 @@ int launch(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, 
   auto kern = attn_tc_kernel<D, BM, OT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);   // two 97 KB CTAs per SM need the full carve-out
+  if (e != cudaSuccess) return (int)e;
   dim3 grid(s6_cdiv(a.Sq, QT), a.H, B);
   cudaError_t le = s6_launch_pdl(kern, grid, dim3(NUM_THREADS), smem, st, tq, tk, tv, a);
   if (le != cudaSuccess) return (int)le;

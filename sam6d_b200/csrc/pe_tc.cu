@@ -11,6 +11,8 @@
 // BatchNorm is folded into the 1x1 convs on the host.  The (B,6,N,ns) grouped tensor and the (B,128,N,ns) activations of the
 // reference are never materialised; padded duplicate samples are simply recomputed (they cannot change a max).
 // Four CTAs share an SM (56 KB smem, 128 TMEM columns each), so one tile's serial chain hides behind the others'.
+#include <cstdlib>
+
 #include "tc.cuh"
 
 namespace {
@@ -19,7 +21,11 @@ constexpr int ROWS = 128;
 constexpr int SLAB = ROWS * 128;            // [128 rows][64 bf16]
 constexpr int W2_SLAB = 64 * 128;           // [64 out][64 k] (k >= 32 unused)
 constexpr int W3_SLAB = 128 * 128;          // [128 out][64 k]
-constexpr int SMEM_BYTES = 2 * SLAB + W2_SLAB + W3_SLAB + 1024;
+// W2 (64 x 32) lives in the UNUSED K columns 32..63 of the first 64 rows of the A1 slab (layer 1 has 32 channels, so A1 fills only
+// K 0..31 of its 128-byte rows): with a slab of its own a CTA took 57 KB + static and only THREE fitted an SM while the grid was
+// sized for four (ncu r02_pe_sel: a second, quarter-filled wave).  (Letting A2 alias A1 instead was measured: 1.23 ms against
+// 0.86 ms for both radii, at any occupancy.)
+constexpr int SMEM_BYTES = 2 * SLAB + W3_SLAB + 1024;
 constexpr int NUM_THREADS = 160;
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -38,8 +44,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a1 = smem;
   uint8_t* a2 = a1 + SLAB;
-  uint8_t* w2s = a2 + SLAB;
-  uint8_t* w3s = w2s + W2_SLAB;
+  uint8_t* w3s = a2 + SLAB;
   __shared__ __align__(16) float w1s[32 * 8];
   __shared__ __align__(16) float b1s[32], b2s[64], b3s[128];
   __shared__ __align__(8) uint64_t a1_full, d2_full, a2_full, d3_full;
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
   // W2 (64 x 32) and W3 (128 x 64) bf16 -> K-major swizzled slabs
   for (int u = tid; u < 64 * 4; u += NUM_THREADS) {
     const int n = u >> 2, c = (u & 3) << 3;
-    *reinterpret_cast<uint4*>(w2s + tc::sw128_offset(n, c)) = *reinterpret_cast<const uint4*>(W2 + n * 32 + c);
+    *reinterpret_cast<uint4*>(a1 + tc::sw128_offset(n, 32 + c)) = *reinterpret_cast<const uint4*>(W2 + n * 32 + c);
   }
   for (int u = tid; u < 128 * 8; u += NUM_THREADS) {
     const int n = u >> 3, c = (u & 7) << 3;
@@ -78,16 +83,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc2 = tc::umma_idesc_bf16(128, 64), idesc3 = tc::umma_idesc_bf16(128, 128);
-      const uint32_t a1_addr = tc::smem_u32(a1), a2_addr = tc::smem_u32(a2), w2_addr = tc::smem_u32(w2s), w3_addr = tc::smem_u32(w3s);
+      const uint32_t a1_addr = tc::smem_u32(a1), a2_addr = tc::smem_u32(a2), w2_addr = tc::smem_u32(a1) + 64, w3_addr = tc::smem_u32(w3s);
       uint32_t ph = 0;
       for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ph ^= 1) {
-        tc::mbar_wait(&a1_full, ph);
+        tc::mbar_wait_suspend(&a1_full, ph);
         tc::tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 2; ++k)
           tc::umma_bf16(tmem_base, tc::umma_desc_sw128(a1_addr + k * 32), tc::umma_desc_sw128(w2_addr + k * 32), idesc2, k ? 1u : 0u);
         tc::umma_commit(&d2_full);
-        tc::mbar_wait(&a2_full, ph);
+        tc::mbar_wait_suspend(&a2_full, ph);
         tc::tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
         tc::mbar_arrive(&a1_full);
       }
       // ---- layer 2 epilogue -> A2
-      tc::mbar_wait(&d2_full, ph);
+      tc::mbar_wait_suspend(&d2_full, ph);
       tc::tc_fence_after_sync();
       {
         uint8_t* row_ptr = a2 + r * 128;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
       load_x(tile + gridDim.x, jn, xn);
       jn = load_idx(tile + 2LL * gridDim.x);
       // ---- layer 3 epilogue: this thread is output channel `tid`; columns [32 c, 32 c + 32) are rows of the tile
-      tc::mbar_wait(&d3_full, ph);
+      tc::mbar_wait_suspend(&d3_full, ph);
       tc::tc_fence_after_sync();
       {
         const float bias = b3s[tid];
@@ -223,13 +228,19 @@ S6_API int sam6d_pe_mlp_max_tc(const float* pts, const int* idx, int B, int N, i
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long total = (long long)B * N;
   const long long ntiles = (total + (128 / ns) - 1) / (128 / ns);
-  const int grid = (int)(ntiles < (long long)sms * 4 ? ntiles : (long long)sms * 4);
   cudaStream_t st = s6_stream(stream);
   const __nv_bfloat16* W2 = reinterpret_cast<const __nv_bfloat16*>(W2_bf16);
   const __nv_bfloat16* W3 = reinterpret_cast<const __nv_bfloat16*>(W3_bf16);
 #define PE_LAUNCH(NSV, OT)                                                                                                          \
   do {                                                                                                                              \
     S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<NSV, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));                 \
+    /* ask for the largest shared-memory carve-out: with the default the driver sizes it for fewer resident CTAs */                   \
+    S6_CHECK(cudaFuncSetAttribute(pe_tc_kernel<NSV, OT>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));                     \
+    /* four CTAs per SM: 4 x 128 TMEM columns, 4 x (49 KB + static) shared memory, 4 x 160 x 96 registers.  (The occupancy    */   \
+    /* API is not used: with the default carve-out it answered fewer and the grid shrank -- measured 1.23 ms instead of 0.86.) */   \
+    int per_sm = 4;                                                                                                                 \
+    if (const char* ev = getenv("SAM6D_PE_CTAS")) per_sm = atoi(ev) > 0 && atoi(ev) < per_sm ? atoi(ev) : per_sm;                   \
+    const int grid = (int)(ntiles < (long long)sms * per_sm ? ntiles : (long long)sms * per_sm);                                    \
     pe_tc_kernel<NSV, OT><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(pts, idx, N, total, W1, B1, W2, B2, W3, B3,                         \
                                                                  reinterpret_cast<OT*>(out), out_ld, out_off);                      \
   } while (0)

@@ -1,16 +1,16 @@
-"""summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list by kernel: python tools/launch_summary.py file.csv [title]"""
-import collections, csv, re, sys
-path = sys.argv[1]
-lines = [l for l in open(path) if not l.startswith('==')]
-agg = collections.defaultdict(lambda: [0, 0.0]); tot = 0
-for row in csv.DictReader(lines):
-    if row.get('Metric Name') != 'gpu__time_duration.sum': continue
-    name = re.sub(r'\(.*', '', row['Kernel Name']).replace('<unnamed>::', '')
-    v = float(row['Metric Value'].replace(',', '')); u = row['Metric Unit']
-    v = v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
-    agg[name][0] += 1; agg[name][1] += v; tot += v
-if len(sys.argv) > 2: print(f"# {sys.argv[2]}\n")
-print("| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|")
-for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:26]:
-    print(f"| `{k[:80]}` | {n} | {t:.0f} | {100*t/tot:.1f}% | {t/n:.1f} |")
-print(f"\nTotal {tot/1e3:.2f} ms over {sum(a[0] for a in agg.values())} launches.")
+"""summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: python tools/launch_summary.py file.csv [top]"""
+import collections
+import csv
+import re
+import sys
+
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10 and r[0].isdigit()]
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+agg, tot = collections.OrderedDict(), 0.0
+for r in rows:
+    n, t = re.sub(r'\(.*', '', r[4])[:90], float(r[-1]) / 1000
+    a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += t; tot += t
+print(f'total {tot:.1f} us over {len(rows)} launches')
+print('| kernel | launches | total us | share | avg us |\n|---|---:|---:|---:|---:|')
+for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
+    print(f'| `{n}` | {c} | {t:.0f} | {100 * t / tot:.1f}% | {t / c:.1f} |')
