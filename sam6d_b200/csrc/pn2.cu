@@ -477,28 +477,62 @@ __global__ void __launch_bounds__(BQP_THREADS) ball_query_pair_kernel(const floa
     }
     __syncthreads();
     if (live) {
-#pragma unroll 4
-      for (int k = 0; k < tn; ++k) {
-        const float4 c = sp[k];
+      // eight candidates per step, branch-free distances, ONE test for "any hit among the eight" (hits are a few per cent, so
+      // the list bookkeeping below is rarely entered and the distance chains of a step overlap)
+      auto dist2 = [&](const float4 c) {
         const float dx = nx - c.x, dy = ny - c.y, dz = nz - c.z;
         float d = __fmul_rn(dx, dx);
         d = __fmaf_rn(dy, dy, d);
-        d = __fmaf_rn(dz, dz, d);
+        return __fmaf_rn(dz, dz, d);
+      };
+      auto take = [&](float d, int k) {
         if (d < rb2) {
           if (cb < nsb) {
-            if (cb == 0) fb = base + k;
-            ob[cb] = base + k;
+            if (cb == 0) fb = k;
+            ob[cb] = k;
           }
           ++cb;
           if (d < ra2) {
             if (ca < nsa) {
-              if (ca == 0) fa = base + k;
-              oa[ca] = base + k;
+              if (ca == 0) fa = k;
+              oa[ca] = k;
+            }
+            ++ca;
+          }
+        }
+      };
+      int k = 0;
+      for (; k + 8 <= tn; k += 8) {
+        float d[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) d[u] = dist2(sp[k + u]);
+        // A lane's hits of the step as a bit mask, then one bookkeeping pass per SET bit: a warp sees ~9 hits among its 256
+        // tests of a step, so "any lane hit" is almost always true, but no single lane has more than one or two
+        unsigned hb = 0, ha = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          hb |= (d[u] < rb2) ? (1u << u) : 0u;
+          ha |= (d[u] < ra2) ? (1u << u) : 0u;
+        }
+        while (hb) {
+          const int u = __ffs(hb) - 1;
+          hb &= hb - 1;
+          const int kk = base + k + u;
+          if (cb < nsb) {
+            if (cb == 0) fb = kk;
+            ob[cb] = kk;
+          }
+          ++cb;
+          if ((ha >> u) & 1u) {
+            if (ca < nsa) {
+              if (ca == 0) fa = kk;
+              oa[ca] = kk;
             }
             ++ca;
           }
         }
       }
+      for (; k < tn; ++k) take(dist2(sp[k]), base + k);
     }
   }
   // pad the lists with their first entry (0 when empty), warp-cooperatively so that the stores are contiguous
