@@ -265,10 +265,6 @@ int sam6d_coarse_hypotheses(const int* idx, const float* pts1, const float* pts2
 int sam6d_topk_smallest(const float* v, int B, int n, int k, int* out, void* stream);
 int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, int n2, const float* pts1, const float* w1, int n,
                         const float* model, int nm, float* scores, float* R, float* t, void* stream);
-/* the same selection with the CAD samples binned into a uniform grid (identical scores; ~1/10 of the distance evaluations);
- * grid_scratch: B * (nm * 16 + 513 * 4 + 32) bytes, 16-byte aligned */
-int sam6d_coarse_select_grid(const float* Rt, const int* top, int B, int n1, int n2, const float* pts1, const float* w1, int n,
-                             const float* model, int nm, float* scores, float* R, float* t, void* grid_scratch, void* stream);
 
 /* ---- fine stage ---------------------------------------------------------------------------------------------------- */
 

@@ -62,7 +62,7 @@ def lib():
 
 _launches = 0
 # entry points that launch more than one kernel
-_MULTI = {"sam6d_fine_assign": 6, "sam6d_coarse_select": 2, "sam6d_coarse_select_grid": 3, "sam6d_geo_embed_tc": 2}
+_MULTI = {"sam6d_fine_assign": 6, "sam6d_coarse_select": 2, "sam6d_geo_embed_tc": 2}
 _timed = {}      # name -> list of (start_event, end_event); filled only for names registered with time_kernel()
 
 

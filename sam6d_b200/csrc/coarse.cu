@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(1024) topk_smallest_kernel(const float* __rest
 // (x, y, z, |m|^2) quadruples, so the inner loop is one 16-byte broadcast load and 4 instructions per (hypothesis, point, sample):
 // min_m (|x|^2 - 2 x.m + |m|^2) = |x|^2 + min_m (|m|^2 - 2 x.m), the clamp at 0 commutes with the minimum
 // (pairwise_distance, model_utils.py:98-111).
-// (a packed-fp32 FFMA2 variant with 8 hypotheses per CTA measured 550 us against 362 us for this one: FFMA2 issues at half rate)
+// (Measured alternatives: a packed-fp32 FFMA2 variant with 8 hypotheses per CTA, 550 us against 362 us for this one -- FFMA2 issues at
+// half rate; a uniform 8^3 grid over the CAD samples walked shell by shell per thread, bit-identical scores but 3.9 ms -- the
+// walks of a warp's 32 points diverge, and at 1024 samples the regular scan below is only ~110 warp instructions per point.)
 constexpr int SEL_PP = 4, SEL_THREADS = 224;
 __device__ __forceinline__ float min3f(float a, float b, float c) {
   float d;
@@ -298,169 +300,6 @@ __global__ void __launch_bounds__(SEL_THREADS) coarse_select_kernel(const float*
     num += wi;
 #pragma unroll
     for (int pp = 0; pp < SEL_PP; ++pp) den[pp] += sqrtf(fmaxf(x2[pp] + best[pp], 0.f)) * wi;
-  }
-  num = warp_sum(num);
-#pragma unroll
-  for (int pp = 0; pp < SEL_PP; ++pp) den[pp] = warp_sum(den[pp]);
-  if ((tid & 31) == 0) {
-#pragma unroll
-    for (int pp = 0; pp < SEL_PP; ++pp) { red[pp][tid >> 5] = num; red[SEL_PP + pp][tid >> 5] = den[pp]; }
-  }
-  __syncthreads();
-  if (tid < SEL_PP && pose0 + tid < n2) {
-    float a = 0.f, c = 0.f;
-    for (int w = 0; w < SEL_THREADS / 32; ++w) { a += red[tid][w]; c += red[SEL_PP + tid][w]; }
-    scores[(size_t)b * n2 + pose0 + tid] = a / (c + 1e-8f);
-  }
-}
-
-// ---- 5b. the same scores through a uniform grid over the CAD samples -----------------------------------------------------------
-// min_m (|m|^2 - 2 x.m) needs only the samples near x: the samples of a proposal are binned once into SG^3 cells (counting sort,
-// cell-major order) and a thread walks the cube shells around its point until the best distance found is below the distance to
-// everything not yet visited.  The per-sample expression and the minimum are those of coarse_select_kernel, and a minimum does
-// not depend on the visiting order or on skipping non-minimal candidates, so the scores are the brute-force ones bit for bit
-// (tests/test_gpu_kernels.py compares them).  The termination test keeps a margin of 2e-3 (the expanded form carries ~3e-7
-// of rounding in d^2, i.e. up to ~6e-4 in a near-zero d).
-constexpr int SG = 8, SG3 = SG * SG * SG, GRID_THREADS = 256;
-struct GridMeta { float ox, oy, oz, cs, inv; };
-
-__global__ void __launch_bounds__(GRID_THREADS) model_grid_kernel(const float* __restrict__ model, int nm, float4* __restrict__ gpts,
-                                                                  int* __restrict__ cstart, GridMeta* __restrict__ meta) {
-  __shared__ float red[6][GRID_THREADS / 32];
-  __shared__ int hist[SG3], start[SG3 + 1];
-  __shared__ GridMeta gm;
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* mp = model + (size_t)b * nm * 3;
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = tid; i < nm; i += GRID_THREADS)
-    for (int a = 0; a < 3; ++a) { const float v = mp[i * 3 + a]; lo[a] = fminf(lo[a], v); hi[a] = fmaxf(hi[a], v); }
-  for (int a = 0; a < 3; ++a) {
-    float l = lo[a], h = hi[a];
-    for (int o = 16; o > 0; o >>= 1) { l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o)); h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o)); }
-    if (lane == 0) { red[a][warp] = l; red[3 + a][warp] = h; }
-  }
-  for (int i = tid; i < SG3; i += GRID_THREADS) hist[i] = 0;
-  __syncthreads();
-  if (tid == 0) {
-    float l[3], h[3];
-    for (int a = 0; a < 3; ++a) {
-      l[a] = red[a][0]; h[a] = red[3 + a][0];
-      for (int w = 1; w < GRID_THREADS / 32; ++w) { l[a] = fminf(l[a], red[a][w]); h[a] = fmaxf(h[a], red[3 + a][w]); }
-    }
-    const float ext = fmaxf(fmaxf(h[0] - l[0], h[1] - l[1]), fmaxf(h[2] - l[2], 1e-6f));
-    gm.ox = l[0]; gm.oy = l[1]; gm.oz = l[2];
-    gm.cs = ext / SG * 1.0001f;
-    gm.inv = 1.f / gm.cs;
-    meta[b] = gm;
-  }
-  __syncthreads();
-  auto cell_of = [&](float x, float y, float z) {
-    const int ix = min(max((int)floorf((x - gm.ox) * gm.inv), 0), SG - 1);
-    const int iy = min(max((int)floorf((y - gm.oy) * gm.inv), 0), SG - 1);
-    const int iz = min(max((int)floorf((z - gm.oz) * gm.inv), 0), SG - 1);
-    return (iz * SG + iy) * SG + ix;
-  };
-  for (int i = tid; i < nm; i += GRID_THREADS) atomicAdd(&hist[cell_of(mp[i * 3], mp[i * 3 + 1], mp[i * 3 + 2])], 1);
-  __syncthreads();
-  if (warp == 0) {                                   // exclusive scan of the SG3 counts: 16 per lane + a warp scan
-    int loc[SG3 / 32], sum = 0;
-    for (int u = 0; u < SG3 / 32; ++u) { loc[u] = sum; sum += hist[lane * (SG3 / 32) + u]; }
-    int inc = sum;
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-    const int base = inc - sum;
-    for (int u = 0; u < SG3 / 32; ++u) start[lane * (SG3 / 32) + u] = base + loc[u];
-    if (lane == 31) start[SG3] = inc;
-  }
-  __syncthreads();
-  for (int i = tid; i <= SG3; i += GRID_THREADS) cstart[(size_t)b * (SG3 + 1) + i] = start[i];
-  for (int i = tid; i < SG3; i += GRID_THREADS) hist[i] = 0;       // reused as the per-cell cursor
-  __syncthreads();
-  for (int i = tid; i < nm; i += GRID_THREADS) {
-    const float* q = mp + i * 3;
-    const float x = q[0], y = q[1], z = q[2];
-    const int c = cell_of(x, y, z);
-    const int pos = start[c] + atomicAdd(&hist[c], 1);
-    gpts[(size_t)b * nm + pos] = make_float4(x, y, z, x * x + y * y + z * z);
-  }
-}
-
-__global__ void __launch_bounds__(SEL_THREADS) coarse_select_grid_kernel(const float* __restrict__ Rt, const int* __restrict__ top, int n1,
-                                                                         int n2, const float* __restrict__ pts1,
-                                                                         const float* __restrict__ w1, int n,
-                                                                         const float4* __restrict__ gpts, const int* __restrict__ cstart,
-                                                                         const GridMeta* __restrict__ meta, int nm,
-                                                                         float* __restrict__ scores) {
-  extern __shared__ float4 smq[];   // nm quadruples in cell order
-  __shared__ unsigned short cs16[SG3 + 1];
-  __shared__ float red[2 * SEL_PP][SEL_THREADS / 32];
-  __shared__ float rts[SEL_PP][12];
-  const int pose0 = blockIdx.x * SEL_PP, b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < nm; i += SEL_THREADS) smq[i] = gpts[(size_t)b * nm + i];
-  for (int i = tid; i <= SG3; i += SEL_THREADS) cs16[i] = (unsigned short)cstart[(size_t)b * (SG3 + 1) + i];
-  if (tid < SEL_PP * 12) {
-    const int pp = tid / 12, e = tid - pp * 12;
-    const int pose = min(pose0 + pp, n2 - 1);
-    rts[pp][e] = Rt[((size_t)b * n1 + top[(size_t)b * n2 + pose]) * 12 + e];
-  }
-  const GridMeta gm = meta[b];
-  __syncthreads();
-  float num = 0.f, den[SEL_PP];
-#pragma unroll
-  for (int pp = 0; pp < SEL_PP; ++pp) den[pp] = 0.f;
-  for (int i = tid; i < n; i += SEL_THREADS) {
-    const float* p = pts1 + ((size_t)b * n + i) * 3;
-    const float px = p[0], py = p[1], pz = p[2];
-    const float wi = w1[(size_t)b * n + i];
-    num += wi;
-#pragma unroll 1
-    for (int pp = 0; pp < SEL_PP; ++pp) {
-      const float* R = rts[pp];
-      const float x = px - R[9], y = py - R[10], z = pz - R[11];
-      const float tx = x * R[0] + y * R[3] + z * R[6];
-      const float ty = x * R[1] + y * R[4] + z * R[7];
-      const float tz = x * R[2] + y * R[5] + z * R[8];
-      const float x2 = tx * tx + ty * ty + tz * tz;
-      const float ax = -2.f * tx, ay = -2.f * ty, az = -2.f * tz;
-      float best = INFINITY;
-      // position in cell units; the home cell is clamped into the grid, the position is not (points outside the box stay outside)
-      const float gx = (tx - gm.ox) * gm.inv, gy = (ty - gm.oy) * gm.inv, gz = (tz - gm.oz) * gm.inv;
-      const int cx = min(max((int)floorf(gx), 0), SG - 1), cy = min(max((int)floorf(gy), 0), SG - 1),
-                cz = min(max((int)floorf(gz), 0), SG - 1);
-      auto scan = [&](int lo, int hi) {                 // samples [lo, hi) of the sorted array
-        for (int m = lo; m < hi; ++m) {
-          const float4 q = smq[m];
-          best = fminf(best, fmaf(ax, q.x, fmaf(ay, q.y, fmaf(az, q.z, q.w))));
-        }
-      };
-      for (int r = 0; r < SG; ++r) {
-        const int z0 = max(cz - r, 0), z1 = min(cz + r, SG - 1), y0 = max(cy - r, 0), y1 = min(cy + r, SG - 1);
-        const int x0 = max(cx - r, 0), x1 = min(cx + r, SG - 1);
-        for (int zz = z0; zz <= z1; ++zz) {
-          const bool zface = (zz == cz - r) || (zz == cz + r);
-          for (int yy = y0; yy <= y1; ++yy) {
-            const int row = (zz * SG + yy) * SG;
-            if (zface || yy == cy - r || yy == cy + r) {
-              scan(cs16[row + x0], cs16[row + x1 + 1]);           // the whole x-run of the row is on the shell: one contiguous range
-            } else {
-              if (cx - r >= 0) scan(cs16[row + cx - r], cs16[row + cx - r + 1]);
-              if (cx + r < SG && r > 0) scan(cs16[row + cx + r], cs16[row + cx + r + 1]);
-            }
-          }
-        }
-        // everything unvisited lies outside the cube of cells [c - r, c + r]: at least `bound` away (faces beyond the grid hold
-        // no samples and do not count)
-        float bound = INFINITY;
-        if (cx - r > 0) bound = fminf(bound, gx - (float)(cx - r));
-        if (cx + r < SG - 1) bound = fminf(bound, (float)(cx + r + 1) - gx);
-        if (cy - r > 0) bound = fminf(bound, gy - (float)(cy - r));
-        if (cy + r < SG - 1) bound = fminf(bound, (float)(cy + r + 1) - gy);
-        if (cz - r > 0) bound = fminf(bound, gz - (float)(cz - r));
-        if (cz + r < SG - 1) bound = fminf(bound, (float)(cz + r + 1) - gz);
-        if (bound == INFINITY) break;                   // the cube covers the grid
-        if (sqrtf(fmaxf(x2 + best, 0.f)) + 2e-3f < bound * gm.cs) break;
-      }
-      den[pp] += sqrtf(fmaxf(x2 + best, 0.f)) * wi;
-    }
   }
   num = warp_sum(num);
 #pragma unroll
@@ -553,30 +392,6 @@ S6_API int sam6d_coarse_select(const float* Rt, const int* top, int B, int n1, i
   coarse_select_kernel<<<grid, SEL_THREADS, smem, s6_stream(stream)>>>(Rt, top, n1, n2, pts1, w1, n, model, nm, scores);
   S6_LAUNCH_CHECK();
   coarse_pick_kernel<<<B, 32, 0, s6_stream(stream)>>>(scores, top, Rt, n1, n2, R, t);
-  S6_LAUNCH_CHECK();
-  return 0;
-}
-
-// sam6d_coarse_select through a uniform grid over the CAD samples (same scores bit for bit, ~1/10 of the distance evaluations).
-// grid_scratch: B * (nm * 16 + 513 * 4 + 32) bytes, 16-byte aligned (sorted samples, cell starts of the 8^3 grid, its geometry).
-S6_API int sam6d_coarse_select_grid(const float* Rt, const int* top, int B, int n1, int n2, const float* pts1, const float* w1, int n,
-                                    const float* model, int nm, float* scores, float* R, float* t, void* grid_scratch, void* stream) {
-  S6_REQUIRE(Rt && top && pts1 && w1 && model && scores && R && t && grid_scratch && B >= 0 && n > 0 && nm > 0 && n2 > 0);
-  S6_REQUIRE((reinterpret_cast<uintptr_t>(grid_scratch) & 15) == 0 && nm < 65536);
-  if (B == 0) return 0;
-  size_t smem = (size_t)nm * 4 * sizeof(float);
-  S6_REQUIRE(smem <= 200 * 1024);
-  float4* gpts = reinterpret_cast<float4*>(grid_scratch);
-  int* cstart = reinterpret_cast<int*>(gpts + (size_t)B * nm);
-  GridMeta* meta = reinterpret_cast<GridMeta*>(cstart + (size_t)B * (SG3 + 1));
-  cudaStream_t st = s6_stream(stream);
-  model_grid_kernel<<<B, GRID_THREADS, 0, st>>>(model, nm, gpts, cstart, meta);
-  S6_LAUNCH_CHECK();
-  S6_CHECK(cudaFuncSetAttribute(coarse_select_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(s6_cdiv(n2, SEL_PP), B);
-  coarse_select_grid_kernel<<<grid, SEL_THREADS, smem, st>>>(Rt, top, n1, n2, pts1, w1, n, gpts, cstart, meta, nm, scores);
-  S6_LAUNCH_CHECK();
-  coarse_pick_kernel<<<B, 32, 0, st>>>(scores, top, Rt, n1, n2, R, t);
   S6_LAUNCH_CHECK();
   return 0;
 }

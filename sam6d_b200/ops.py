@@ -632,9 +632,7 @@ def topk_smallest(v: Tensor, k: int) -> Tensor:
     return out
 
 
-def coarse_select(Rt: Tensor, top: Tensor, pts1: Tensor, w1: Tensor, model: Tensor, brute_force: bool = False):
-    """scores the retained hypotheses against the CAD samples and returns the best pose (model_utils.py:239-246); by default
-    through the uniform-grid kernel, `brute_force` = all samples for every point (identical scores)"""
+def coarse_select(Rt: Tensor, top: Tensor, pts1: Tensor, w1: Tensor, model: Tensor):
     _check(Rt, torch.float32, "Rt", 3)
     _check(top, torch.int32, "top", 2)
     _check(model, torch.float32, "model", 3)
@@ -644,14 +642,8 @@ def coarse_select(Rt: Tensor, top: Tensor, pts1: Tensor, w1: Tensor, model: Tens
     scores = torch.empty(B, n2, dtype=torch.float32, device=Rt.device)
     R = torch.empty(B, 3, 3, dtype=torch.float32, device=Rt.device)
     t = torch.empty(B, 3, dtype=torch.float32, device=Rt.device)
-    if brute_force:
-        _lib.call("sam6d_coarse_select", _p(Rt), _p(top), B, n1, n2, _p(pts1), _p(w1), n, _p(model), model.shape[1], _p(scores),
-                  _p(R), _p(t), _s())
-    else:
-        nm = model.shape[1]
-        scratch = torch.empty(B * (nm * 16 + 513 * 4 + 32), dtype=torch.uint8, device=Rt.device)
-        _lib.call("sam6d_coarse_select_grid", _p(Rt), _p(top), B, n1, n2, _p(pts1), _p(w1), n, _p(model), nm, _p(scores),
-                  _p(R), _p(t), _p(scratch), _s())
+    _lib.call("sam6d_coarse_select", _p(Rt), _p(top), B, n1, n2, _p(pts1), _p(w1), n, _p(model), model.shape[1], _p(scores),
+              _p(R), _p(t), _s())
     return R, t, scores
 
 

@@ -225,32 +225,6 @@ def test_rpe_scores_tensor_core(ops, B, S):
     torch.testing.assert_close(got, old, atol=2e-3, rtol=1e-4)
 
 
-@pytest.mark.parametrize("case", ["fit", "offset", "far", "flat"])
-def test_coarse_select_grid_equals_brute_force(ops, case):
-    """the uniform-grid walk over the CAD samples returns the brute-force hypothesis scores bit for bit: hypotheses that fit, that
-    are shifted by a fraction of the object size, that put the points far outside the sample box (the walk must widen to the whole
-    grid), and a flat model (a degenerate box axis)"""
-    from sam6d_b200 import synth
-    B, n, nm, n1, n2 = 6, 196, 1024, 400, 300
-    g = G(11)
-    d = torch.randn(B, nm + n, 3, generator=g)
-    d = d / d.norm(dim=2, keepdim=True) * (0.4 + 0.6 * torch.rand(B, 1, 1, generator=g))
-    if case == "flat":
-        d[..., 2] = 0.25
-    model, src = d[:, :nm].contiguous(), d[:, nm:].contiguous()
-    R = synth.random_rotation(B * n1, g).view(B, n1, 3, 3)
-    t = torch.randn(B, n1, 3, generator=g) * {"fit": 0.0, "offset": 0.15, "far": 3.0, "flat": 0.1}[case]
-    R[:, ::2] = torch.eye(3)                                     # half of the hypotheses are the identity rotation
-    pts1 = src + (0.01 * torch.randn(B, n, 3, generator=g) if case != "far" else 0.0)
-    Rt = torch.cat([R.reshape(B, n1, 9), t], dim=2).contiguous()
-    top = torch.stack([torch.randperm(n1, generator=g)[:n2] for _ in range(B)]).int()
-    w1 = (torch.rand(B, n, generator=g) > 0.2).float()
-    dev = lambda x: x.cuda()      # noqa: E731
-    Rb, tb, sb = ops.coarse_select(dev(Rt), dev(top), dev(pts1), dev(w1), dev(model), brute_force=True)
-    Rg, tg, sg = ops.coarse_select(dev(Rt), dev(top), dev(pts1), dev(w1), dev(model))
-    assert torch.equal(sg, sb) and torch.equal(Rg, Rb) and torch.equal(tg, tb)
-
-
 @pytest.mark.parametrize("B,S", [(2, 197), (3, 65), (2, 130), (1, 200)])
 def test_padded_bias_attention_equals_dense_bias(ops, B, S):
     """score planes with 16-key padded rows (sam6d_rpe_scores_tc_ld) + the cp.async-streamed bias of sam6d_attn_tc_bias_ld:
