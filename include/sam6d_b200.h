@@ -83,6 +83,11 @@ int sam6d_gemm_tma_batched(const void* A, const void* W, const float* bias, cons
  * [vt_S, vt_N1) of Vt are left untouched and must be finite. */
 int sam6d_gemm_tma_vt(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long lda, long long ldw,
                       long long ldc, void* Vt, int vt_col0, int vt_S, int vt_N1, void* stream);
+/* sam6d_gemm_tma_vt with a third column range: [0, vt_col0) -> C, [vt_col0, vt_col1) -> Vt, [vt_col1, N) -> C2 (M, N - vt_col1)
+ * bf16, row stride ldc2: one launch for the q | k | v | u projections of an RPE self-attention layer */
+int sam6d_gemm_tma_vt2(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long lda, long long ldw,
+                       long long ldc, void* Vt, int vt_col0, int vt_col1, int vt_S, int vt_N1, void* C2, long long ldc2,
+                       void* stream);
 
 /* ---- token-row ops (row r lives at base + (r / rpb) * bstride + (r % rpb) * ld) ----------------------------------- */
 

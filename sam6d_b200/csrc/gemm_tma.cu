@@ -43,6 +43,9 @@ struct Args {
   // VT kernels: output columns >= vt_col0 are V of an attention layer and are written transposed, as the K-major B operand of
   // the P V MMA: vt[(cloud * vt_C + c) * vt_N1 + token], cloud = row / vt_S (saves the transpose pass over V)
   void* vt; int vt_col0, vt_S, vt_N1, vt_C;
+  // ... and columns >= vt_col1 = vt_col0 + vt_C go to a SECOND row-major output c2 (ldc2), column j at c2[row * ldc2 + j - vt_col1]
+  // (the folded rel-pos queries of an RPE layer: one launch projects q | k, V^T and u)
+  int vt_col1; void* c2; long long ldc2;
 };
 
 template <typename OT, int ACT, bool HAS_BIAS, bool HAS_RES, int STAGES, int EW, bool VT = false>
@@ -164,13 +167,18 @@ __global__ void __launch_bounds__(64 + EW * 32, 1) gemm_tma_kernel(const __grid_
           if (col0 >= g.N) break;
           float v[32];
           tc::tmem_ld32(t_addr + c * 32, v);
+          if (VT && col0 >= g.vt_col1) {
+            epi::process_chunk<OT, ACT, HAS_BIAS, HAS_RES, OT>(v, stage, lane, m0 + quad * 32, g.M, col0, g.N, g.alpha, g.bias, Rb, g.ldr,
+                                                               reinterpret_cast<OT*>(g.c2) - g.vt_col1, g.ldc2);
+            continue;
+          }
           if (VT && col0 >= g.vt_col0) {
             // lane = token: 32 lanes write 32 adjacent tokens of one channel row (64 bytes) per store
             if (vrow < g.M) {
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(g.vt) + ((size_t)vcloud * g.vt_C + (col0 - g.vt_col0)) * g.vt_N1 + vtok;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
-                if (col0 + i < g.N) {
+                if (col0 + i < g.vt_col1) {
                   float x = v[i] * g.alpha;
                   if constexpr (HAS_BIAS) x += __ldg(g.bias + col0 + i);
                   dst[(size_t)i * g.vt_N1] = __float2bfloat16(epi::act_fn<ACT>(x));
@@ -228,7 +236,7 @@ namespace {
 int launch_gemm_tma(const void* A, const void* W, const float* bias, const void* R, void* C, int c_dtype, int M, int N, int K,
                     long long lda, long long ldw, long long ldc, long long ldr, int batch, long long a_rpb, long long w_rpb,
                     long long c_bs, long long r_bs, float alpha, int act, void* stream, void* vt = nullptr, int vt_col0 = 0, int vt_S = 1,
-                    int vt_N1 = 0) {
+                    int vt_N1 = 0, int vt_col1 = -1, void* c2 = nullptr, long long ldc2 = 0) {
   S6_REQUIRE(A && W && C && M >= 0 && N > 0 && K > 0 && (K % 8) == 0 && (lda % 8) == 0 && (ldw % 8) == 0 && act >= 0 && act <= 2);
   S6_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && batch >= 0);
   S6_REQUIRE(a_rpb * (long long)batch < 2000000000LL && w_rpb * (long long)batch < 2000000000LL);
@@ -244,7 +252,9 @@ int launch_gemm_tma(const void* A, const void* W, const float* bias, const void*
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const long long ntiles = (long long)s6_cdiv(M, BM) * s6_cdiv(N, BN) * batch;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act, batch, a_rpb, w_rpb, c_bs, r_bs, vt, vt_col0, vt_S, vt_N1, N - vt_col0};
+  if (vt_col1 < 0) vt_col1 = N;
+  Args g{bias, R, C, M, N, K, ldc, ldr, alpha, act, batch, a_rpb, w_rpb, c_bs, r_bs, vt, vt_col0, vt_S, vt_N1, vt_col1 - vt_col0,
+         vt_col1, c2, ldc2};
   cudaStream_t st = s6_stream(stream);
   const bool deep_k = K >= 1024;
 #define LAUNCH_ONE(OT, ACT, HB, HR, ST, EWN)                                                                           \
@@ -265,6 +275,8 @@ int launch_gemm_tma(const void* A, const void* W, const float* bias, const void*
     // V^T epilogue: bf16 output, bias, no activation / residual (the QKV and KV projections)
     S6_REQUIRE(c_dtype == 1 && bias && !R && act == 0 && batch == 1 && vt_col0 > 0 && vt_col0 < N && (vt_col0 % 32) == 0 && vt_S > 0 &&
                vt_N1 >= vt_S);
+    S6_REQUIRE(vt_col1 > vt_col0 && vt_col1 <= N && (vt_col1 % 32) == 0 &&
+               (vt_col1 == N || (c2 && (ldc2 % 8) == 0 && ldc2 >= N - vt_col1 && (reinterpret_cast<uintptr_t>(c2) & 15) == 0)));
     if (deep_k) {
       auto k = gemm_tma_kernel<__nv_bfloat16, 0, true, false, 4, 4, true>;
       S6_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<4, 4>::kSmem));
@@ -312,4 +324,15 @@ S6_API int sam6d_gemm_tma_vt(const void* A, const void* W, const float* bias, vo
                              long long ldc, void* Vt, int vt_col0, int vt_S, int vt_N1, void* stream) {
   S6_REQUIRE(Vt != nullptr);
   return launch_gemm_tma(A, W, bias, nullptr, C, 1, M, N, K, lda, ldw, ldc, 0, 1, 0, 0, 0, 0, 1.f, 0, stream, Vt, vt_col0, vt_S, vt_N1);
+}
+
+// sam6d_gemm_tma_vt with a third column range: [0, vt_col0) -> C, [vt_col0, vt_col1) -> Vt (transposed per cloud), [vt_col1, N) ->
+// C2 (M, N - vt_col1) bf16 with row stride ldc2.  One launch for the q | k | v | u projections of an RPE self-attention layer
+// (PEM/model/transformer.py:369-394 with proj_p folded into the query).
+S6_API int sam6d_gemm_tma_vt2(const void* A, const void* W, const float* bias, void* C, int M, int N, int K, long long lda, long long ldw,
+                              long long ldc, void* Vt, int vt_col0, int vt_col1, int vt_S, int vt_N1, void* C2, long long ldc2,
+                              void* stream) {
+  S6_REQUIRE(Vt != nullptr && C2 != nullptr);
+  return launch_gemm_tma(A, W, bias, nullptr, C, 1, M, N, K, lda, ldw, ldc, 0, 1, 0, 0, 0, 0, 1.f, 0, stream, Vt, vt_col0, vt_S, vt_N1, vt_col1,
+                         C2, ldc2);
 }

@@ -234,6 +234,23 @@ def gemm_tma_vt(A: Tensor, W: Tensor, bias: Tensor, vt_col0: int, S: int, slot: 
     return out, vt
 
 
+def gemm_tma_vt2(A: Tensor, W: Tensor, bias: Tensor, vt_col0: int, vt_col1: int, S: int, slot: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """gemm_tma_vt with a third column range: -> (C (M, vt_col0), Vt of columns [vt_col0, vt_col1), C2 (M, N - vt_col1)), all bf16"""
+    _check(A, torch.bfloat16, "A", 2)
+    _check(W, torch.bfloat16, "W", 2)
+    M, K = A.shape
+    N = W.shape[0]
+    if W.shape[1] != K or M % S or not (0 < vt_col0 < vt_col1 < N):
+        raise RuntimeError("gemm_tma_vt2: shape mismatch")
+    n1 = (S + 15) // 16 * 16
+    out = torch.empty(M, vt_col0, dtype=torch.bfloat16, device=A.device)
+    out2 = torch.empty(M, N - vt_col1, dtype=torch.bfloat16, device=A.device)
+    vt = _vt_buffer((M // S) * (vt_col1 - vt_col0), n1, A.device, slot)
+    _lib.call("sam6d_gemm_tma_vt2", _p(A), _p(W), _p(bias), _p(out), M, N, K, _ll(K), _ll(K), _ll(vt_col0), _p(vt), int(vt_col0),
+              int(vt_col1), int(S), int(n1), _p(out2), _ll(N - vt_col1), _s())
+    return out, vt, out2
+
+
 def layernorm_raw(x_ptr, x_view, y_ptr, y_view, gamma: Tensor, beta: Tensor, rows: int, C: int, eps: float = 1e-5):
     _lib.call("sam6d_layernorm", ctypes.c_void_p(x_ptr), _ll(x_view[0]), _ll(x_view[1]), _ll(x_view[2]),
               ctypes.c_void_p(y_ptr), _ll(y_view[0]), _ll(y_view[1]), _ll(y_view[2]), _p(gamma), _p(beta), _ll(rows), int(C),

@@ -255,19 +255,21 @@ class GeometricTransformer(nn.Module):
         B, S, C = x.shape
         d = C // NUM_HEADS
         x2d = x.view(B * S, C)
-        qk, vt = ops.gemm_tma_vt(x2d, w["w_qkv"].bf16, w["b_qkv"], 2 * C, S)                        # (B*S, q|k) and V^T
         if RPE_TC and S <= 200 and emb.dtype == torch.bfloat16:
-            # the folded rel-pos queries as bf16 rows: B operand of the TMA / tcgen05 stream over E (csrc/rpe_tc.cu)
-            u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"], out_dtype=torch.bfloat16)                # (B*S, 4*C) bf16
+            # ONE projection launch: (q | k) rows, V^T, and the folded rel-pos queries u as bf16 rows = the B operand of the TMA /
+            # tcgen05 stream over E (csrc/rpe_tc.cu)
+            qk, vt, u = ops.gemm_tma_vt2(x2d, w["w_self"].bf16, w["b_self"], 2 * C, 3 * C, S)
             if PADDED_BIAS:
                 # score planes with 16-key padded rows: the attention kernel streams them with 16-byte cp.async copies
                 sp = ops.rpe_scores_tc_padded(emb, u)
                 hid = ops.attn_tc_padded_bias(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), sp)
                 return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
             sp = ops.rpe_scores_tc(emb, u)
-        else:
-            u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                          # (B*S, 4*C) fp32
-            sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
+            hid = ops.attn_tc(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
+            return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
+        qk, vt = ops.gemm_tma_vt(x2d, w["w_qkv"].bf16, w["b_qkv"], 2 * C, S)                        # (B*S, q|k) and V^T
+        u = ops.gemm_tma(x2d, w["w_u"].bf16, w["b_u"])                                              # (B*S, 4*C) fp32
+        sp = ops.rpe_scores(emb, None, u_ptr=u.data_ptr(), u_ld=NUM_HEADS * C)
         hid = ops.attn_tc(qk, 0, qk, C, vt, B, NUM_HEADS, S, S, d, 1.0 / math.sqrt(d), bias=sp, out_dtype=torch.bfloat16)
         return self._tail_bf16(x2d, hid, w["tail_self"]).view(B, S, C)
 
@@ -279,10 +281,11 @@ class GeometricTransformer(nn.Module):
         f = self._self_bf16(f, emb, w)
         out = torch.empty_like(f)
         x0, x1 = f[:B].view(B * S, C), f[B:].view(B * S, C)
-        # cross layer 0: cloud 0 attends to cloud 1.  Cloud 1's projection also yields its queries for the second layer.
-        q0 = ops.gemm_tma(x0, w["wq_c"].bf16, w["bq_c"], out_dtype=torch.bfloat16)
-        kq1, vt1 = ops.gemm_tma_vt(x1, w["wkqv_c"].bf16, w["bkqv_c"], 2 * C, S, slot=1)            # (B*S, k | q) and V^T
-        hid = ops.attn_tc(q0, 0, kq1, 0, vt1, B, NUM_HEADS, S, S, d, scale, out_dtype=torch.bfloat16)
+        # cross layer 0: cloud 0 attends to cloud 1.  ONE projection [k | q | v] over both clouds: cloud 0's queries, cloud 1's keys
+        # / values, and cloud 1's queries for the second layer (cloud 0's keys / values of the old features are not used)
+        kq, vt_all = ops.gemm_tma_vt(f.view(2 * B * S, C), w["wkqv_c"].bf16, w["bkqv_c"], 2 * C, S, slot=1)
+        kq1, vt1 = kq[B * S:], vt_all[B * C:]
+        hid = ops.attn_tc(kq, C, kq1, 0, vt1, B, NUM_HEADS, S, S, d, scale, out_dtype=torch.bfloat16)
         self._tail_bf16(x0, hid, w["tail_cross"], out=out[:B].view(B * S, C))
         # cross layer 1: cloud 1 attends to the updated cloud 0 (sequential, transformer.py:505-507)
         k0, vt0 = ops.gemm_tma_vt(out[:B].view(B * S, C), w["wkv_c"].bf16, w["bkv_c"], C, S, slot=2)

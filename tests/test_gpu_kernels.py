@@ -758,6 +758,22 @@ def test_gemm_tma_vt_matches_gemm_plus_transpose(ops, nB, S, C, K):
     assert torch.equal(vt, vt_ref)
 
 
+@pytest.mark.parametrize("nB,S", [(5, 197), (64, 197), (2, 64)])
+def test_gemm_tma_vt2_three_column_ranges(ops, nB, S):
+    """q | k rows, V^T and the folded rel-pos queries u from ONE launch == the plain GEMM's columns, bit for bit"""
+    C, K = 256, 256
+    M, N = nB * S, 3 * C + 4 * C
+    A = torch.randn(M, K, generator=G(1)).bfloat16().cuda()
+    W = (torch.randn(N, K, generator=G(2)) / math.sqrt(K)).bfloat16().cuda()
+    b = torch.randn(N, generator=G(3)).cuda()
+    full = ops.gemm_tma(A, W, b, out_dtype=torch.bfloat16)
+    vt_ref = ops.transpose_tokens(full, 2 * C, C, nB, S)
+    qk, vt, u = ops.gemm_tma_vt2(A, W, b, 2 * C, 3 * C, S, slot=9)
+    assert torch.equal(qk, full[:, :2 * C])
+    assert torch.equal(vt, vt_ref)
+    assert torch.equal(u, full[:, 3 * C:])
+
+
 @pytest.mark.parametrize("B,S", [(2, 513), (3, 2049), (1, 130)])
 def test_fine_assign_tensor_core_fused(ops, B, S):
     """compute_fine_Rt's assignment recomputed tile by tile on tcgen05 (no (B,S,S) matrix) against fp64 math on the same
