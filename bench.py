@@ -221,6 +221,8 @@ def run_scene(args):
     scenes, P = (1, 200) if ycbv else (8, 16)
     net = Net(precision=args.precision).to(dev).eval()
     net.load_state_dict(synth.make_pem_state_dict(seed=1), strict=True)
+    if not args.no_graph:
+        net.enable_graphs()          # the per-rank chunk keeps its shape and (through the caching allocator) its buffers: replayed
     # template banks of the O objects (dense_po / dense_fo, 2048 points each) and per-scene proposals
     bank = synth.make_pem_inputs(B=O, n=N_PTS, n_model=N_MODEL, seed=50)
     bank_po, bank_fo, bank_model = bank["dense_po"].to(dev), bank["dense_fo"].to(dev), bank["model"].to(dev)
@@ -312,6 +314,8 @@ def run_scene(args):
                                             f"scenes sharded x{world} (SAM ViT-H encoder + scoring + matching per scene) + 1 all-gather of poses",
                                 cache="per-step working set exceeds L2"),
                     gpu_launches=launches, clocks=sampler.summary() if sampler else None)
+        if net._graphs is not None:
+            line["config"]["launch"] = f"matching step replayed as a CUDA graph where the buffers recur ({net._graphs.captures} captures, {net._graphs.replays} replays on rank 0)"
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -399,6 +403,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true", help="skip the same-box reference lines (oracle port + reference _ext kernels on this GPU)")
     ap.add_argument("--batch", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch every kernel of a step one by one instead of replaying the captured step (Net.enable_graphs)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16: tcgen05 tensor-core kernels (bf16 operands, fp32 accumulate); fp32: CUDA-core exact path")
     ap.add_argument("--rgb", action="store_true",
@@ -449,6 +455,11 @@ def main():
         for h in host:
             h["rgb"] = torch.randn(B, 3, 224, 224, generator=g_rgb).pin_memory()
             h["rgb_choose"] = torch.randint(0, 224 * 224, (B, N_PTS), generator=g_rgb).pin_memory()
+    graphs = not args.no_graph and not os.environ.get("SAM6D_PROFILE_ONE_STEP")
+    if graphs:
+        # repeated calls on the same input buffers replay one captured CUDA graph per input set (sam6d_b200/graph.py); the first
+        # call on a buffer set runs launch by launch, the second captures -- both happen during warm-up
+        net.enable_graphs()
     resident = [{k: v.to(dev) for k, v in h.items()} for h in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
     gen = torch.Generator(device=dev).manual_seed(1 + rank)
@@ -525,7 +536,8 @@ def main():
             ms = t.item()
         return ms, launches, kernel_ms
 
-    for i in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 3)
+    for i in range(max(n_warm, 4) if graphs else n_warm):      # two input sets: sighting, capture (+ first replay) of each
         step_resident(i)
     if os.environ.get("SAM6D_PROFILE_ONE_STEP"):
         # ncu --profile-from-start off: capture exactly one warmed-up step
@@ -546,10 +558,13 @@ def main():
     padded = rpe_name == "sam6d_rpe_scores_tc" and _pem.PADDED_BIAS
     if padded:
         rpe_name = "sam6d_rpe_scores_tc_ld"              # score planes with padded rows, consumed by sam6d_attn_tc_bias_ld
+    # (launch by launch: the events bracket single launches, which a graph replay does not expose; same kernels, same inputs)
+    step_graphs, net._graphs = net._graphs, None
     _, _, kall = timed(step_resident, args.steps,
                        profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_attn_tc_bias_ld", "sam6d_geo_embed_tc"])
+    net._graphs = step_graphs
     kms = kall[rpe_name]
-    for i in range(2):
+    for i in range(4 if graphs else 2):
         step_e2e(i)
     torch.cuda.synchronize()
     pipe["next"], computed[0], computed[1] = 0, None, None     # the timed run issues all of its own copies
@@ -607,7 +622,10 @@ def main():
             dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
             config=dict(workload=WORKLOAD + ("+vitb_rgb_branch" if args.rgb else ""), proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
                         feat_dim=C_FEAT, model_points=N_MODEL, parallelism=f"proposal-sharded x{world}, 1 all-gather of poses",
-                        cache="inputs+intermediates per step (>1 GB) exceed the 126 MB L2; two input sets alternate"),
+                        cache="inputs+intermediates per step (>1 GB) exceed the 126 MB L2; two input sets alternate",
+                        launch=(f"one CUDA-graph replay per step ({launches // args.steps} kernels each, captured from Net.forward; "
+                                f"{step_graphs.captures} graphs, {step_graphs.replays} replays in this run)") if graphs and step_graphs
+                        else "kernel by kernel"),
             e2e=dict(value=e2e_val, unit=UNIT, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=world * B * sdist.POSE_FLOATS * 4,
                      ms_per_step=ms_e2e / args.steps),
             gpu_launches=launches,

@@ -71,6 +71,12 @@ def launch_count() -> int:
     return _launches
 
 
+def add_launches(n: int):
+    """a captured forward replayed as one CUDA graph launches the kernels counted while it was captured"""
+    global _launches
+    _launches += int(n)
+
+
 def time_kernel(name: str, enable: bool = True):
     """bracket every call of C-ABI function `name` with CUDA events on the launching (current) stream"""
     if enable:

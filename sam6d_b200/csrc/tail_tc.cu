@@ -12,17 +12,21 @@
 //                G1 : hid W_o^T                -> A
 //                G2a: y W_e[0:256]^T           -> B          G2b: y W_e[256:512]^T -> A   (A is free once LN1 has read it)
 //                G3 : h[:,0:256] W_s[:,0:256]^T (+) h[:,256:512] W_s[:,256:512]^T -> B     (B is free once h[:,0:256] is written)
-//   warps 2-9  epilogues, thread = (row, 128-column half):
+//   warps 2-17 epilogues, thread = (row, 64-column quarter) (eight warps with 128 columns per thread left the four epilogue
+//              phases of a tile as 17 of its 22 us: each is a dependent tcgen05.ld -> math -> st chain per thread, so the phase
+//              time is set by the columns per thread, not by issue slots):
 //                E1 : acc + b_o + x -> LayerNorm1 -> y (bf16) written over the hid slabs as the next A operand
 //                E2a/E2b: relu(acc + b_e) -> h half (bf16) into the slabs the x tile occupied
 //                E3 : acc + b_s + y -> LayerNorm2 -> bf16 tile staged in shared memory -> TMA store
-//              LayerNorm statistics: sum and sum of squares per thread, exchanged between the two warps of a TMEM lane quadrant;
+//              LayerNorm statistics: sum and sum of squares per thread, exchanged between the four warps of a TMEM lane quadrant;
 //              pass 1 writes the pre-norm values back to TMEM so pass 2 is a load + affine.
 // Shared memory: 64 KB (hid -> y) + 64 KB (x -> h half -> output stage) + 96 KB weight ring.
 // Measured and not kept: CTA pairs sharing the weight stream (each CTA loads half of every k-block and TMA-multicasts it into
 // both rings, stages released by multicast tcgen05.commit) -- 0.997 ms per step for the 21 launches against 0.977 ms: the weight
 // reads from L2 are not what bounds a tile, its serial GEMM -> epilogue chain is (22 us per tile, 5 us of it MMA time).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "tc.cuh"
 
@@ -34,8 +38,8 @@ constexpr int T_BYTES = 4 * T_SLAB;              // 64 KB token tile
 constexpr int W_STAGE = 256 * 128;               // 32 KB: [256 rows][64 k] bf16
 constexpr int W_STAGES = 3;
 constexpr int W_PER_TILE = 20;                   // weight k-blocks per tile: 4 (W_o) + 8 (W_e) + 8 (W_s)
-constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + EPI_WARPS * 32;
+// EPI_WARPS (template parameter): 16 = four column parts per row (default), 8 = two (the first cut, kept as the comparator:
+// SAM6D_TAIL_EPI_WARPS=8)
 constexpr int SMEM = 2 * T_BYTES + W_STAGES * W_STAGE + 1024;
 
 struct TailArgs {
@@ -67,10 +71,14 @@ __device__ __forceinline__ void unpack8(const uint4& t, float f[8]) {
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 
-__global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_constant__ CUtensorMap tmHid, const __grid_constant__ CUtensorMap tmX,
+template <int EPI_WARPS>
+__global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) tail_tc_kernel(const __grid_constant__ CUtensorMap tmHid, const __grid_constant__ CUtensorMap tmX,
                                                              const __grid_constant__ CUtensorMap tmWo, const __grid_constant__ CUtensorMap tmWe,
                                                              const __grid_constant__ CUtensorMap tmWs, const __grid_constant__ CUtensorMap tmOut,
                                                              TailArgs a) {
+  constexpr int PARTS = EPI_WARPS / 4;             // column parts per row (one warp per TMEM lane quadrant and part)
+  constexpr int CPT = C / PARTS;                   // columns per epilogue thread
+  constexpr int CHUNKS = CPT / 32;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* a_buf = smem;                      // hid -> y
@@ -174,10 +182,10 @@ __global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogues: thread = (row, column half)
-    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    // ------------------------------------------------------------------ epilogues: thread = (row, column part)
+    const int ew = warp - 2, quad = warp & 3, part = ew >> 2;
     const int r = quad * 32 + lane;
-    const int col_h = half * 128;
+    const int col_h = part * CPT;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
     const int etid = tid - 64;
     int it = 0;
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_consta
                                   const float* __restrict__ b, uint8_t* dst_tile) {
       float s = 0.f, q = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = col_h + c * 32;
         float v[32];
         tc::tmem_ld32(lane_addr + acc + col0, v);
@@ -206,18 +214,20 @@ __global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_consta
         }
         tc::tmem_st32(lane_addr + acc + col0, v);
       }
-      // statistics of the two column halves meet in the first 16 bytes of the row's slot in the destination tile: only this
-      // row's two threads ever touch those bytes, and pass 2 overwrites them after both have read
+      // statistics of the column parts meet in the first 8 * PARTS bytes of the row's slot in the destination tile: only this
+      // row's threads ever touch those bytes, and pass 2 overwrites them after all of them have read
       float* stat = reinterpret_cast<float*>(dst_tile + r * 128);
-      stat[half * 2] = s;
-      stat[half * 2 + 1] = q;
-      named_bar(1 + quad, 64);                       // the two warps that share this TMEM lane quadrant
-      const float ts = stat[0] + stat[2], tq = stat[1] + stat[3];
+      stat[part * 2] = s;
+      stat[part * 2 + 1] = q;
+      named_bar(1 + quad, PARTS * 32);               // the warps that share this TMEM lane quadrant
+      float ts = 0.f, tq = 0.f;
+#pragma unroll
+      for (int p = 0; p < PARTS; ++p) { ts += stat[2 * p]; tq += stat[2 * p + 1]; }
       const float mean = ts * (1.f / C);
       const float rstd = rsqrtf(fmaxf(tq * (1.f / C) - mean * mean, 0.f) + a.eps);
-      named_bar(1 + quad, 64);                       // stat[] may be rewritten by the next LayerNorm only after both have read
+      named_bar(1 + quad, PARTS * 32);               // stat[] may be rewritten by the next LayerNorm only after all have read
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = col_h + c * 32;
         float v[32];
         tc::tmem_ld32(lane_addr + acc + col0, v);
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_consta
     };
     auto relu_epilogue = [&](uint32_t acc, const float* __restrict__ bias) {   // h half = relu(acc + b_e[...]) -> x_buf
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CHUNKS; ++c) {
         const int col0 = col_h + c * 32;
         float v[32];
         tc::tmem_ld32(lane_addr + acc + col0, v);
@@ -255,29 +265,29 @@ __global__ void __launch_bounds__(THREADS, 1) tail_tc_kernel(const __grid_consta
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const uint32_t ph = (uint32_t)(it & 1);
       // E1: y = LN1(acc A + b_o + x) -> a_buf (the hid slabs: G1 has completed)
-      tc::mbar_wait(&acc_full[0], ph);
+      tc::mbar_wait_suspend(&acc_full[0], ph);
       tc::tc_fence_after_sync();
       layernorm_epilogue(0u, a.bo, x_buf, a.g1, a.b1, a_buf);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&y_ready);
       // E2a: h[:, 0:256] = relu(acc B + b_e[0:256]) -> x_buf (the x tile is dead: every thread passed y_ready before G2a ran)
-      tc::mbar_wait(&acc_full[1], ph);
+      tc::mbar_wait_suspend(&acc_full[1], ph);
       tc::tc_fence_after_sync();
       relu_epilogue(256u, a.be);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&h0_ready);
       // E2b: h[:, 256:512] = relu(acc A + b_e[256:512]) -> x_buf once G3's first half has consumed h[:, 0:256]
-      tc::mbar_wait(&acc_full[2], ph);
-      tc::mbar_wait(&acc_full[4], ph);
+      tc::mbar_wait_suspend(&acc_full[2], ph);
+      tc::mbar_wait_suspend(&acc_full[4], ph);
       tc::tc_fence_after_sync();
       relu_epilogue(0u, a.be + 256);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&h1_ready);
       // E3: out = LN2(acc B + b_s + y) -> staged in x_buf (G3 has completed) -> TMA store
-      tc::mbar_wait(&acc_full[3], ph);
+      tc::mbar_wait_suspend(&acc_full[3], ph);
       tc::tc_fence_after_sync();
       layernorm_epilogue(256u, a.bs, a_buf, a.g2, a.b2, x_buf);
       tc::tc_fence_before_sync();
@@ -353,8 +363,14 @@ S6_API int sam6d_transformer_tail_bf16(const void* hid, long long ld_hid, const 
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int ntiles = s6_cdiv(M, BM), grid = ntiles < sms ? ntiles : sms;
   TailArgs a{bo, g1, b1, be, bs, g2, b2, M, eps};
-  S6_CHECK(cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  S6_CHECK(s6_launch_pdl(tail_tc_kernel, dim3(grid), dim3(THREADS), SMEM, s6_stream(stream), tmHid, tmX, tmWo, tmWe, tmWs, tmOut, a));
+  static const int epi_warps = [] { const char* e = getenv("SAM6D_TAIL_EPI_WARPS"); return (e && atoi(e) == 8) ? 8 : 16; }();
+  if (epi_warps == 8) {
+    S6_CHECK(cudaFuncSetAttribute(tail_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    S6_CHECK(s6_launch_pdl(tail_tc_kernel<8>, dim3(grid), dim3(64 + 8 * 32), SMEM, s6_stream(stream), tmHid, tmX, tmWo, tmWe, tmWs, tmOut, a));
+  } else {
+    S6_CHECK(cudaFuncSetAttribute(tail_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    S6_CHECK(s6_launch_pdl(tail_tc_kernel<16>, dim3(grid), dim3(64 + 16 * 32), SMEM, s6_stream(stream), tmHid, tmX, tmWo, tmWe, tmWs, tmOut, a));
+  }
   S6_LAUNCH_CHECK();
   return 0;
 }

@@ -882,7 +882,20 @@ class Net(nn.Module):
         self.geo_embedding = GeometricStructureEmbedding(cfg.geo_embedding)
         self.coarse_point_matching = CoarsePointMatching(cfg.coarse_point_matching)
         self.fine_point_matching = FinePointMatching(cfg.fine_point_matching)
+        self._graphs = None
         self.set_precision(precision)
+
+    def enable_graphs(self, max_graphs: int = 8):
+        """replay repeated fixed-shape calls of forward() as one CUDA graph each (sam6d_b200/graph.py: a call signature seen for
+        the second time is captured, reading the caller's tensors in place; results are identical to the launch-by-launch
+        forward, which stays the path for first sightings, `init_pose` calls and `disable_graphs()`)"""
+        from .graph import StepGraphs
+        self._graphs = StepGraphs(max_graphs)
+        return self
+
+    def disable_graphs(self):
+        self._graphs = None
+        return self
 
     def set_precision(self, precision: str):
         """'fp32' (CUDA-core kernels, exact path) or 'bf16' (tcgen05 tensor-core kernels, bf16 operands / fp32 accumulate)"""
@@ -918,6 +931,15 @@ class Net(nn.Module):
         hypothesis selection."""
         if self.training:
             raise NotImplementedError("sam6d_b200 implements the inference path: call model.eval()")
+        if self._graphs is not None and init_pose is None and 'pts' in end_points:
+            n_rand = self.coarse_point_matching.cfg.nproposal1 * 3
+            out = self._graphs.run(lambda ep, r: self._forward(ep, r, None), end_points, rand, n_rand,
+                                   extra=(self.precision, hash(_param_key(self))))
+            if out is not None:
+                return out
+        return self._forward(end_points, rand, init_pose)
+
+    def _forward(self, end_points, rand, init_pose):
         dense_pm, dense_fm, dense_po, dense_fo, radius = self._features(end_points)
         B = dense_pm.size(0)
         if dense_pm.shape == dense_po.shape and dense_fm.shape == dense_fo.shape:
