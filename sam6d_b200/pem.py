@@ -420,15 +420,16 @@ def compute_coarse_Rt(atten, pts1, pts2, model_pts=None, n_proposal1=6000, n_pro
     return R, t
 
 
-def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, temp=0.1, radius=None):
+def compute_fine_Rt(atten, pts1, pts2, model_pts=None, dis_thres=0.15, temp=0.1, radius=None, check_bound=True):
     """model_utils.py:250-283.  Returns (R, t, pose_score); with `radius` also t * (radius + 1e-6).
     `atten` must be a cosine-similarity matrix divided by `temp` (|atten| <= 1/temp): the assignment kernels use the fixed
     soft-max shift 1/temp instead of a per-row / per-column maximum pass, which is exact for such scores and overflows for
-    unbounded ones -- so out-of-range input raises instead of silently returning inf / NaN."""
+    unbounded ones -- so out-of-range input raises instead of silently returning inf / NaN (`check_bound=False` skips that
+    host read-back for callers whose scores are cosines by construction: FinePointMatching)."""
     if model_pts is None:
         model_pts = pts2
     bound = 1.0 / temp
-    if float(atten.abs().max()) > bound * (1.0 + 1e-3):
+    if check_bound and float(atten.abs().max()) > bound * (1.0 + 1e-3):
         raise ValueError(f"compute_fine_Rt: |atten| exceeds 1/temp = {bound:g}; the CUDA path handles cosine scores "
                          "(sim_type='cosine', normalize_feat=True) only")
     pts1, pts2 = pts1.contiguous(), pts2.contiguous()
@@ -837,7 +838,9 @@ class FinePointMatching(nn.Module):
                 raise NotImplementedError("FinePointMatching: normalize_feat=False scores are unbounded; the fixed-shift assignment "
                                           "kernels need cosine similarities (the SAM-6D configuration)")
             atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
-            pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous())
+            # cosine scores of normalised features: bounded by 1/temp by construction, no read-back (keeps the forward capturable)
+            pred_R, _, score, t_scaled = compute_fine_Rt(atten, p1, p2, model, temp=self.cfg.temp, radius=radius.contiguous(),
+                                                         check_bound=False)
         end_points['pred_R'] = pred_R
         end_points['pred_t'] = t_scaled
         end_points['pred_pose_score'] = score
