@@ -171,6 +171,19 @@ int sam6d_masked_patch_normalize(const float* tokens, long long tok_ld, long lon
 int sam6d_appearance_reduce(const float* sim, long long sim_ld, long long sim_bs, int P, int N, const unsigned char* qvalid, float thred,
                             float* appe, float* vis, void* stream);
 
+/* ---- ISM geometric score (ISM/model/detector.py:209-258, 311-323; ISM/utils/trimesh_utils.py:77-105; ISM/utils/bbox_utils.py:197-221) */
+
+/* Calculate_the_query_translation -> depth_image_to_pointcloud_translate_torch: masks (N,H,W) f32 0/1, depth (H,W) i32, K (3,3) f64
+ * row-major ON THE DEVICE, depth_scale -> translate (N,3) f32 = mean back-projected point of the masked depth (float64 sums) */
+int sam6d_query_translation(const float* masks, const int* depth, int N, int H, int W, const double* K, double depth_scale,
+                            float* translate, void* stream);
+/* project_template_to_image + the IoU of compute_geometric_score: poses (T,4,4) f32, pointcloud (O,npc,3) f32, best_pose / pred_obj
+ * (N) i64, translate (N,3) f32, K (3,3) f64 on the device, boxes (N,4) i64 xyxy -> image_vu (N,npc,2) i32 or NULL, xyxy (N,4) i32
+ * (box of the projected samples), iou (N) f32, ok (N) u8 (non-empty intersection; the reference scores the batch 0 unless all are) */
+int sam6d_project_template_iou(const float* poses, int T, const float* pointcloud, int O, int npc, const long long* best_pose,
+                               const long long* pred_obj, const float* translate, const double* K, int N, int H, int W,
+                               const long long* boxes, int* image_vu, int* xyxy, float* iou, unsigned char* ok, void* stream);
+
 /* ---- SAM prompt encoder / mask decoder / automatic mask generator: everything that is not a GEMM
  *      (ISM/segment_anything/modeling/{prompt_encoder,mask_decoder,transformer}.py, automatic_mask_generator.py:225-321,
  *       utils/amg.py:156-176,303-345, modeling/sam.py:133-162) ------------------------------------------------------------ */

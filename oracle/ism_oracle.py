@@ -5,11 +5,15 @@ CPU restatement of the ISM template-scoring path:
     compute_semantic_score   ISM/model/detector.py:260-296 with aggregation 'avg_5', and best_template_pose :198-207
     appearance_score         ISM/model/loss.py:52-63   (MaskedPatch_MatrixSimilarity.compute_straight), detector.py:298-309
     visible_ratio            ISM/model/loss.py:65-77   (compute_visible_ratio), detector.py:311-323
+    query_translation        ISM/model/detector.py:237-250 (Calculate_the_query_translation) + ISM/utils/trimesh_utils.py:77-105
+    project_template_to_image ISM/model/detector.py:209-235;  geometric_iou  detector.py:311-323 + ISM/utils/bbox_utils.py:197-221
 Parity status: PINNED.  tools/make_golden_ism.py imports the reference's own loss.py / detector.py from /root/reference
 (absent third-party imports stubbed, no reference line changed), runs them on the seeded descriptors of BASELINE configs
 #3 and #5 and finds this restatement bit-identical (similarity tensor, selected proposals, object indices, scores, template
 indices); the outputs are committed as tests/golden/ism_scoring.pt and checked by tests/test_oracle_ism.py (CPU) and
-tests/test_gpu_kernels.py (CUDA kernel, bit-exact indices).
+tests/test_gpu_kernels.py (CUDA kernel, bit-exact indices).  The geometric score (translation, projection, box, IoU) is pinned
+by tools/make_golden_ism_geo.py against the reference's own detector methods on the dtypes its run_inference_custom.py feeds them
+(int32 depth, float64 intrinsics and depth scale): tests/golden/ism_geo.pt.
 """
 import torch
 import torch.nn.functional as F
@@ -55,6 +59,85 @@ def visible_ratio(query_patches: torch.Tensor, ref_patches: torch.Tensor, thred:
     valid = torch.count_nonzero(sim, dim=(1,)) + 1e-6
     hit = torch.count_nonzero(sim * (sim > thred), dim=(1,))
     return hit / valid
+
+
+def query_translation(masks: torch.Tensor, depth: torch.Tensor, K: torch.Tensor, depth_scale: torch.Tensor) -> torch.Tensor:
+    """masks (N,H,W) f32 0/1, depth (H,W) int32, K (3,3) float64, depth_scale (1,) float64 -> (N,3) f32: mean back-projected point
+    of the masked depth.  With the reference's input dtypes the whole computation is float64 (the (1,)-shaped float64 scale and the
+    float64 intrinsics promote it), the result is cast to float32 at the end."""
+    masked = masks * depth[None, ...].repeat(masks.shape[0], 1, 1)
+    u = torch.arange(0, masked.shape[2])
+    v = torch.arange(0, masked.shape[1])
+    u, v = torch.meshgrid(u, v, indexing="xy")
+    Z = masked * depth_scale / 1000
+    X = (u - K[0, 2]) * Z / K[0, 0]
+    Y = (v - K[1, 2]) * Z / K[1, 1]
+    valid = Z > 0
+    X, Y, Z = X * valid, Y * valid, Z * valid
+    n = torch.count_nonzero(valid, dim=(1, 2)) + 1e-8
+    tr = torch.vstack((torch.sum(X, dim=(1, 2)) / n, torch.sum(Y, dim=(1, 2)) / n, torch.sum(Z, dim=(1, 2)) / n)).permute(1, 0)
+    return tr.to(torch.float32)
+
+
+def project_template_to_image(poses: torch.Tensor, pointcloud: torch.Tensor, best_pose: torch.Tensor, pred_obj: torch.Tensor,
+                              translate: torch.Tensor, K: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """poses (T,4,4) f32, pointcloud (O,Np,3) f32, best_pose / pred_obj (N,) int64, translate (N,3) f32 -> (N,Np,2) int32 pixel
+    coordinates (x, y) of the posed CAD samples, truncated and clamped to the image"""
+    R = poses[best_pose, 0:3, 0:3]
+    pc = pointcloud[pred_obj, ...]
+    n, npc, _ = pc.shape
+    posed = torch.matmul(R, pc.permute(0, 2, 1)).permute(0, 2, 1)
+    posed = posed + translate[:, None, :].repeat(1, npc, 1)
+    Kf = K[None, ...].repeat(n, 1, 1).to(torch.float32)
+    homo = torch.bmm(Kf, posed.permute(0, 2, 1)).permute(0, 2, 1)
+    vu = (homo / homo[:, :, -1][:, :, None])[:, :, 0:2].to(torch.int)
+    vu[:, :, 0].clamp_(min=0, max=W - 1)
+    vu[:, :, 1].clamp_(min=0, max=H - 1)
+    return vu
+
+
+def geometric_iou(image_vu: torch.Tensor, boxes: torch.Tensor):
+    """-> (xyxy (N,4) of the projected samples, IoU with the proposal boxes (N,) f32, or the float 0.0 when ANY proposal's
+    intersection is empty: the reference's `if (wh_inter > 0).all()` is a property of the whole batch)"""
+    xyxy = torch.cat((torch.min(image_vu, dim=1).values, torch.max(image_vu, dim=1).values), dim=-1)
+    tl = torch.max(xyxy[:, 0:2], boxes[:, 0:2])
+    br = torch.min(xyxy[:, 2:4], boxes[:, 2:4])
+    wh_a, wh_b, wh = xyxy[:, 2:4] - xyxy[:, 0:2], boxes[:, 2:4] - boxes[:, 0:2], br - tl
+    if (wh > 0).all():
+        inter = wh[:, 0] * wh[:, 1]
+        return xyxy, inter / (wh_a[:, 0] * wh_a[:, 1] + wh_b[:, 0] * wh_b[:, 1] - inter)
+    return xyxy, 0.0
+
+
+def make_geometric_inputs(N: int = 12, H: int = 480, W: int = 640, T: int = 42, O: int = 2, npc: int = 2048, seed: int = 0):
+    """a synthetic frame for the geometric score: elliptic masks over a depth ramp with holes, template rotations, CAD samples,
+    proposal boxes around the masks (so that every projected box meets its proposal box) -- dtypes as run_inference_custom.py"""
+    g = torch.Generator().manual_seed(seed)
+    K = torch.tensor([[572.4114, 0.0, 325.2611], [0.0, 573.57043, 242.04899], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    depth_scale = torch.tensor([1.0], dtype=torch.float64)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    depth = (700 + 0.25 * xx + 0.15 * yy + 30 * torch.rand(H, W, generator=g)).to(torch.int32)
+    depth[torch.rand(H, W, generator=g) < 0.05] = 0                         # sensor holes
+    masks, boxes = [], []
+    for i in range(N):
+        cx, cy = 80 + torch.rand(1, generator=g).item() * (W - 160), 70 + torch.rand(1, generator=g).item() * (H - 140)
+        rx, ry = 25 + torch.rand(1, generator=g).item() * 45, 20 + torch.rand(1, generator=g).item() * 40
+        m = (((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2) <= 1.0
+        masks.append(m.float())
+        ys, xs = torch.nonzero(m, as_tuple=True)
+        boxes.append(torch.stack([xs.min(), ys.min(), xs.max(), ys.max()]))
+    masks, boxes = torch.stack(masks), torch.stack(boxes).long()
+    A = torch.randn(T, 3, 3, generator=g)
+    Q, _ = torch.linalg.qr(A)
+    Q = Q * torch.sign(torch.linalg.det(Q))[:, None, None]
+    poses = torch.eye(4).repeat(T, 1, 1)
+    poses[:, :3, :3] = Q
+    poses[:, :3, 3] = torch.randn(T, 3, generator=g)
+    pointcloud = (torch.rand(O, npc, 3, generator=g) - 0.5) * torch.tensor([0.10, 0.07, 0.05])     # metres, a box-like object
+    best_pose = torch.randint(0, T, (N,), generator=g)
+    pred_obj = torch.randint(0, O, (N,), generator=g)
+    return dict(masks=masks, depth=depth, K=K, depth_scale=depth_scale, poses=poses, pointcloud=pointcloud, best_pose=best_pose,
+                pred_obj=pred_obj, boxes=boxes)
 
 
 from sam6d_b200.synth import make_descriptors  # noqa: E402,F401  (synthetic descriptors: shared with bench.py)

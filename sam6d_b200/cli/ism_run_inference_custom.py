@@ -100,40 +100,6 @@ def build_models(args, device):
     return seg, desc
 
 
-def project_template_to_image(poses, pointcloud, best_pose, masks, depth, K, depth_scale):
-    """detector.py:209-258 + trimesh_utils.py:77-105: CAD samples posed by the best template's rotation, translated to the masked
-    depth centroid, projected -> (N, n_points, 2) pixel coordinates"""
-    R = poses[best_pose, 0:3, 0:3]
-    N = R.shape[0]
-    pc = pointcloud.unsqueeze(0).expand(N, -1, -1)
-    posed = torch.matmul(R, pc.permute(0, 2, 1)).permute(0, 2, 1)
-    H, W = depth.shape
-    md = masks * depth[None].float()
-    u = torch.arange(W, device=depth.device)[None, None, :].float()
-    v = torch.arange(H, device=depth.device)[None, :, None].float()
-    Z = md * depth_scale / 1000
-    X, Y = (u - K[0, 2]) * Z / K[0, 0], (v - K[1, 2]) * Z / K[1, 1]
-    valid = Z > 0
-    num = torch.count_nonzero(valid, dim=(1, 2)) + 1e-8
-    tr = torch.stack([(X * valid).sum((1, 2)) / num, (Y * valid).sum((1, 2)) / num, (Z * valid).sum((1, 2)) / num], dim=1).float()
-    posed = posed + tr[:, None, :]
-    homo = torch.bmm(K[None].expand(N, -1, -1).float(), posed.permute(0, 2, 1)).permute(0, 2, 1)
-    vu = (homo / homo[:, :, -1][:, :, None])[:, :, 0:2].to(torch.int)
-    vu[:, :, 0].clamp_(min=0, max=W - 1)
-    vu[:, :, 1].clamp_(min=0, max=H - 1)
-    return vu
-
-
-def compute_iou(a, b):
-    """bbox_utils.py:197-221"""
-    tl, br = torch.max(a[:, 0:2], b[:, 0:2]), torch.min(a[:, 2:4], b[:, 2:4])
-    wh_a, wh_b, wh = a[:, 2:4] - a[:, 0:2], b[:, 2:4] - b[:, 0:2], br - tl
-    if (wh > 0).all():
-        inter = wh[:, 0] * wh[:, 1]
-        return inter / (wh_a[:, 0] * wh_a[:, 1] + wh_b[:, 0] * wh_b[:, 1] - inter)
-    return 0.0
-
-
 def main(argv=None):
     args = get_parser().parse_args(argv)
     if args.segmentor_model != "sam":
@@ -190,9 +156,8 @@ def main(argv=None):
         poses = torch.tensor(np.load(pose_path)).float().to(device)
         verts, faces, _ = meshio.load_ply(args.cad_path)
         pc = torch.from_numpy(meshio.sample_surface(verts, faces, 2048) / 1000.0).float().to(device)
-        vu = project_template_to_image(poses, pc, best_t, det.masks, depth, K, float(np.array(cam["depth_scale"])))
-        xyxy = torch.cat((torch.min(vu, dim=1).values, torch.max(vu, dim=1).values), dim=-1)
-        geo = compute_iou(xyxy, det.boxes)
+        geo, _, _ = ism.compute_geometric_iou(poses, pc, best_t, torch.zeros_like(best_t), det.masks, depth, K,
+                                              float(np.array(cam["depth_scale"])), det.boxes)
         final = (sem + appe + geo * vis) / (1 + 1 + vis)
     else:
         print("=> no template poses: final score = (semantic + appearance) / 2", file=sys.stderr)

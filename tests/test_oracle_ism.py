@@ -21,3 +21,24 @@ def test_oracle_matches_reference_scoring(golden_dir, case):
     torch.testing.assert_close(sem, c["semantic_score"], atol=1e-6, rtol=0)
     torch.testing.assert_close(scores, c["sim"], atol=1e-6, rtol=0)
     assert 0 < len(idx_sel) < c["P"]                               # the threshold splits the synthetic proposals
+
+
+@pytest.mark.parametrize("case", ["frame12", "frame64"])
+def test_oracle_matches_reference_geometric_score(golden_dir, case):
+    """tests/golden/ism_geo.pt = outputs of the reference's own Calculate_the_query_translation / project_template_to_image /
+    compute_geometric_score (tools/make_golden_ism_geo.py), on int32 depth and float64 intrinsics like its run_inference_custom.py"""
+    gold = torch.load(os.path.join(golden_dir, "ism_geo.pt"), weights_only=False)
+    c = gold["cases"][case]
+    inp = io.make_geometric_inputs(**c["kw"])
+    assert float(inp["masks"].double().sum() + inp["depth"].double().sum() + inp["pointcloud"].double().sum()) == c["input_checksum"]
+    H, W = inp["depth"].shape
+    tr = io.query_translation(inp["masks"], inp["depth"], inp["K"], inp["depth_scale"])
+    vu = io.project_template_to_image(inp["poses"], inp["pointcloud"], inp["best_pose"], inp["pred_obj"], tr, inp["K"], H, W)
+    xyxy, iou = io.geometric_iou(vu, inp["boxes"])
+    assert torch.equal(tr, c["translate"]) and int(vu.long().sum()) == c["vu_checksum"]
+    assert torch.equal(xyxy, c["xyxy"]) and torch.equal(iou, c["iou"])
+    assert (iou > 0.2).all() and (iou < 1).all()
+    # batch-wide rule of compute_iou: one empty intersection zeroes the whole batch
+    boxes = inp["boxes"].clone()
+    boxes[1] = torch.tensor([0, 0, 2, 2])
+    assert io.geometric_iou(vu, boxes)[1] == 0.0
