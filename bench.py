@@ -561,7 +561,7 @@ def main():
     # (launch by launch: the events bracket single launches, which a graph replay does not expose; same kernels, same inputs)
     step_graphs, net._graphs = net._graphs, None
     _, _, kall = timed(step_resident, args.steps,
-                       profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_attn_tc_bias_ld", "sam6d_geo_embed_tc"])
+                       profile_kernel=[rpe_name, "sam6d_attn_tc", "sam6d_attn_tc_bias_ld", "sam6d_geo_embed_tc", "sam6d_geo_embed_lut"])
     net._graphs = step_graphs
     kms = kall[rpe_name]
     for i in range(4 if graphs else 2):
@@ -607,6 +607,19 @@ def main():
                                    frac=flops_min / (geo_ms * 1e-3) / 1e12 / pk["tensor"], avg_call_ms=geo_ms,
                                    flops_min_per_call=flops_min, flops_issued_per_call=flops_issued,
                                    share_of_step=sum(geo) / ms)
+        roofline_geo = None
+        lut = kall.get("sam6d_geo_embed_lut") or []
+        if lut:
+            # table-interpolation kernel (csrc/geo_lut.cu): no MMA left, E is written exactly once -> HBM-write bound.  Algorithmic
+            # bytes = E (2B clouds x S x S x 256 bf16) + the four fp32 indices per pair it reads
+            lut_ms = sum(lut) / len(lut)
+            geo_bytes = (2 * B) * S * S * (256 * 2 + 16)
+            roofline_geo = dict(kernel="geo_embed_lut_kernel (GeometricStructureEmbedding by table interpolation: writes E once)", bound="hbm",
+                                achieved=geo_bytes / (lut_ms * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s",
+                                frac=geo_bytes / (lut_ms * 1e-3) / 1e9 / pk["hbm"], avg_launch_ms=lut_ms,
+                                algorithmic_bytes_per_launch=geo_bytes, share_of_step=sum(lut) / ms,
+                                note="replaces the tcgen05 projections (977 GFLOP min per step, 1.30 ms = 0.53 of the sustained bf16 rate): "
+                                     "the projected embedding of one scalar is tabulated, so the flops are gone rather than run faster")
         value = world * B * args.steps / (ms * 1e-3)
         e2e_val = world * B * args.steps / (ms_e2e * 1e-3)
         traffic = None
@@ -637,6 +650,7 @@ def main():
                           attention_frac=attention_frac, attention_avg_ms=(k_avg_ms + att_avg_ms) if att_avg_ms else None,
                           attention_note="score stream + the attn_tc launch that consumes it (softmax, PV), same algorithmic bytes"),
             roofline_tensor=roofline_tensor,
+            roofline_geo=roofline_geo,
             clocks=sampler.summary() if sampler else None,
         )
         if world == 1 and not args.no_cpu_baseline:

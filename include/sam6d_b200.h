@@ -129,6 +129,18 @@ int sam6d_geo_embed_f32(const float* T, long long npairs, const float* div_term,
 /* tensor-core version (tcgen05, bf16 operands, fp32 accumulate): Wa/Wd are the (out,in) weights in bf16, E fp32 (0) or bf16 (1) */
 int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div_term, const void* Wa_bf16, const void* Wd_bf16,
                        const float* bias, void* E, int e_is_bf16, void* stream);
+/* the distance projection of sam6d_geo_embed_tc alone: T (npairs,4) f32 -> E (npairs,256) bf16 = proj_d(emb(T[:,3])) + bias */
+int sam6d_geo_embed_dist_tc(const float* T, long long npairs, const float* div_term, const void* Wd_bf16, const float* bias, void* E,
+                            void* stream);
+/* GeometricStructureEmbedding by table interpolation (csrc/geo_lut.cu; transformer.py:334-349): g_a(x) = W_a emb(x) and
+ * g_d(x) = W_d emb(x) + bias are functions of ONE scalar, tabulated on a uniform grid (tabA (na,256) bf16 at step 1/inv_ha from 0,
+ * tabD (nd,256) bf16 at step 1/inv_hd) -> E (clouds*S*S,256) bf16 = lerp(tabD, d) + max_k lerp(tabA, a_k), written once.
+ * Distances outside tabD: row 0 / column 0 of a cloud read far (clouds,2,S,256) bf16 (exact g_d of those 2 S distances, from
+ * sam6d_geo_embed_dist_tc); any other pair is evaluated exactly from div_term (128 f32), WdT (256 in, 256 out) bf16 and bias.
+ * precise = 1: interpolation, maximum and sum in fp32 with one rounding at the store; 0: packed bf16x2 arithmetic. */
+int sam6d_geo_embed_lut(const float* T, long long clouds, int S, const void* tabA, int na, float inv_ha, const void* tabD, int nd,
+                        float inv_hd, const void* far, const float* div_term, const void* WdT_bf16, const float* bias, void* E,
+                        int precise, void* stream);
 
 /* ---- PEM input builder (PEM/run_inference_custom.py:165-253 get_test_data; PEM/utils/data_utils.py:73-160) ----------- */
 

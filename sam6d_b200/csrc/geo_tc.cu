@@ -445,3 +445,16 @@ S6_API int sam6d_geo_embed_tc(const float* T, long long npairs, const float* div
   }
   return rc;
 }
+
+// the distance projection alone: T (npairs,4) fp32 (index 3 = distance index) -> E (npairs,256) bf16 = proj_d(emb(d)) + bias.
+// Used by the table-interpolation kernel (geo_lut.cu) for the few distances outside its table (row / column of the background point)
+S6_API int sam6d_geo_embed_dist_tc(const float* T, long long npairs, const float* div_term, const void* Wd_bf16, const float* bias, void* E,
+                                   void* stream) {
+  S6_REQUIRE(T && div_term && Wd_bf16 && bias && E && npairs >= 0 && npairs < 2000000000LL);
+  if (npairs == 0) return 0;
+  int dev = 0, sms = 0;
+  S6_CHECK(cudaGetDevice(&dev));
+  S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return launch_pass<1, __nv_bfloat16>(T, npairs, div_term, reinterpret_cast<const __nv_bfloat16*>(Wd_bf16), bias,
+                                       reinterpret_cast<__nv_bfloat16*>(E), sms, s6_stream(stream));
+}

@@ -429,6 +429,35 @@ def geo_embed_tc(T: Tensor, div_term: Tensor, Wa_bf16: Tensor, Wd_bf16: Tensor, 
     return E
 
 
+def geo_embed_dist_tc(T: Tensor, div_term: Tensor, Wd_bf16: Tensor, bias: Tensor) -> Tensor:
+    """distance projection only: T (..., 4) f32 -> (..., 256) bf16 = proj_d(emb(T[..., 3])) + bias (tcgen05)"""
+    if T.dtype != torch.float32 or not T.is_cuda or not T.is_contiguous() or T.shape[-1] != 4:
+        raise RuntimeError("T must be a contiguous CUDA float32 tensor (..., 4)")
+    _check(Wd_bf16, torch.bfloat16, "Wd", 2)
+    n = T.numel() // 4
+    E = torch.empty(*T.shape[:-1], 256, dtype=torch.bfloat16, device=T.device)
+    _lib.call("sam6d_geo_embed_dist_tc", _p(T), _ll(n), _p(div_term), _p(Wd_bf16), _p(bias), _p(E), _s())
+    return E
+
+
+def geo_embed_lut(T: Tensor, tabA: Tensor, inv_ha: float, tabD: Tensor, inv_hd: float, far: Tensor, div_term: Tensor, WdT_bf16: Tensor,
+                  bias: Tensor, precise: bool = True) -> Tensor:
+    """table-interpolation geometric embedding (csrc/geo_lut.cu): T (B,S,S,4) f32, tabA (na,256) / tabD (nd,256) bf16,
+    far (B,2,S,256) bf16 -> E (B,S,S,256) bf16"""
+    _check(T, torch.float32, "T", 4)
+    _check(tabA, torch.bfloat16, "tabA", 2)
+    _check(tabD, torch.bfloat16, "tabD", 2)
+    _check(far, torch.bfloat16, "far", 4)
+    _check(WdT_bf16, torch.bfloat16, "WdT", 2)
+    b, s, _, _ = T.shape
+    if far.shape != (b, 2, s, 256) or tabA.shape[1] != 256 or tabD.shape[1] != 256 or T.shape[3] != 4:
+        raise RuntimeError("geo_embed_lut: shape mismatch")
+    E = torch.empty(b, s, s, 256, dtype=torch.bfloat16, device=T.device)
+    _lib.call("sam6d_geo_embed_lut", _p(T), _ll(b), s, _p(tabA), tabA.shape[0], _f(inv_ha), _p(tabD), tabD.shape[0], _f(inv_hd), _p(far),
+              _p(div_term), _p(WdT_bf16), _p(bias), _p(E), int(bool(precise)), _s())
+    return E
+
+
 # ---------------------------------------------------------------------------------------------- attention
 def rpe_scores(E: Tensor, U: Tensor, u_ptr: Optional[int] = None, u_ld: int = 1024) -> Tensor:
     """E (B,S,S,256) f32|bf16, U (B,S,4,256) f32 (or a raw address + row stride) -> (B,4,S,S) f32."""

@@ -34,6 +34,11 @@ FUSED_TAIL = os.environ.get("SAM6D_FUSED_TAIL", "1") != "0"
 # the relative-position score stream over E on TMA + tcgen05 (csrc/rpe_tc.cu); False = the CUDA-core kernel (csrc/attn.cu)
 PADDED_BIAS = os.environ.get("SAM6D_PADDED_BIAS", "1") != "0"
 RPE_TC = os.environ.get("SAM6D_RPE_TC", "1") != "0"
+# bf16 path: the geometric embedding by table interpolation (csrc/geo_lut.cu); False = the tcgen05 projections (csrc/geo_tc.cu)
+GEO_LUT = os.environ.get("SAM6D_GEO_LUT", "1") != "0"
+GEO_LUT_PRECISE = os.environ.get("SAM6D_GEO_LUT_PRECISE", "1") != "0"   # fp32 interpolation, one rounding at the store
+GEO_LUT_INV_H = 8.0            # table step 1/8 index unit
+GEO_LUT_D_MAX = 16.0           # distance indices below this come from the table (normalised clouds stay below 12)
 
 
 class _W:
@@ -352,8 +357,26 @@ class GeometricStructureEmbedding(nn.Module):
                                   wa_bf=_f32(self.proj_a.weight).to(torch.bfloat16).contiguous(),
                                   wd_bf=_f32(self.proj_d.weight).to(torch.bfloat16).contiguous(),
                                   bias=(_f32(self.proj_a.bias) + _f32(self.proj_d.bias)).contiguous())
+            self._packed.w.update(self._tables(self._packed.w))
             self._packed.key = key
         return self._packed.w
+
+    def _tables(self, w):
+        """g_a(x) = W_a emb(x) on [0, 180 / sigma_a] and g_d(x) = W_d emb(x) + (b_a + b_d) on [0, GEO_LUT_D_MAX], step
+        1 / GEO_LUT_INV_H, evaluated in float64 from the fp32 weights and stored in bf16 (csrc/geo_lut.cu interpolates them)"""
+        div = w["div"].double()
+
+        def table(weight, x_max, bias=None):
+            n = int(math.ceil(x_max * GEO_LUT_INV_H)) + 1
+            om = (torch.arange(n, dtype=torch.float64, device=div.device) / GEO_LUT_INV_H)[:, None] * div[None, :]
+            emb = torch.stack([torch.sin(om), torch.cos(om)], dim=2).reshape(n, -1)      # interleaved (sin, cos) per frequency
+            g = emb @ weight.detach().double().t()
+            if bias is not None:
+                g = g + bias.double()
+            return g.to(torch.float32).to(torch.bfloat16).contiguous()
+
+        return dict(tab_a=table(self.proj_a.weight, 180.0 / self.sigma_a), tab_d=table(self.proj_d.weight, GEO_LUT_D_MAX, w["bias"]),
+                    wdT_bf=_f32(self.proj_d.weight).t().contiguous().to(torch.bfloat16).contiguous())
 
     @torch.no_grad()
     def get_embedding_indices(self, points):
@@ -364,6 +387,12 @@ class GeometricStructureEmbedding(nn.Module):
     def forward(self, points):
         w = self._weights()
         T = ops.geo_indices(points.contiguous(), self.sigma_d, self.factor_a)
+        if self.precision == "bf16" and GEO_LUT:
+            # distances of row 0 / column 0 (the background point of SAM-6D: far outside the table) go through the exact
+            # tensor-core projection: 2 S values per cloud
+            far = ops.geo_embed_dist_tc(torch.stack([T[:, 0, :, :], T[:, :, 0, :]], dim=1).contiguous(), w["div"], w["wd_bf"], w["bias"])
+            return ops.geo_embed_lut(T, w["tab_a"], GEO_LUT_INV_H, w["tab_d"], GEO_LUT_INV_H, far, w["div"], w["wdT_bf"], w["bias"],
+                                     precise=GEO_LUT_PRECISE)
         if self.precision == "bf16":
             return ops.geo_embed_tc(T, w["div"], w["wa_bf"], w["wd_bf"], w["bias"], out_dtype=torch.bfloat16)
         return ops.geo_embed_f32(T, w["div"], w["waT"], w["wdT"], w["bias"])

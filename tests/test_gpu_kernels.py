@@ -589,6 +589,50 @@ def test_geo_embed_tc(ops, S, edt):
     torch.testing.assert_close(E, E32, atol=6e-2, rtol=0)
 
 
+@pytest.mark.parametrize("precise", [True, False])
+@pytest.mark.parametrize("S,far_point", [(197, False), (64, False), (197, True), (33, True)])
+def test_geo_embed_lut(ops, S, far_point, precise, monkeypatch):
+    """table-interpolated geometric embedding (csrc/geo_lut.cu) through the module, against the float64-index embedding: at least as
+    close as the tensor-core product, incl. the background point's row / column (exact distance projection, `far`) and -- far_point
+    -- an ordinary point 40 units away, whose pairs take the exact per-pair fallback"""
+    from sam6d_b200 import pem
+    sd = po.make_state_dict(seed=2)
+    pts = _sparse_cloud(3, S, 9)
+    if far_point:
+        pts[:, 5, :] = torch.tensor([30.0, -20.0, 10.0])
+    ref = exact_geo_embedding(sd, pts)
+    geo = pem.GeometricStructureEmbedding(pem.DEFAULT_MODEL_CFG["geo_embedding"]).cuda()
+    geo.load_state_dict({k[len("geo_embedding."):]: v for k, v in sd.items() if k.startswith("geo_embedding.")})
+    geo.precision = "bf16"
+    monkeypatch.setattr(pem, "GEO_LUT", True)
+    monkeypatch.setattr(pem, "GEO_LUT_PRECISE", precise)     # fp32 interpolation (default) / packed bf16x2 arithmetic
+    E = geo(pts.cuda())
+    assert E.dtype == torch.bfloat16 and E.shape == ref.shape
+    E = E.float().cpu()
+    assert torch.isfinite(E).all()
+    err = (E - ref).abs()
+    assert err.median().item() < 4e-3, err.median().item()
+    assert (err > 6e-2).float().mean().item() < 2e-3
+    T = ops.geo_indices(pts.cuda(), po.SIGMA_D, 180.0 / (po.SIGMA_A * math.pi))
+    w = geo._weights()
+    Etc = ops.geo_embed_tc(T, w["div"], w["wa_bf"], w["wd_bf"], w["bias"], out_dtype=torch.bfloat16).float().cpu()
+    # same indices: the two kernels differ only by their bf16 roundings (no knn-tie outliers)
+    torch.testing.assert_close(E, Etc, atol=4e-2, rtol=0)
+    rms_lut, rms_tc = (E - ref).pow(2).mean().sqrt().item(), (Etc - ref).pow(2).mean().sqrt().item()
+    print(f"geo S={S} far_point={far_point} precise={precise}: rms error vs float64-index embedding: table {rms_lut:.3e}, tensor-core {rms_tc:.3e}")
+    assert rms_lut < 1.1 * rms_tc + 1e-4
+    # rows / columns whose distance index is outside the table
+    far_rows = [0, 5] if far_point else [0]
+    for r in far_rows:
+        others = [m for m in range(S) if m != r]
+        assert (T[:, r, others, 3] > 16).all()
+        assert (E[:, r] - ref[:, r]).abs().median().item() < 4e-3 and (E[:, :, r] - ref[:, :, r]).abs().median().item() < 4e-3
+    # the distance-only tensor-core projection that feeds `far`
+    far = ops.geo_embed_dist_tc(T[:, 0].contiguous(), w["div"], w["wd_bf"], w["bias"]).float().cpu()
+    want = po._lin(sd, "geo_embedding.proj_d", po.sinusoidal_embedding(T[:, 0, :, 3].cpu(), 256)) + sd["geo_embedding.proj_a.bias"]
+    torch.testing.assert_close(far, want, atol=3e-2, rtol=0)
+
+
 def test_positional_encoding_tensor_core(ops):
     """layers 2/3 of the PE shared MLP on tcgen05 (bf16 operands) against the fp32 oracle"""
     from sam6d_b200.pem import PositionalEncoding
