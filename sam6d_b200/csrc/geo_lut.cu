@@ -4,10 +4,10 @@
 //
 // emb(x) is the 256-entry sinusoidal embedding of ONE scalar, so g_a and g_d are smooth vector-valued functions of a scalar:
 // frequencies <= 1 rad per index unit, angle indices in [0, 12] (angles in [0, pi] / sigma_a), distance indices of points in
-// normalised clouds below 16.  The reference evaluates them with 4 x 256 sin/cos and two 256 x 256 products PER PAIR (651 GFLOP
+// normalised clouds below 12 (the table spans [0, 32): 6.4 object radii).  The reference evaluates them with 4 x 256 sin/cos and two 256 x 256 products PER PAIR (651 GFLOP
 // per cloud batch; the tensor-core version of this repo, geo_tc.cu, still spent 1.3 ms per step on it, bound by MUFU, MMA issue and
 // its epilogue together).  Here both functions are tabulated once per weight set on a grid of step 1/8 (host side, float64,
-// from the fp32 weights: 97 + 129 rows of 256 bf16 = 116 KB) and a pair costs four linear interpolations out of shared memory:
+// from the fp32 weights: 97 + 257 rows of 256 bf16 = 181 KB) and a pair costs four linear interpolations out of shared memory:
 // no sin/cos, no MMA, E written exactly once.  Interpolation error at step 1/8 is < 1e-4 of |E| -- below the bf16 rounding of
 // the table and of E itself; measured against the float64 embedding the result is closer than the bf16-operand tensor-core
 // product was (rms 1.6e-3 vs 1.8e-3 at |E| ~ 0.56, tools/geo_lut_error.py).
@@ -19,10 +19,12 @@
 // Bounds per 64-cloud call: E write 1.27 GB (HBM), 4 KB of table reads per pair (shared-memory bandwidth), ~70 warp
 // instructions per pair.
 //
-// Distance indices outside the table (>= 16): pairs of row 0 / column 0 -- the background point of SAM-6D sits at (100,100,100),
+// Distance indices outside the table (>= 32): pairs of row 0 / column 0 -- the background point of SAM-6D sits at (100,100,100),
 // ~870 index units from everything -- read g_d from `far` (clouds, 2, S, 256), computed exactly (tensor-core distance pass of
 // geo_tc.cu) from the 2 S distances of that row and column; any other out-of-range pair takes a slow exact path (sin/cos + a
-// 256 x 256 product per pair on CUDA cores), so the kernel is correct for any input and fast for the clouds the model produces.
+// 256 x 256 product per pair on CUDA cores, ~5000 warp instructions against ~100 for a table pair: measured on the bench's
+// synthetic clouds, whose 20 % gaussian outliers put 3 % of the pairs beyond index 16, a [0, 16) table spent most of its 1.5 ms
+// there -- hence the [0, 32) span), so the kernel is correct for any input and fast for the clouds the model produces.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -56,14 +58,18 @@ __device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// linear interpolation of one table row pair: lane's 8 channels of g(x)
-__device__ __forceinline__ uint4 lut_lerp(const uint4* __restrict__ tab, float x, float inv_h, int nent, int lane) {
+// table position of an index value: row offset (in uint4 units, lane-relative) and interpolation weight.  Computed ONCE per pair by
+// the lane that loaded the pair's indices and broadcast by shuffles (per lane and lookup it cost 8 of the ~25 instructions)
+__device__ __forceinline__ void lut_pos(float x, float inv_h, int nent, int& row, float& t) {
   const float u = x * inv_h;
   int i = (int)u;
   i = max(0, min(i, nent - 2));
-  const float t = u - (float)i;
-  const uint32_t t2 = bf2_pack(t, t);
-  const uint4 lo = tab[i * 32 + lane], hi = tab[i * 32 + 32 + lane];
+  t = u - (float)i;
+  row = i * 32;
+}
+// linear interpolation between table rows `row` and `row + 1`: lane's 8 channels of g(x), packed bf16x2 arithmetic (t2 = (t, t))
+__device__ __forceinline__ uint4 lut_lerp(const uint4* __restrict__ tab, int row, uint32_t t2) {
+  const uint4 lo = tab[row], hi = tab[row + 32];
   uint4 r;
   r.x = bf2_fma(t2, bf2_sub(hi.x, lo.x), lo.x);
   r.y = bf2_fma(t2, bf2_sub(hi.y, lo.y), lo.y);
@@ -71,14 +77,9 @@ __device__ __forceinline__ uint4 lut_lerp(const uint4* __restrict__ tab, float x
   r.w = bf2_fma(t2, bf2_sub(hi.w, lo.w), lo.w);
   return r;
 }
-
 // the same interpolation in fp32 (table entries unpacked, no intermediate rounding): 8 channels as floats
-__device__ __forceinline__ void lut_lerp_f32(const uint4* __restrict__ tab, float x, float inv_h, int nent, int lane, float v[8]) {
-  const float u = x * inv_h;
-  int i = (int)u;
-  i = max(0, min(i, nent - 2));
-  const float t = u - (float)i;
-  const uint4 lo = tab[i * 32 + lane], hi = tab[i * 32 + 32 + lane];
+__device__ __forceinline__ void lut_lerp_f32(const uint4* __restrict__ tab, int row, float t, float v[8]) {
+  const uint4 lo = tab[row], hi = tab[row + 32];
   const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w}, h[4] = {hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -144,36 +145,52 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) geo_embed_lut_kernel(const flo
     const int cnt = (int)min(32LL, npairs - base);
     float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (lane < cnt) tv = T[base + lane];
+    // this lane's pair: table rows and weights of its four indices (a distance outside the table is flagged by row -1)
+    int r0, r1, r2, r3;
+    float t0, t1, t2, t3;
+    lut_pos(tv.x, inv_ha, na, r0, t0);
+    lut_pos(tv.y, inv_ha, na, r1, t1);
+    lut_pos(tv.z, inv_ha, na, r2, t2);
+    lut_pos(tv.w, inv_hd, nd, r3, t3);
+    if (!(tv.w < d_limit)) r3 = -1;
+    if constexpr (!PRECISE) {                              // the packed variant broadcasts the weight as a bf16x2 word
+      t0 = __uint_as_float(bf2_pack(t0, t0)); t1 = __uint_as_float(bf2_pack(t1, t1));
+      t2 = __uint_as_float(bf2_pack(t2, t2)); t3 = __uint_as_float(bf2_pack(t3, t3));
+    }
+    const uint4* tabA_l = tabA + lane;
+    const uint4* tabD_l = tabD + lane;
 #pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
-      const float a0 = __shfl_sync(0xffffffffu, tv.x, j), a1 = __shfl_sync(0xffffffffu, tv.y, j);
-      const float a2 = __shfl_sync(0xffffffffu, tv.z, j), xd = __shfl_sync(0xffffffffu, tv.w, j);
+      const int q0 = __shfl_sync(0xffffffffu, r0, j), q1 = __shfl_sync(0xffffffffu, r1, j);
+      const int q2 = __shfl_sync(0xffffffffu, r2, j), q3 = __shfl_sync(0xffffffffu, r3, j);
+      const float w0 = __shfl_sync(0xffffffffu, t0, j), w1 = __shfl_sync(0xffffffffu, t1, j);
+      const float w2 = __shfl_sync(0xffffffffu, t2, j), w3 = __shfl_sync(0xffffffffu, t3, j);
       uint4 dv;
-      const bool in_table = xd < d_limit;                  // warp-uniform: xd is a broadcast value
+      const bool in_table = q3 >= 0;                       // warp-uniform: a broadcast value
       if (!in_table) {
         const long long p = base + j;
         const long long c = p / SS;
         const int rem = (int)(p - c * SS), n = rem / S, m = rem - n * S;
         if (n == 0) dv = far[((c * 2 + 0) * S + m) * 32 + lane];
         else if (m == 0) dv = far[((c * 2 + 1) * S + n) * 32 + lane];
-        else dv = slow_distance(xd, div_term, WdT, bias, lane);
+        else dv = slow_distance(__shfl_sync(0xffffffffu, tv.w, j), div_term, WdT, bias, lane);
       }
       uint4 o;
       if constexpr (PRECISE) {
         float f0[8], f1[8], f2[8], fd[8];
-        lut_lerp_f32(tabA, a0, inv_ha, na, lane, f0);
-        lut_lerp_f32(tabA, a1, inv_ha, na, lane, f1);
-        lut_lerp_f32(tabA, a2, inv_ha, na, lane, f2);
-        if (in_table) lut_lerp_f32(tabD, xd, inv_hd, nd, lane, fd);
+        lut_lerp_f32(tabA_l, q0, w0, f0);
+        lut_lerp_f32(tabA_l, q1, w1, f1);
+        lut_lerp_f32(tabA_l, q2, w2, f2);
+        if (in_table) lut_lerp_f32(tabD_l, q3, w3, fd);
         else unpack8(dv, fd);
 #pragma unroll
         for (int k = 0; k < 8; ++k) fd[k] += fmaxf(fmaxf(f0[k], f1[k]), f2[k]);
         o = make_uint4(bf2_pack(fd[0], fd[1]), bf2_pack(fd[2], fd[3]), bf2_pack(fd[4], fd[5]), bf2_pack(fd[6], fd[7]));
       } else {
-        const uint4 v0 = lut_lerp(tabA, a0, inv_ha, na, lane);
-        const uint4 v1 = lut_lerp(tabA, a1, inv_ha, na, lane);
-        const uint4 v2 = lut_lerp(tabA, a2, inv_ha, na, lane);
-        if (in_table) dv = lut_lerp(tabD, xd, inv_hd, nd, lane);
+        const uint4 v0 = lut_lerp(tabA_l, q0, __float_as_uint(w0));
+        const uint4 v1 = lut_lerp(tabA_l, q1, __float_as_uint(w1));
+        const uint4 v2 = lut_lerp(tabA_l, q2, __float_as_uint(w2));
+        if (in_table) dv = lut_lerp(tabD_l, q3, __float_as_uint(w3));
         o.x = bf2_add(dv.x, bf2_max(bf2_max(v0.x, v1.x), v2.x));
         o.y = bf2_add(dv.y, bf2_max(bf2_max(v0.y, v1.y), v2.y));
         o.z = bf2_add(dv.z, bf2_max(bf2_max(v0.z, v1.z), v2.z));

@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) tail_tc_kernel(const _
     tc::mbar_init(&in_full, 1);
     for (int s = 0; s < W_STAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], 1); }
     for (int i = 0; i < 5; ++i) tc::mbar_init(&acc_full[i], 1);
-    tc::mbar_init(&y_ready, EPI_WARPS * 32); tc::mbar_init(&h0_ready, EPI_WARPS * 32); tc::mbar_init(&h1_ready, EPI_WARPS * 32);
+    tc::mbar_init(&y_ready, EPI_WARPS); tc::mbar_init(&h0_ready, EPI_WARPS); tc::mbar_init(&h1_ready, EPI_WARPS);   // one arrival per warp
     tc::mbar_init(&tile_done, 1);
     tc::mbar_fence_init();
     tc::tma_prefetch_desc(&tmHid); tc::tma_prefetch_desc(&tmX); tc::tma_prefetch_desc(&tmWo);
@@ -270,14 +270,16 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) tail_tc_kernel(const _
       layernorm_epilogue(0u, a.bo, x_buf, a.g1, a.b1, a_buf);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&y_ready);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&y_ready);          // per warp: 512 arrivals on one barrier word serialise
       // E2a: h[:, 0:256] = relu(acc B + b_e[0:256]) -> x_buf (the x tile is dead: every thread passed y_ready before G2a ran)
       tc::mbar_wait_suspend(&acc_full[1], ph);
       tc::tc_fence_after_sync();
       relu_epilogue(256u, a.be);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&h0_ready);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&h0_ready);          // per warp: 512 arrivals on one barrier word serialise
       // E2b: h[:, 256:512] = relu(acc A + b_e[256:512]) -> x_buf once G3's first half has consumed h[:, 0:256]
       tc::mbar_wait_suspend(&acc_full[2], ph);
       tc::mbar_wait_suspend(&acc_full[4], ph);
@@ -285,7 +287,8 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) tail_tc_kernel(const _
       relu_epilogue(0u, a.be + 256);
       tc::tc_fence_before_sync();
       tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&h1_ready);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&h1_ready);          // per warp: 512 arrivals on one barrier word serialise
       // E3: out = LN2(acc B + b_s + y) -> staged in x_buf (G3 has completed) -> TMA store
       tc::mbar_wait_suspend(&acc_full[3], ph);
       tc::tc_fence_after_sync();

@@ -38,7 +38,8 @@ RPE_TC = os.environ.get("SAM6D_RPE_TC", "1") != "0"
 GEO_LUT = os.environ.get("SAM6D_GEO_LUT", "1") != "0"
 GEO_LUT_PRECISE = os.environ.get("SAM6D_GEO_LUT_PRECISE", "1") != "0"   # fp32 interpolation, one rounding at the store
 GEO_LUT_INV_H = 8.0            # table step 1/8 index unit
-GEO_LUT_D_MAX = 16.0           # distance indices below this come from the table (normalised clouds stay below 12)
+GEO_LUT_D_MAX = 32.0           # distance indices below this come from the table: 6.4 object radii (the reference's input builder
+                               # keeps scene points within 1.2 radii of the mask centroid: indices <= 12)
 
 
 class _W:

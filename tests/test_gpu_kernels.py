@@ -625,7 +625,7 @@ def test_geo_embed_lut(ops, S, far_point, precise, monkeypatch):
     far_rows = [0, 5] if far_point else [0]
     for r in far_rows:
         others = [m for m in range(S) if m != r]
-        assert (T[:, r, others, 3] > 16).all()
+        assert (T[:, r, others, 3] > 32).all()
         assert (E[:, r] - ref[:, r]).abs().median().item() < 4e-3 and (E[:, :, r] - ref[:, :, r]).abs().median().item() < 4e-3
     # the distance-only tensor-core projection that feeds `far`
     far = ops.geo_embed_dist_tc(T[:, 0].contiguous(), w["div"], w["wd_bf"], w["bias"]).float().cpu()

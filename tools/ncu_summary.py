@@ -1,10 +1,14 @@
-"""key metrics of every kernel in an .ncu-rep as a markdown table: python tools/ncu_summary.py report.ncu-rep"""
+"""key metrics of every kernel in an .ncu-rep (or in the CSV of `ncu -i report.ncu-rep --page raw --csv`, which is what travels
+back from the GPU box: reports exceed the 64 MiB gpurun_out cap) as a markdown table: python tools/ncu_summary.py report.ncu-rep|raw.csv"""
 import csv
 import subprocess
 import sys
 
-raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+if sys.argv[1].endswith(".csv"):
+    raw = open(sys.argv[1]).read()
+else:
+    raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = [r for r in csv.reader(raw.splitlines()) if len(r) > 20]
 hdr = rows[0]
 col = {h: i for i, h in enumerate(hdr)}
 M = [("time us", "gpu__time_duration.sum", 1), ("warp inst M", "smsp__inst_executed.sum", 1e-6),
