@@ -27,11 +27,12 @@
 // there -- hence the [0, 32) span), so the kernel is correct for any input and fast for the clouds the model produces.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int LUT_THREADS = 1024;
 
 __device__ __forceinline__ uint32_t bf2_sub(uint32_t a, uint32_t b) {
   uint32_t d;
@@ -123,7 +124,9 @@ __device__ __noinline__ uint4 slow_distance(float x, const float* __restrict__ d
 
 // PRECISE: interpolation, maximum and sum in fp32, ONE rounding to bf16 at the store (rms error 1.2e-3 against 1.6e-3 for the packed
 // bf16x2 arithmetic, at about twice the instructions per pair)
-template <bool PRECISE>
+// LUT_THREADS / UNROLL: warps per CTA against pairs in flight per warp (the kernel is bound by the shared-memory pipe: ncu shows it
+// 60-68 % busy with 32 warps and one pair per iteration, warps waiting on their LDS results)
+template <bool PRECISE, int LUT_THREADS, int UNROLL>
 __global__ void __launch_bounds__(LUT_THREADS, 1) geo_embed_lut_kernel(const float4* __restrict__ T, long long npairs, int S,
                                                                       const uint4* __restrict__ tabA_g, int na, float inv_ha,
                                                                       const uint4* __restrict__ tabD_g, int nd, float inv_hd,
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(LUT_THREADS, 1) geo_embed_lut_kernel(const flo
     }
     const uint4* tabA_l = tabA + lane;
     const uint4* tabD_l = tabD + lane;
-#pragma unroll 1
+#pragma unroll UNROLL
     for (int j = 0; j < cnt; ++j) {
       const int q0 = __shfl_sync(0xffffffffu, r0, j), q1 = __shfl_sync(0xffffffffu, r1, j);
       const int q2 = __shfl_sync(0xffffffffu, r2, j), q3 = __shfl_sync(0xffffffffu, r3, j);
@@ -221,14 +224,30 @@ S6_API int sam6d_geo_embed_lut(const float* T, long long clouds, int S, const vo
   S6_CHECK(cudaGetDevice(&dev));
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int smem = (na + nd) * 512;
-  auto kern = precise ? geo_embed_lut_kernel<true> : geo_embed_lut_kernel<false>;
-  S6_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  // launch shape: 0 = 32 warps, one pair per iteration (default); 1 = 16 warps x 2 pairs; 2 = 24 warps x 2 pairs (SAM6D_GEO_LUT_CFG)
+  static const int cfg = [] { const char* e = getenv("SAM6D_GEO_LUT_CFG"); return e ? atoi(e) : 0; }();
   const long long nblocks = (npairs + 31) / 32;
-  const long long want = (nblocks + LUT_THREADS / 32 - 1) / (LUT_THREADS / 32);
-  const int grid = (int)(want < sms ? want : sms);
-  kern<<<grid, LUT_THREADS, smem, s6_stream(stream)>>>(
-      reinterpret_cast<const float4*>(T), npairs, S, reinterpret_cast<const uint4*>(tabA), na, inv_ha, reinterpret_cast<const uint4*>(tabD), nd,
-      inv_hd, reinterpret_cast<const uint4*>(far), div_term, reinterpret_cast<const uint4*>(WdT_bf16), bias, reinterpret_cast<uint4*>(E));
+  cudaStream_t st = s6_stream(stream);
+#define S6_LUT_LAUNCH(P, TH, UN)                                                                                                    \
+  do {                                                                                                                               \
+    auto kern = geo_embed_lut_kernel<P, TH, UN>;                                                                                     \
+    S6_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                                         \
+    const long long want = (nblocks + TH / 32 - 1) / (TH / 32);                                                                     \
+    const int grid = (int)(want < sms ? want : sms);                                                                                 \
+    kern<<<grid, TH, smem, st>>>(reinterpret_cast<const float4*>(T), npairs, S, reinterpret_cast<const uint4*>(tabA), na, inv_ha,     \
+                                 reinterpret_cast<const uint4*>(tabD), nd, inv_hd, reinterpret_cast<const uint4*>(far), div_term,  \
+                                 reinterpret_cast<const uint4*>(WdT_bf16), bias, reinterpret_cast<uint4*>(E));                       \
+  } while (0)
+  if (precise) {
+    if (cfg == 1) S6_LUT_LAUNCH(true, 512, 2);
+    else if (cfg == 2) S6_LUT_LAUNCH(true, 768, 2);
+    else S6_LUT_LAUNCH(true, 1024, 1);
+  } else {
+    if (cfg == 1) S6_LUT_LAUNCH(false, 512, 2);
+    else if (cfg == 2) S6_LUT_LAUNCH(false, 768, 2);
+    else S6_LUT_LAUNCH(false, 1024, 1);
+  }
+#undef S6_LUT_LAUNCH
   S6_LAUNCH_CHECK();
   return 0;
 }

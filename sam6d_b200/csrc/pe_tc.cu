@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
     *reinterpret_cast<uint4*>(w3s + tc::sw128_offset(n, c)) = *reinterpret_cast<const uint4*>(W3 + n * 64 + c);
   }
   if (tid == 0) {
-    tc::mbar_init(&a1_full, 128); tc::mbar_init(&a2_full, 128);
+    tc::mbar_init(&a1_full, 4); tc::mbar_init(&a2_full, 4);   // one arrival per worker warp (128 arrivals on one word serialise)
     tc::mbar_init(&d2_full, 1); tc::mbar_init(&d3_full, 1);
     tc::mbar_fence_init();
   }
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
           *reinterpret_cast<uint4*>(row_ptr + ((c ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&a1_full);
+        __syncwarp();
+        if ((tid & 31) == 0) tc::mbar_arrive(&a1_full);
       }
       // ---- layer 2 epilogue -> A2
       tc::mbar_wait_suspend(&d2_full, ph);
@@ -182,7 +183,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 4) pe_tc_kernel(const float* __re
         }
         tc::tc_fence_before_sync();          // our TMEM reads are done before the issuer overwrites the columns
         tc::fence_proxy_async_smem();
-        tc::mbar_arrive(&a2_full);
+        __syncwarp();
+        if ((tid & 31) == 0) tc::mbar_arrive(&a2_full);
       }
       load_x(tile + gridDim.x, jn, xn);
       jn = load_idx(tile + 2LL * gridDim.x);
