@@ -12,7 +12,7 @@
 // the table and of E itself; measured against the float64 embedding the result is closer than the bf16-operand tensor-core
 // product was (rms 1.6e-3 vs 1.8e-3 at |E| ~ 0.56, tools/geo_lut_error.py).
 //
-// Kernel: persistent, 32 warps per CTA, both tables resident in shared memory.  A warp takes 32 consecutive pairs: lane l loads
+// Kernel: persistent, 16 warps per CTA (two pairs in flight per warp), both tables resident in shared memory.  A warp takes 32 consecutive pairs: lane l loads
 // the indices of pair l (one coalesced 512-byte read), then for each pair the four indices are broadcast by shuffles and lane l
 // interpolates channels [8l, 8l+8) as four packed bf16x2 words per table row (sub / fma / max / add on bf16x2: the same packed
 // arithmetic the tensor-core epilogue used), one 16-byte store per lane = one 512-byte row of E per warp instruction.
@@ -224,8 +224,9 @@ S6_API int sam6d_geo_embed_lut(const float* T, long long clouds, int S, const vo
   S6_CHECK(cudaGetDevice(&dev));
   S6_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int smem = (na + nd) * 512;
-  // launch shape: 0 = 32 warps, one pair per iteration (default); 1 = 16 warps x 2 pairs; 2 = 24 warps x 2 pairs (SAM6D_GEO_LUT_CFG)
-  static const int cfg = [] { const char* e = getenv("SAM6D_GEO_LUT_CFG"); return e ? atoi(e) : 0; }();
+  // launch shape (SAM6D_GEO_LUT_CFG): 1 = 16 warps x 2 pairs in flight per warp (default: 0.615 ms per 64 clouds); 0 = 32 warps x 1
+  // pair (0.666 ms); 2 = 24 warps x 2 pairs (0.671 ms) -- profiles/r02_bench_bf16_v8.json and its cfg lines
+  static const int cfg = [] { const char* e = getenv("SAM6D_GEO_LUT_CFG"); return e ? atoi(e) : 1; }();
   const long long nblocks = (npairs + 31) / 32;
   cudaStream_t st = s6_stream(stream);
 #define S6_LUT_LAUNCH(P, TH, UN)                                                                                                    \
@@ -239,13 +240,13 @@ S6_API int sam6d_geo_embed_lut(const float* T, long long clouds, int S, const vo
                                  reinterpret_cast<const uint4*>(WdT_bf16), bias, reinterpret_cast<uint4*>(E));                       \
   } while (0)
   if (precise) {
-    if (cfg == 1) S6_LUT_LAUNCH(true, 512, 2);
+    if (cfg == 0) S6_LUT_LAUNCH(true, 1024, 1);
     else if (cfg == 2) S6_LUT_LAUNCH(true, 768, 2);
-    else S6_LUT_LAUNCH(true, 1024, 1);
+    else S6_LUT_LAUNCH(true, 512, 2);
   } else {
-    if (cfg == 1) S6_LUT_LAUNCH(false, 512, 2);
+    if (cfg == 0) S6_LUT_LAUNCH(false, 1024, 1);
     else if (cfg == 2) S6_LUT_LAUNCH(false, 768, 2);
-    else S6_LUT_LAUNCH(false, 1024, 1);
+    else S6_LUT_LAUNCH(false, 512, 2);
   }
 #undef S6_LUT_LAUNCH
   S6_LAUNCH_CHECK();
