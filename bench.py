@@ -144,6 +144,7 @@ def same_box_reference(dev, B):
         ref = pn2._ref()
         x = po.make_inputs(B=B, n=N_PTS, n_model=N_MODEL, seed=1)["dense_po"].to(dev)
         x2 = torch.cat([x, x.flip(1)], dim=0).contiguous()                      # 2B clouds, the launch shape of the step
+        x2 = (x2 / (x2.norm(dim=2).amax(dim=1).reshape(-1, 1, 1) + 1e-6)).contiguous()   # unit radius, as Net.forward feeds them
 
         def t_us(fn, reps=5):
             fn(); torch.cuda.synchronize()

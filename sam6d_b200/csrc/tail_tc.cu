@@ -103,6 +103,16 @@ __global__ void __launch_bounds__(64 + EPI_WARPS * 32, 1) tail_tc_kernel(const _
     tc::tma_prefetch_desc(&tmWe); tc::tma_prefetch_desc(&tmWs); tc::tma_prefetch_desc(&tmOut);
   }
   s6_pdl_trigger();
+  if (warp >= 2) {
+    // the 2048 bias / LayerNorm parameters (8 KB) are read with __ldg inside the four epilogue phases, i.e. on the tile's serial
+    // GEMM -> epilogue chain: a first touch costs an L2 round trip per 32-column chunk (ncu: the epilogue warps' top stall is the
+    // long scoreboard).  They do not depend on the previous kernel, so they are pulled into L1 here, in front of the dependency wait
+    for (int i = tid - 64; i < 512; i += EPI_WARPS * 32) {
+      const float* p = i < 64 ? a.bo + i * 4 : i < 128 ? a.g1 + (i - 64) * 4 : i < 192 ? a.b1 + (i - 128) * 4 : i < 320 ? a.be + (i - 192) * 4
+                     : i < 384 ? a.bs + (i - 320) * 4 : i < 448 ? a.g2 + (i - 384) * 4 : a.b2 + (i - 448) * 4;
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    }
+  }
   if (warp == 1) tc::tmem_alloc(&tmem_slot, 512);
   tc::tc_fence_before_sync();
   __syncthreads();
