@@ -53,6 +53,9 @@ class _W:
 
 def _gemm(prec, A, W: "_W", bias=None, residual=None, relu=False):
     if prec == "bf16":
+        if A.dtype == torch.bfloat16 and residual is None and A.is_contiguous() and A.shape[1] % 64 == 0:
+            # bf16 token matrix: the persistent TMA kernel (fp32 output); the register-staged kernel below is for fp32 operands
+            return ops.gemm_tma(A, W.bf16, bias, act=1 if relu else 0)
         return ops.gemm_tc(A, W.bf16, bias, residual=residual, relu=relu)
     return ops.gemm(A, W.f32, bias, residual=residual, relu=relu)
 
@@ -406,7 +409,8 @@ def sample_pts_feats(pts, feats, npoint=2048, return_index=False):
     """model_utils.py:53-66 (FPS + two gathers, channel-last)."""
     idx = ops.furthest_point_sampling(pts.contiguous(), npoint)
     p = ops.gather_rows(pts.contiguous(), idx)
-    f = ops.gather_rows(feats.contiguous(), idx)
+    # a bf16 feature matrix (Net.forward's stacked bf16 copy) comes back as fp32 rows -- exact, and what the coarse in_proj reads
+    f = ops.gather_rows_bf16_f32(feats.contiguous(), idx) if feats.dtype == torch.bfloat16 else ops.gather_rows(feats.contiguous(), idx)
     return (p, f, idx) if return_index else (p, f)
 
 
@@ -527,8 +531,13 @@ class CoarsePointMatching(nn.Module):
             f1, f2 = blk(f1, geo1, f2, geo2)
         B, S, H = f1.shape
         w = self._weights()
-        o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
-        o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+        f12 = _stack2(f1, f2)
+        if f12 is not None:                                     # both clouds: one out_proj launch
+            o = _gemm(self.precision, f12.reshape(2 * B * S, H), w["w_out"], w["b_out"]).view(2 * B, S, -1)
+            o1, o2 = o[:B], o[B:]
+        else:
+            o1 = _gemm(self.precision, f1.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
+            o2 = _gemm(self.precision, f2.reshape(B * S, H), w["w_out"], w["b_out"]).view(B, S, -1)
         atten = compute_feature_similarity(o1, o2, self.cfg.sim_type, self.cfg.temp, self.cfg.normalize_feat, self.precision)
         model = ops.scale_by_radius(end_points['model'].contiguous(), radius.contiguous())
         init_R, init_t, self.last_select_scores = compute_coarse_Rt(atten, p1, p2, model, self.cfg.nproposal1,
@@ -818,7 +827,11 @@ class FinePointMatching(nn.Module):
         if self.precision == "bf16":
             # the dense token stream of the fine stage is bf16 from here on (fp32 accumulation inside every kernel):
             # in_proj(f) in bf16 is the residual of the mlp3 GEMM over the bf16 local features, written behind the bg row
-            tmp = ops.gemm_tc(f.reshape(B * N, C), w["w_in"].bf16, w["b_in"], out_dtype=torch.bfloat16)
+            f2d = f.reshape(B * N, C)
+            if f2d.dtype == torch.bfloat16 and f2d.is_contiguous():
+                tmp = ops.gemm_tma(f2d, w["w_in"].bf16, w["b_in"], out_dtype=torch.bfloat16)
+            else:
+                tmp = ops.gemm_tc(f2d, w["w_in"].bf16, w["b_in"], out_dtype=torch.bfloat16)
             out = torch.empty(B, N + 1, H, dtype=torch.bfloat16, device=f.device)
             out[:, 0, :] = self.bg_token.detach().reshape(1, -1).to(torch.bfloat16)
             ops.gemm_tma_batched(local, pw["w3"].bf16, out[:, 1:, :], N, H, H, (N + 1) * H, bias=pw["b3"],
@@ -980,7 +993,14 @@ class Net(nn.Module):
             # one (2B, ...) allocation: FPS, the geometric embedding, PE, the self-attention and dense layers each run once
             # on 2B clouds; the views below keep the reference's two-argument interfaces.
             pts2 = torch.cat([dense_pm, dense_po], dim=0)
-            fts2 = torch.cat([dense_fm, dense_fo], dim=0)
+            if self.precision == "bf16":
+                # every consumer of the point features rounds them to bf16 operands (in_proj of both stages): round once while
+                # stacking -- 134 MB read + 67 MB written instead of a 268 MB fp32 copy, and the fine in_proj reads 67 MB by TMA
+                fts2 = torch.empty(2 * B, *dense_fm.shape[1:], dtype=torch.bfloat16, device=dense_fm.device)
+                fts2[:B].copy_(dense_fm)
+                fts2[B:].copy_(dense_fo)
+            else:
+                fts2 = torch.cat([dense_fm, dense_fo], dim=0)
             dense_pm, dense_po, dense_fm, dense_fo = pts2[:B], pts2[B:], fts2[:B], fts2[B:]
             sp, sf, idx = sample_pts_feats(pts2, fts2, self.coarse_npoint, return_index=True)
             bg_point = torch.ones(2 * B, 1, 3, dtype=torch.float32, device=pts2.device) * 100
