@@ -254,8 +254,9 @@ class CustomDINOv2(nn.Module):
             n = f["x_norm_clstoken"].shape[0]
             cls[i:i + n] = f["x_norm_clstoken"]
             pt = f["x_norm_patchtokens"]                                     # view of (n, S, C): row stride C, batch stride S*C
+            mk = masks[i:i + n].contiguous()                                 # named: must outlive the launch
             _lib.call("sam6d_masked_patch_normalize", _p(pt), ctypes.c_longlong(pt.stride(1)), ctypes.c_longlong(pt.stride(0)),
-                      _p(masks[i:i + n].contiguous()), n, G, self.patch_size, C, ctypes.c_float(self.validpatch_thresh), _p(pf[i:i + n]),
+                      _p(mk), n, G, self.patch_size, C, ctypes.c_float(self.validpatch_thresh), _p(pf[i:i + n]),
                       _p(pb[i:i + n]) if want_bf16 else None, _p(valid[i:i + n]), _s())
         self.last_patch_bf16, self.last_valid = pb, valid
         return cls, pf

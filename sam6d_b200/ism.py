@@ -113,8 +113,9 @@ def project_template_iou(poses, pointcloud, best_pose, pred_object_idx, translat
     xyxy = torch.empty(N, 4, dtype=torch.int32, device=dev)
     iou = torch.empty(N, dtype=torch.float32, device=dev)
     ok = torch.empty(N, dtype=torch.uint8, device=dev)
+    tr = translate.to(torch.float32).contiguous()      # a named tensor: a temporary inside the argument list would be freed before the launch
     _lib.call("sam6d_project_template_iou", _p(poses), poses.shape[0], _p(pc), pc.shape[0], npc, _p(bp), _p(po),
-              _p(translate.to(torch.float32).contiguous()), _p(K), N, H, W, _p(bx), _p(vu), _p(xyxy), _p(iou), _p(ok), _s())
+              _p(tr), _p(K), N, H, W, _p(bx), _p(vu), _p(xyxy), _p(iou), _p(ok), _s())
     out = dict(xyxy=xyxy, iou=iou, ok=ok.bool())
     if want_image_vu:
         out["image_vu"] = vu

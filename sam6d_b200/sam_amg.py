@@ -55,8 +55,9 @@ class _PositionEmbeddingRandom(nn.Module):
 def _pe_encode(coords01: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     """coords (rows,2) in [0,1] -> (rows,256)"""
     c = coords01.float().contiguous()
+    g = G.float().contiguous()                           # named: must outlive the launch
     out = torch.empty(c.shape[0], 256, dtype=torch.float32, device=c.device)
-    _lib.call("sam6d_sam_pe_encode", _p(c), _p(G.float().contiguous()), c.shape[0], _p(out), _s())
+    _lib.call("sam6d_sam_pe_encode", _p(c), _p(g), c.shape[0], _p(out), _s())
     return out
 
 
