@@ -538,9 +538,8 @@ def main():
         return ms, launches, kernel_ms
 
     n_warm = max(args.warmup, 3)
-    if graphs:
-        n_warm = max(n_warm, 4)                                # two input sets: sighting, capture (+ first replay) of each
-    for i in range(n_warm):
+    n_warm_run = max(n_warm, 4) if graphs else n_warm          # two input sets: sighting, capture (+ first replay) of each
+    for i in range(n_warm_run):
         step_resident(i)
     if os.environ.get("SAM6D_PROFILE_ONE_STEP"):
         # ncu --profile-from-start off: capture exactly one warmed-up step
@@ -633,7 +632,7 @@ def main():
             if traffic is not None and rec.get("clouds_per_launch", B) != clouds:      # ncu capture of another launch shape
                 traffic = None
         line = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm,
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=n_warm, warmup_run=n_warm_run,
             ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
             config=dict(workload=WORKLOAD + ("+vitb_rgb_branch" if args.rgb else ""), proposals_per_gpu=B, scene_points=N_PTS, template_points=N_PTS, sparse_points=net.coarse_npoint,
